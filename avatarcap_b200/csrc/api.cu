@@ -1,0 +1,274 @@
+// C-ABI entry points: context, weights, feature maps, field-evaluation dispatch, host-buffer (end-to-end) variants.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+static std::string g_create_error;
+
+int avc_fail(avc_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+int avc_check_cuda(avc_ctx* ctx, cudaError_t e, const char* what) {
+  return avc_fail(ctx, AVC_ECUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+}
+
+int avc_ensure_scratch(avc_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_cap) return AVC_OK;
+  if (ctx->d_scratch) { cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_cap = 0; }
+  const size_t cap = bytes + (bytes >> 3) + 4096;
+  AVC_CUDA(ctx, cudaMalloc(&ctx->d_scratch, cap));
+  ctx->scratch_cap = cap;
+  return AVC_OK;
+}
+
+extern "C" int avc_abi_version(void) { return 2; }
+
+extern "C" int avc_ctx_create(int device, avc_ctx** out) {
+  if (!out) return avc_fail(nullptr, AVC_EINVAL, "avc_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return avc_fail(nullptr, AVC_ECUDA, "avc_ctx_create: no CUDA device available (%s)", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return avc_fail(nullptr, AVC_EINVAL, "avc_ctx_create: device %d out of range (0..%d)", device, count - 1);
+  avc_ctx* ctx = new avc_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete ctx;
+    return avc_fail(nullptr, AVC_ECUDA, "avc_ctx_create: %s", cudaGetErrorString(e));
+  }
+  ctx->sm_count = prop.multiProcessorCount; ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+  if ((e = cudaMallocHost(&ctx->h_counts, 8 * sizeof(int64_t))) != cudaSuccess) {
+    delete ctx;
+    return avc_fail(nullptr, AVC_ECUDA, "avc_ctx_create: cudaMallocHost: %s", cudaGetErrorString(e));
+  }
+  cudaStreamCreateWithFlags(&ctx->s_copy_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_copy_out, cudaStreamNonBlocking);
+  *out = ctx;
+  return AVC_OK;
+}
+
+static void free_weights(AvcWeights& w) {
+  if (w.d_blob) cudaFree(w.d_blob);
+  w = AvcWeights();
+}
+
+extern "C" void avc_ctx_destroy(avc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  free_weights(ctx->avatar); free_weights(ctx->recon);
+  for (int i = 0; i < 2; ++i) if (ctx->maps[i].d_hwc) cudaFree(ctx->maps[i].d_hwc);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->s_copy_in) cudaStreamDestroy(ctx->s_copy_in);
+  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->s_copy_out) cudaStreamDestroy(ctx->s_copy_out);
+  delete ctx;
+}
+
+extern "C" const char* avc_last_error(const avc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" int avc_has_tensor_core_path(const avc_ctx* ctx) { return ctx ? avc_tc_available(ctx) : 0; }
+extern "C" int64_t avc_launch_count(const avc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void avc_reset_launch_count(avc_ctx* ctx) { if (ctx) ctx->launches = 0; }
+
+// -----------------------------------------------------------------------------------------------------------------
+static int load_weights(avc_ctx* ctx, AvcWeights& w, const void* blob, size_t nbytes, uint32_t kind, uint32_t n_layers) {
+  if (!ctx || !blob) return avc_fail(ctx, AVC_EINVAL, "load weights: NULL argument");
+  if (nbytes < sizeof(AvcBlobHeader)) return avc_fail(ctx, AVC_EFORMAT, "weight blob too small (%zu bytes)", nbytes);
+  AvcBlobHeader h; memcpy(&h, blob, sizeof(h));
+  if (h.magic != AVC_MAGIC) return avc_fail(ctx, AVC_EFORMAT, "weight blob: bad magic 0x%08x", h.magic);
+  if (h.version != AVC_BLOB_VERSION) return avc_fail(ctx, AVC_EFORMAT, "weight blob: version %u, library expects %u", h.version, AVC_BLOB_VERSION);
+  if (h.kind != kind || h.n_layers != n_layers) return avc_fail(ctx, AVC_EFORMAT, "weight blob: kind %u with %u layers, expected kind %u with %u", h.kind, h.n_layers, kind, n_layers);
+  if (h.f32_off + h.f32_bytes > nbytes || h.f16_off + h.f16_bytes > nbytes || (h.f32_off & 15) || (h.f16_off & 127))
+    return avc_fail(ctx, AVC_EFORMAT, "weight blob: section out of range or misaligned");
+  for (uint32_t l = 0; l < n_layers; ++l) {
+    const AvcLayerDesc& L = h.layers[l];
+    const int64_t ktot = (int64_t)L.k0 + L.k1;
+    if (L.k0 <= 0 || L.k1 < 0 || L.n <= 0 || L.wt_off < 0 || L.sb_off < 0 ||
+        ((int64_t)L.wt_off + ktot * L.n) * 4 > (int64_t)h.f32_bytes || ((int64_t)L.sb_off + 2 * L.n) * 4 > (int64_t)h.f32_bytes)
+      return avc_fail(ctx, AVC_EFORMAT, "weight blob: layer %u descriptor out of range", l);
+  }
+  AVC_CUDA(ctx, cudaSetDevice(ctx->device));
+  free_weights(w);
+  AVC_CUDA(ctx, cudaMalloc(&w.d_blob, nbytes));
+  AVC_CUDA(ctx, cudaMemcpy(w.d_blob, blob, nbytes, cudaMemcpyHostToDevice));
+  w.hdr = h; w.d_f32 = reinterpret_cast<const float*>(w.d_blob + h.f32_off); w.d_f16 = w.d_blob + h.f16_off; w.loaded = true;
+  return AVC_OK;
+}
+
+extern "C" int avc_load_avatar_weights(avc_ctx* ctx, const void* blob, size_t nbytes) {
+  return load_weights(ctx, ctx->avatar, blob, nbytes, AVC_KIND_AVATAR, 20);
+}
+extern "C" int avc_load_recon_weights(avc_ctx* ctx, const void* blob, size_t nbytes) {
+  return load_weights(ctx, ctx->recon, blob, nbytes, AVC_KIND_RECON, 4);
+}
+
+// (C,H,W) -> (H,W,C): one bilinear tap becomes one contiguous C*4-byte read
+__global__ void chw_to_hwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? in[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < HW && c < C) out[(size_t)p * C + c] = tile[threadIdx.x][r];
+  }
+}
+
+extern "C" int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw, int C, int H, int W, void* stream) {
+  if (!ctx || !chw) return avc_fail(ctx, AVC_EINVAL, "avc_set_feature_map: NULL argument");
+  if (which != AVC_MAP_POSE && which != AVC_MAP_IMAGE) return avc_fail(ctx, AVC_EINVAL, "avc_set_feature_map: bad slot %d", which);
+  const int want = which == AVC_MAP_POSE ? 64 : 32;
+  if (C != want || H < 1 || W < 1) return avc_fail(ctx, AVC_EINVAL, "avc_set_feature_map: slot %d needs C=%d (got %d), H,W >= 1", which, want, C);
+  AvcMap& m = ctx->maps[which];
+  const size_t need = (size_t)C * H * W * sizeof(float);
+  if (need > m.cap) {
+    if (m.d_hwc) cudaFree(m.d_hwc);
+    m.d_hwc = nullptr; m.cap = 0;
+    AVC_CUDA(ctx, cudaMalloc(&m.d_hwc, need));
+    m.cap = need;
+  }
+  m.C = C; m.H = H; m.W = W;
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32), block(32, 8);
+  chw_to_hwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(chw, m.d_hwc, C, H * W);
+  AVC_LAUNCH_CHECK(ctx, "chw_to_hwc_kernel");
+  return AVC_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+static int pick_impl(avc_ctx* ctx, int impl, bool* use_tc) {
+  if (impl == AVC_IMPL_SIMT) { *use_tc = false; return AVC_OK; }
+  if (impl == AVC_IMPL_TC) {
+    if (!avc_tc_available(ctx)) return avc_fail(ctx, AVC_ESTATE, "tensor-core path requested but not available (needs sm_100 and a library built with tcgen05)");
+    *use_tc = true; return AVC_OK;
+  }
+  if (impl == AVC_IMPL_AUTO) { *use_tc = avc_tc_available(ctx) != 0; return AVC_OK; }
+  return avc_fail(ctx, AVC_EINVAL, "bad impl %d", impl);
+}
+
+static int eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* occ, float* off, float* rgb, float* alpha,
+                       int if_type, int impl, int mode, cudaStream_t st) {
+  if (!ctx) return AVC_EINVAL;
+  if (n < 0 || (n > 0 && !pts)) return avc_fail(ctx, AVC_EINVAL, "field eval: bad points");
+  if (if_type != AVC_IF_SDF && if_type != AVC_IF_OCCUPANCY) return avc_fail(ctx, AVC_EVALUE, "Invalid config.if_type!");   // arch_avatar.py:82
+  if (!ctx->avatar.loaded) return avc_fail(ctx, AVC_ESTATE, "avatar weights not loaded");
+  if (mode != AVC_MODE_TEMPLATE_ONLY && (!ctx->maps[AVC_MAP_POSE].d_hwc || !center))
+    return avc_fail(ctx, AVC_ESTATE, "pose feature map not set (call avc_set_feature_map after WarpingField.precompute_conv)");
+  bool use_tc; int rc = pick_impl(ctx, impl, &use_tc);
+  if (rc) return rc;
+  const float zero[3] = {0, 0, 0};
+  const float* c = center ? center : zero;
+  return use_tc ? avc_tc_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st)
+                : avc_simt_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st);
+}
+
+extern "C" int avc_eval_occupancy(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
+                                  float* out_rgb, float* out_alpha, int if_type, int impl, void* stream) {
+  if (ctx && n > 0 && !out_occ) return avc_fail(ctx, AVC_EINVAL, "avc_eval_occupancy: out_occ is NULL");
+  return eval_avatar(ctx, pts, n, center, out_occ, out_off, out_rgb, out_alpha, if_type, impl, AVC_MODE_QUERY, (cudaStream_t)stream);
+}
+
+extern "C" int avc_eval_warp(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_off, int impl, void* stream) {
+  if (ctx && n > 0 && !out_off) return avc_fail(ctx, AVC_EINVAL, "avc_eval_warp: out_off is NULL");
+  return eval_avatar(ctx, pts, n, center, nullptr, out_off, nullptr, nullptr, AVC_IF_SDF, impl, AVC_MODE_WARP_ONLY, (cudaStream_t)stream);
+}
+
+extern "C" int avc_eval_template(avc_ctx* ctx, const float* pts, int64_t n, float* out_rgb, float* out_alpha, float* out_occ, int if_type,
+                                 int impl, void* stream) {
+  return eval_avatar(ctx, pts, n, nullptr, out_occ, nullptr, out_rgb, out_alpha, if_type, impl, AVC_MODE_TEMPLATE_ONLY, (cudaStream_t)stream);
+}
+
+extern "C" int avc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, int impl, void* stream) {
+  if (!ctx) return AVC_EINVAL;
+  if (n < 0 || (n > 0 && (!pts || !out_ov)) || !center) return avc_fail(ctx, AVC_EINVAL, "avc_eval_recon: bad argument");
+  if (!ctx->recon.loaded) return avc_fail(ctx, AVC_ESTATE, "recon weights not loaded");
+  if (!ctx->maps[AVC_MAP_IMAGE].d_hwc) return avc_fail(ctx, AVC_ESTATE, "image feature map not set");
+  bool use_tc; int rc = pick_impl(ctx, impl, &use_tc);
+  if (rc) return rc;
+  return use_tc ? avc_tc_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream)
+                : avc_simt_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream);
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Host-buffer variants: chunked, double-buffered  H2D -> kernel -> D2H  on three internal streams.
+// Staging layout per slot: pts (chunk,3) | occ (chunk) | off (chunk,3)  in pinned host memory and in device memory.
+static int ensure_staging(avc_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap && bytes <= ctx->stage_cap) return AVC_OK;
+  if (ctx->h_pinned) { cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->pinned_cap = 0; }
+  if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->stage_cap = 0; }
+  AVC_CUDA(ctx, cudaMallocHost(&ctx->h_pinned, bytes)); ctx->pinned_cap = bytes;
+  AVC_CUDA(ctx, cudaMalloc(&ctx->d_stage, bytes)); ctx->stage_cap = bytes;
+  return AVC_OK;
+}
+
+static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, const float center[3], float* out_a, float* out_off, int if_type,
+                     int impl) {
+  if (!ctx) return AVC_EINVAL;
+  if (n < 0 || (n > 0 && (!pts || !out_a)) || !center) return avc_fail(ctx, AVC_EINVAL, "host eval: bad argument");
+  if (n == 0) return AVC_OK;
+  AVC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t chunk = 1 << 21;                       // 2 Mi points per pipeline slot (24 MB in, 8..32 MB out)
+  const size_t slot_floats = (size_t)chunk * 7;
+  int rc = ensure_staging(ctx, 2 * slot_floats * sizeof(float));
+  if (rc) return rc;
+  cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+  for (int s = 0; s < 2; ++s) { cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming); }
+  const int64_t n_chunks = (n + chunk - 1) / chunk;
+  int status = AVC_OK;
+  // software pipeline: iteration c stages chunk c (memcpy to pinned + H2D), launches its kernel, queues its D2H,
+  // and retires chunk c-2's slot (copies its pinned outputs to the caller's buffers) before reusing it.
+  for (int64_t c = 0; c < n_chunks + 2 && status == AVC_OK; ++c) {
+    if (c >= 2) {            // retire chunk c-2
+      const int s = (int)(c & 1); const int64_t b = (c - 2) * chunk; const int64_t m = (n - b < chunk) ? n - b : chunk;
+      if (cudaEventSynchronize(ev_out[s]) != cudaSuccess) { status = avc_check_cuda(ctx, cudaGetLastError(), "host eval: D2H"); break; }
+      float* hp = (float*)ctx->h_pinned + (size_t)s * slot_floats;
+      memcpy(out_a + b, hp + (size_t)chunk * 3, (size_t)m * sizeof(float));
+      if (out_off) memcpy(out_off + b * 3, hp + (size_t)chunk * 4, (size_t)m * 3 * sizeof(float));
+    }
+    if (c < n_chunks) {
+      const int s = (int)(c & 1); const int64_t b = c * chunk; const int64_t m = (n - b < chunk) ? n - b : chunk;
+      float* hp = (float*)ctx->h_pinned + (size_t)s * slot_floats;
+      float* dp = (float*)ctx->d_stage + (size_t)s * slot_floats;
+      memcpy(hp, pts + b * 3, (size_t)m * 3 * sizeof(float));
+      cudaMemcpyAsync(dp, hp, (size_t)m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->s_copy_in);
+      cudaEventRecord(ev_in[s], ctx->s_copy_in);
+      cudaStreamWaitEvent(ctx->s_compute, ev_in[s], 0);
+      float* d_occ = dp + (size_t)chunk * 3; float* d_off = dp + (size_t)chunk * 4;
+      status = recon ? avc_eval_recon(ctx, dp, m, center, d_occ, impl, ctx->s_compute)
+                     : avc_eval_occupancy(ctx, dp, m, center, d_occ, out_off ? d_off : nullptr, nullptr, nullptr, if_type, impl, ctx->s_compute);
+      if (status != AVC_OK) break;
+      cudaEventRecord(ev_k[s], ctx->s_compute);
+      cudaStreamWaitEvent(ctx->s_copy_out, ev_k[s], 0);
+      cudaMemcpyAsync(hp + (size_t)chunk * 3, d_occ, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      if (out_off) cudaMemcpyAsync(hp + (size_t)chunk * 4, d_off, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      cudaEventRecord(ev_out[s], ctx->s_copy_out);
+      // the next use of this slot's device buffer (chunk c+2) must wait for this D2H
+      cudaStreamWaitEvent(ctx->s_copy_in, ev_out[s], 0);
+    }
+  }
+  cudaStreamSynchronize(ctx->s_copy_in); cudaStreamSynchronize(ctx->s_compute); cudaStreamSynchronize(ctx->s_copy_out);
+  for (int s = 0; s < 2; ++s) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_k[s]); cudaEventDestroy(ev_out[s]); }
+  if (status == AVC_OK) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) status = avc_check_cuda(ctx, e, "host eval"); }
+  return status;
+}
+
+extern "C" int avc_eval_occupancy_host(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
+                                       int if_type, int impl) {
+  return eval_host(ctx, false, pts, n, center, out_occ, out_off, if_type, impl);
+}
+extern "C" int avc_eval_recon_host(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, int impl) {
+  return eval_host(ctx, true, pts, n, center, out_ov, nullptr, AVC_IF_SDF, impl);
+}

@@ -1,0 +1,97 @@
+// Shared declarations for the avatarcap_b200 CUDA library (context, weight-blob layout, error helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/avatarcap_b200.h"
+
+#define AVC_MAGIC 0x57435641u /* 'AVCW' */
+#define AVC_BLOB_VERSION 2u
+#define AVC_MAX_LAYERS 24
+
+// Fixed layer order inside a blob (packer.py writes them in this order).
+// avatar: 0..6 warp conv1..7 (BN folded, softplus) | 7 warp out (256->3) | 8..14 shared fc0..6 | 15,16 geo | 17..19 clr
+// recon : 0..3 image_decoder fc0..3
+enum { AVC_KIND_AVATAR = 0, AVC_KIND_RECON = 1 };
+enum { AVC_ACT_NONE = 0, AVC_ACT_RELU = 1, AVC_ACT_LRELU = 2, AVC_ACT_SOFTPLUS = 3, AVC_ACT_SIGMOID = 4 };
+
+struct AvcLayerDesc {
+  int32_t k0, k1;      // true K of the first / second (skip) input segment, in the reference's concat order
+  int32_t k0p, k1p;    // padded to a multiple of 16 (tensor-core path)
+  int32_t n, np;       // output channels, padded to a multiple of 16 (>= 16)
+  int32_t act;
+  int32_t wt_off;      // f32 section, float index: W^T[(k0+k1)][n] (row k holds n contiguous outputs); heads (n<=4): W[n][k0+k1]
+  int32_t sb_off;      // f32 section, float index: scale[n] then bias[n]   (y = acc*scale + bias)
+  int32_t tc_w_off;    // f16 section, byte offset: for each 16-wide k-step: hi slab (np*32 B) then lo slab (np*32 B)
+  int32_t tc_sb_off;   // f32 section, float index: scale[np] then bias[np] for the tensor-core path (scale includes 2^-wshift)
+  int32_t reserved;
+};
+
+struct AvcBlobHeader {
+  uint32_t magic, version, kind, n_layers;
+  uint64_t f32_off, f32_bytes;    // byte offset / size of the float32 section
+  uint64_t f16_off, f16_bytes;    // byte offset / size of the fp16 hi/lo section
+  AvcLayerDesc layers[AVC_MAX_LAYERS];
+};
+
+struct AvcWeights {
+  bool loaded = false;
+  AvcBlobHeader hdr;
+  unsigned char* d_blob = nullptr;   // whole blob on the device
+  const float* d_f32 = nullptr;
+  const unsigned char* d_f16 = nullptr;
+};
+
+struct AvcMap {
+  float* d_hwc = nullptr;   // (H,W,C)
+  size_t cap = 0;
+  int C = 0, H = 0, W = 0;
+};
+
+struct avc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  std::string err;
+  AvcWeights avatar, recon;
+  AvcMap maps[2];
+  int64_t launches = 0;
+  // scratch owned by the context (marching cubes scans, host staging)
+  void* d_scratch = nullptr; size_t scratch_cap = 0;
+  void* h_pinned = nullptr;  size_t pinned_cap = 0;
+  void* d_stage = nullptr;   size_t stage_cap = 0;
+  cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
+  int64_t* h_counts = nullptr;   // pinned, small
+};
+
+int avc_fail(avc_ctx* ctx, int code, const char* fmt, ...);
+int avc_check_cuda(avc_ctx* ctx, cudaError_t e, const char* what);
+int avc_ensure_scratch(avc_ctx* ctx, size_t bytes);
+
+#define AVC_CUDA(ctx, call)                                                        \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) return avc_check_cuda((ctx), _e, #call);                \
+  } while (0)
+
+#define AVC_LAUNCH_CHECK(ctx, name)                                                \
+  do {                                                                             \
+    (ctx)->launches++;                                                             \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) return avc_check_cuda((ctx), _e, name);                 \
+  } while (0)
+
+// ---- kernels implemented in the other translation units -------------------------------------------------
+int avc_simt_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
+                         float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
+int avc_simt_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
+int avc_tc_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
+                       float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
+int avc_tc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
+int avc_tc_available(const avc_ctx* ctx);
+
+// mode for the avatar evaluation
+enum { AVC_MODE_QUERY = 0 /* warp + template */, AVC_MODE_WARP_ONLY = 1, AVC_MODE_TEMPLATE_ONLY = 2 };

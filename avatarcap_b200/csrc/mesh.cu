@@ -1,0 +1,403 @@
+// Grid generation, mask scatter and marching-cubes mesh extraction with fused Sobel normals.
+//
+// Reference call sites replaced:
+//   generate_volume_points         dataset/avatarcap_dataset.py:312-326
+//   vol[flag]=vals; vol[~flag]=fill main.py:357,362-364 / 438,442-443
+//   recon_mesh                     utils/recon_util.py:51-70   (skimage marching_cubes :64 runs on the CPU after a D2H copy)
+//   extract_normal_volume          utils/recon_util.py:9-29    (full 3xR^3 conv3d; here only the 4x4x4 stencil around each vertex)
+//   extract_normal_from_volume     utils/recon_util.py:32-48
+//
+// All of this is HBM-bound scan/compaction work: the volume is read with coalesced z-fastest accesses, warp
+// ballots/shuffles do the in-block scans, and the only intermediate is a 4 B/voxel vertex-base array.
+#include "common.cuh"
+#include "mc_tables.inc"
+
+namespace {
+
+constexpr int MC_NT = 256;
+constexpr int MC_VPT = 4;                  // voxels per thread (consecutive in z)
+constexpr int MC_VPB = MC_NT * MC_VPT;     // voxels per block
+
+struct McDims {
+  int rx, ry, rz;        // local extents (including halo planes)
+  int lo, hi_excl;       // owned planes: lo <= i < hi_excl
+  int scan_end;          // planes lo <= i < scan_end take part in the vertex scan (hi_excl, or hi_excl+1 with a hi halo)
+  float iso;
+  int64_t nvox;
+};
+
+__device__ __forceinline__ float ldv(const float* __restrict__ vol, int64_t idx) { return __ldg(vol + idx); }
+
+// per-voxel classification: cut flags of the 3 owned edges (bit0 x, bit1 y, bit2 z) and the cell's case index (or -1)
+struct VoxInfo { int cut; int ccase; bool in_scan; bool owned; };
+
+__device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const McDims& d, int64_t v) {
+  VoxInfo r; r.cut = 0; r.ccase = -1; r.in_scan = false; r.owned = false;
+  if (v >= d.nvox) return r;
+  const int k = (int)(v % d.rz); const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
+  if (i < d.lo || i >= d.scan_end) return r;
+  r.in_scan = true; r.owned = i < d.hi_excl;
+  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
+  const bool hx = i + 1 < d.rx, hy = j + 1 < d.ry, hz = k + 1 < d.rz;
+  const bool b000 = ldv(vol, v) > d.iso;
+  bool b100 = false, b010 = false, b001 = false;
+  if (hx) { b100 = ldv(vol, v + sx) > d.iso; r.cut |= (b100 != b000) ? 1 : 0; }
+  if (hy) { b010 = ldv(vol, v + sy) > d.iso; r.cut |= (b010 != b000) ? 2 : 0; }
+  if (hz) { b001 = ldv(vol, v + 1) > d.iso; r.cut |= (b001 != b000) ? 4 : 0; }
+  if (r.owned && hx && hy && hz) {
+    const bool b110 = ldv(vol, v + sx + sy) > d.iso, b101 = ldv(vol, v + sx + 1) > d.iso;
+    const bool b011 = ldv(vol, v + sy + 1) > d.iso, b111 = ldv(vol, v + sx + sy + 1) > d.iso;
+    // corner c has offset (c&1, c>>1&1, c>>2&1) in (x,y,z)   (mc_tables.py)
+    r.ccase = (int)b000 | ((int)b100 << 1) | ((int)b010 << 2) | ((int)b110 << 3) | ((int)b001 << 4) | ((int)b101 << 5) |
+              ((int)b011 << 6) | ((int)b111 << 7);
+  }
+  return r;
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ int block_excl_scan(int val, int* total) {
+  __shared__ int warp_sums[MC_NT / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = val;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  __syncthreads();   // protect warp_sums reuse across calls
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  int wprefix = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < MC_NT / 32; ++w) { const int s = warp_sums[w]; if (w < wid) wprefix += s; tot += s; }
+  *total = tot;
+  return wprefix + inc - val;
+}
+
+// pass A: per-block totals {vertices in scan range, owned vertices, triangles}
+__global__ void __launch_bounds__(MC_NT) mc_count_kernel(const float* __restrict__ vol, McDims d, int* __restrict__ blk) {
+  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  int nv = 0, nvo = 0, nt = 0;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) {
+    const VoxInfo r = classify(vol, d, v0 + q);
+    const int c = __popc(r.cut);
+    if (r.in_scan) nv += c;
+    if (r.owned) { nvo += c; if (r.ccase >= 0) nt += c_mc_ntri[r.ccase]; }
+  }
+  int tv, tvo, tt;
+  block_excl_scan(nv, &tv); block_excl_scan(nvo, &tvo); block_excl_scan(nt, &tt);
+  if (threadIdx.x == 0) { blk[3 * blockIdx.x] = tv; blk[3 * blockIdx.x + 1] = tvo; blk[3 * blockIdx.x + 2] = tt; }
+}
+
+// pass B: exclusive scan over blocks (single CTA); totals -> tot[0..2] (int64)
+__global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(int* __restrict__ blk, int nblk, int64_t* __restrict__ tot) {
+  __shared__ long long carry[3];
+  __shared__ long long wsum[3][32];
+  if (threadIdx.x < 3) carry[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < nblk; base += 1024) {
+    const int b = base + threadIdx.x;
+    long long x[3], inc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { x[c] = b < nblk ? blk[3 * b + c] : 0; inc[c] = x[c]; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const long long t = __shfl_up_sync(0xffffffffu, inc[c], o); if (lane >= o) inc[c] += t; }
+    if (lane == 31) { wsum[0][wid] = inc[0]; wsum[1][wid] = inc[1]; wsum[2][wid] = inc[2]; }
+    __syncthreads();
+    long long pre[3] = {0, 0, 0}, tt[3] = {0, 0, 0};
+    for (int w = 0; w < 32; ++w)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { const long long s = wsum[c][w]; if (w < wid) pre[c] += s; tt[c] += s; }
+    if (b < nblk)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) blk[3 * b + c] = (int)(carry[c] + pre[c] + inc[c] - x[c]);
+    __syncthreads();
+    if (threadIdx.x < 3) carry[threadIdx.x] += tt[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) tot[threadIdx.x] = carry[threadIdx.x];
+}
+
+// pass C: vbase[v] = exclusive vertex prefix of voxel v (canonical order: voxel linear index, then axis)
+__global__ void __launch_bounds__(MC_NT) mc_vbase_kernel(const float* __restrict__ vol, McDims d, const int* __restrict__ blk,
+                                                         int* __restrict__ vbase) {
+  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  int c[MC_VPT]; int nv = 0;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) { const VoxInfo r = classify(vol, d, v0 + q); c[q] = r.in_scan ? __popc(r.cut) : 0; nv += c[q]; }
+  int tot; int p = blk[3 * blockIdx.x] + block_excl_scan(nv, &tot);
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = p; p += c[q]; }
+}
+
+struct McEmit {
+  float vox[3], bmin[3], len[3];
+  int gres[3];        // global resolution (for the normal-sampling coordinates)
+  int x_origin;       // global index of local plane 0
+  float* verts; float* normals; int32_t* faces;
+};
+
+// Sobel gradient (recon_util.py:10-26) at local grid point (i,j,k): zero padding outside the GLOBAL volume.
+// The caller guarantees the halo covers every point the stencil touches inside the global volume.
+__device__ __forceinline__ float vol_at(const float* __restrict__ vol, const McDims& d, const McEmit& e, int i, int j, int k) {
+  const int gi = i + e.x_origin;
+  if (gi < 0 || gi >= e.gres[0] || j < 0 || j >= d.ry || k < 0 || k >= d.rz) return 0.f;
+  if (i < 0 || i >= d.rx) return 0.f;   // not covered by the halo (cannot happen with the documented halo widths)
+  return ldv(vol, ((int64_t)i * d.ry + j) * d.rz + k);
+}
+
+// pass D: emit vertices (+normals) and faces
+__global__ void __launch_bounds__(MC_NT) mc_emit_kernel(const float* __restrict__ vol, McDims d, McEmit e, const int* __restrict__ blk,
+                                                        const int* __restrict__ vbase) {
+  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  VoxInfo info[MC_VPT]; int nt = 0;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) { info[q] = classify(vol, d, v0 + q); if (info[q].owned && info[q].ccase >= 0) nt += c_mc_ntri[info[q].ccase]; }
+  int tot; int tbase = blk[3 * blockIdx.x + 2] + block_excl_scan(nt, &tot);
+  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) {
+    const int64_t v = v0 + q;
+    const VoxInfo r = info[q];
+    if (!r.owned) continue;
+    const int k = (int)(v % d.rz); const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
+    // ---- vertices owned by this voxel -------------------------------------------------------------------------
+    if (r.cut) {
+      int vid = vbase[v];
+      const float va = ldv(vol, v);
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        if (!((r.cut >> ax) & 1)) continue;
+        const float vb = ldv(vol, v + (ax == 0 ? sx : (ax == 1 ? sy : 1)));
+        const float tt = __fdiv_rn(__fsub_rn(d.iso, va), __fsub_rn(vb, va));      // linear interpolation (skimage: edge-weighted)
+        float idx[3] = {(float)(i + e.x_origin), (float)j, (float)k};
+        idx[ax] = __fadd_rn(idx[ax], tt);
+        float p[3], g[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          // vertices = mc*voxel (spacing) ; + bounds[0] + 0.5*voxel   recon_util.py:64-65
+          p[c] = __fadd_rn(__fadd_rn(__fmul_rn(idx[c], e.vox[c]), e.bmin[c]), __fmul_rn(0.5f, e.vox[c]));
+          // vertices_grid = 2*(v - bmin)/len - 1   :66 ; grid_sample unnormalise ((g+1)/2)*(R-1), border clip
+          const float gg = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(p[c], e.bmin[c])), e.len[c]), 1.f);
+          float s = __fmul_rn(__fdiv_rn(__fadd_rn(gg, 1.f), 2.f), (float)(e.gres[c] - 1));
+          g[c] = fminf((float)(e.gres[c] - 1), fmaxf(s, 0.f));
+        }
+        e.verts[(int64_t)vid * 3 + 0] = p[0]; e.verts[(int64_t)vid * 3 + 1] = p[1]; e.verts[(int64_t)vid * 3 + 2] = p[2];
+        if (e.normals) {
+          // trilinear sample of the Sobel gradient volume: 8 corners, each a 3x3x3 stencil -> a 4x4x4 block of voxels
+          const int x0 = (int)floorf(g[0]), y0 = (int)floorf(g[1]), z0 = (int)floorf(g[2]);
+          const float fx = g[0] - (float)x0, fy = g[1] - (float)y0, fz = g[2] - (float)z0;
+          float blk4[4][4][4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) blk4[a][b][c] = vol_at(vol, d, e, x0 - 1 + a - e.x_origin, y0 - 1 + b, z0 - 1 + c);
+          float n[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+              for (int dz = 0; dz < 2; ++dz) {
+                // corner (x0+dx, y0+dy, z0+dz); taps beyond the last plane have weight 0 (border clip)
+                const bool ok = (x0 + dx <= e.gres[0] - 1) && (y0 + dy <= e.gres[1] - 1) && (z0 + dz <= e.gres[2] - 1);
+                const float w = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * (dz ? fz : 1.f - fz);
+                if (!ok) continue;
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                  for (int b = 0; b < 3; ++b) {
+                    const float sw = (float)((a == 1 ? 2 : 1) * (b == 1 ? 2 : 1));
+                    gx += sw * (blk4[dx + 2][dy + a][dz + b] - blk4[dx][dy + a][dz + b]);
+                    gy += sw * (blk4[dx + a][dy + 2][dz + b] - blk4[dx + a][dy][dz + b]);
+                    gz += sw * (blk4[dx + a][dy + b][dz + 2] - blk4[dx + a][dy + b][dz]);
+                  }
+                n[0] += w * (gx / (32.f * e.vox[0])); n[1] += w * (gy / (32.f * e.vox[1])); n[2] += w * (gz / (32.f * e.vox[2]));
+              }
+          const float nn = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);   // no epsilon (recon_util.py:46-47)
+          e.normals[(int64_t)vid * 3 + 0] = -(n[0] / nn);                      // negated (:68)
+          e.normals[(int64_t)vid * 3 + 1] = -(n[1] / nn);
+          e.normals[(int64_t)vid * 3 + 2] = -(n[2] / nn);
+        }
+        ++vid;
+      }
+    }
+    // ---- faces of the cell whose lowest corner is this voxel -------------------------------------------------
+    if (r.ccase >= 0) {
+      const int ntri = c_mc_ntri[r.ccase];
+      for (int tix = 0; tix < ntri; ++tix) {
+        int ids[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int ed = c_mc_tri[r.ccase][3 * tix + c];
+          const int corner = c_mc_edge_corner[ed], ax = c_mc_edge_axis[ed];
+          const int64_t ov = v + (corner & 1) * sx + ((corner >> 1) & 1) * sy + ((corner >> 2) & 1);
+          // rank of `ax` among the owner's cut edges: recompute the owner's lower-axis cut flags
+          int rank = 0;
+          if (ax > 0) {
+            const bool o0 = ldv(vol, ov) > d.iso;
+            const int oi = i + (corner & 1), oj = j + ((corner >> 1) & 1);
+            if (oi + 1 < d.rx && ((ldv(vol, ov + sx) > d.iso) != o0)) ++rank;
+            if (ax > 1 && oj + 1 < d.ry && ((ldv(vol, ov + sy) > d.iso) != o0)) ++rank;
+          }
+          ids[c] = vbase[ov] + rank;
+        }
+        const int64_t f = (int64_t)tbase + tix;
+        e.faces[f * 3 + 0] = ids[2]; e.faces[f * 3 + 1] = ids[1]; e.faces[f * 3 + 2] = ids[0];   // faces[:, [2,1,0]]  :69
+      }
+      tbase += ntri;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void make_grid_kernel(float* __restrict__ out, float bx, float by, float bz, float lx, float ly, float lz, int rx, int ry,
+                                 int rz, int x_first, int64_t n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int k = (int)(idx % rz); const int64_t t = idx / rz; const int j = (int)(t % ry); const int i = (int)(t / ry) + x_first;
+  // torch.linspace(0, 1, steps) in float32: start + step*i below the midpoint, end - step*(steps-1-i) above it
+  auto lin = [](int q, int steps) -> float {
+    if (steps <= 1) return 0.f;
+    const float step = __fdiv_rn(1.f, (float)(steps - 1));
+    return q < steps / 2 ? __fmul_rn(step, (float)q) : __fsub_rn(1.f, __fmul_rn(step, (float)(steps - 1 - q)));
+  };
+  out[idx * 3 + 0] = __fadd_rn(__fmul_rn(lin(i, rx), lx), bx);     // pts * (bmax - bmin) + bmin   avatarcap_dataset.py:324
+  out[idx * 3 + 1] = __fadd_rn(__fmul_rn(lin(j, ry), ly), by);
+  out[idx * 3 + 2] = __fadd_rn(__fmul_rn(lin(k, rz), lz), bz);
+}
+
+__global__ void __launch_bounds__(MC_NT) flag_count_kernel(const uint8_t* __restrict__ flag, int64_t n, int* __restrict__ blk) {
+  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  int c = 0;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) if (v0 + q < n && flag[v0 + q]) ++c;
+  int tot; block_excl_scan(c, &tot);
+  if (threadIdx.x == 0) { blk[3 * blockIdx.x] = tot; blk[3 * blockIdx.x + 1] = 0; blk[3 * blockIdx.x + 2] = 0; }
+}
+
+__global__ void __launch_bounds__(MC_NT) scatter_fill_kernel(const uint8_t* __restrict__ flag, int64_t n, const int* __restrict__ blk,
+                                                             const float* __restrict__ vals, const float* __restrict__ fill,
+                                                             float* __restrict__ out) {
+  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  int c = 0; bool f[MC_VPT];
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) { f[q] = (v0 + q < n) && flag[v0 + q]; c += f[q]; }
+  int tot; int64_t p = (int64_t)blk[3 * blockIdx.x] + block_excl_scan(c, &tot);
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) {
+    const int64_t v = v0 + q;
+    if (v >= n) break;
+    if (f[q]) { out[v] = vals[p]; ++p; } else { out[v] = fill[v - p]; }
+  }
+}
+
+int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi, McDims* d, int* nblk, int** d_blk, int64_t** d_tot,
+             int** d_vbase) {
+  if (res[0] < 2 || res[1] < 2 || res[2] < 2) return avc_fail(ctx, AVC_EINVAL, "marching cubes needs res >= 2 per axis");
+  if (halo_lo < 0 || halo_hi < 0 || halo_lo + halo_hi >= res[0]) return avc_fail(ctx, AVC_EINVAL, "bad halo widths");
+  d->rx = res[0]; d->ry = res[1]; d->rz = res[2];
+  d->lo = halo_lo; d->hi_excl = res[0] - halo_hi; d->scan_end = halo_hi > 0 ? d->hi_excl + 1 : d->hi_excl;
+  d->iso = iso; d->nvox = (int64_t)res[0] * res[1] * res[2];
+  if (d->nvox > (int64_t)1 << 40) return avc_fail(ctx, AVC_EINVAL, "volume too large");
+  *nblk = (int)((d->nvox + MC_VPB - 1) / MC_VPB);
+  const size_t need = (size_t)*nblk * 3 * sizeof(int) + 64 + (size_t)d->nvox * sizeof(int) + 256;
+  int rc = avc_ensure_scratch(ctx, need);
+  if (rc) return rc;
+  char* base = (char*)ctx->d_scratch;
+  *d_tot = (int64_t*)base;
+  *d_blk = (int*)(base + 64);
+  size_t off = 64 + (size_t)*nblk * 3 * sizeof(int); off = (off + 255) & ~(size_t)255;
+  *d_vbase = (int*)(base + off);
+  return AVC_OK;
+}
+
+}  // namespace
+
+extern "C" int avc_make_grid(avc_ctx* ctx, const float bounds[6], const int res[3], int x_first, int x_count, float* out_pts, void* stream) {
+  if (!ctx || !bounds || !res || !out_pts) return avc_fail(ctx, AVC_EINVAL, "avc_make_grid: NULL argument");
+  if (x_first < 0 || x_count < 0 || x_first + x_count > res[0]) return avc_fail(ctx, AVC_EINVAL, "avc_make_grid: bad slab");
+  const int64_t n = (int64_t)x_count * res[1] * res[2];
+  if (n == 0) return AVC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (int)((n + 255) / 256);
+  make_grid_kernel<<<nb, 256, 0, st>>>(out_pts, bounds[0], bounds[1], bounds[2], bounds[3] - bounds[0], bounds[4] - bounds[1],
+                                       bounds[5] - bounds[2], res[0], res[1], res[2], x_first, n);
+  AVC_LAUNCH_CHECK(ctx, "make_grid_kernel");
+  return AVC_OK;
+}
+
+extern "C" int avc_scatter_fill(avc_ctx* ctx, const uint8_t* flag, int64_t n_total, const float* vals, const float* fill, float* out_vol,
+                                void* stream) {
+  if (!ctx || !flag || !out_vol) return avc_fail(ctx, AVC_EINVAL, "avc_scatter_fill: NULL argument");
+  if (n_total == 0) return AVC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)((n_total + MC_VPB - 1) / MC_VPB);
+  int rc = avc_ensure_scratch(ctx, (size_t)nblk * 3 * sizeof(int) + 64);
+  if (rc) return rc;
+  int64_t* d_tot = (int64_t*)ctx->d_scratch; int* d_blk = (int*)((char*)ctx->d_scratch + 64);
+  flag_count_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, d_blk);
+  AVC_LAUNCH_CHECK(ctx, "flag_count_kernel");
+  mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(d_blk, nblk, d_tot);
+  AVC_LAUNCH_CHECK(ctx, "mc_scan_blocks_kernel");
+  scatter_fill_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, d_blk, vals, fill, out_vol);
+  AVC_LAUNCH_CHECK(ctx, "scatter_fill_kernel");
+  return AVC_OK;
+}
+
+static int mc_run_count(avc_ctx* ctx, const float* vol, const McDims& d, int nblk, int* d_blk, int64_t* d_tot, cudaStream_t st) {
+  mc_count_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk);
+  AVC_LAUNCH_CHECK(ctx, "mc_count_kernel");
+  mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(d_blk, nblk, d_tot);
+  AVC_LAUNCH_CHECK(ctx, "mc_scan_blocks_kernel");
+  AVC_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, d_tot, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  AVC_CUDA(ctx, cudaStreamSynchronize(st));
+  return AVC_OK;
+}
+
+extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], float iso, int x_halo_lo, int x_halo_hi, int64_t* n_verts,
+                            int64_t* n_faces, void* stream) {
+  if (!ctx || !vol || !res || !n_verts || !n_faces) return avc_fail(ctx, AVC_EINVAL, "avc_mc_count: NULL argument");
+  McDims d; int nblk; int* d_blk; int64_t* d_tot; int* d_vbase;
+  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);
+  if (rc) return rc;
+  rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, (cudaStream_t)stream);
+  if (rc) return rc;
+  *n_verts = ctx->h_counts[1]; *n_faces = ctx->h_counts[2];
+  return AVC_OK;
+}
+
+extern "C" int avc_mc_emit(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
+                           int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
+                           void* stream) {
+  if (!ctx || !vol || !res || !bounds || !verts || !faces) return avc_fail(ctx, AVC_EINVAL, "avc_mc_emit: NULL argument");
+  if (gres_x < res[0] - x_halo_lo - x_halo_hi || x_origin < -x_halo_lo) return avc_fail(ctx, AVC_EINVAL, "avc_mc_emit: bad slab placement");
+  cudaStream_t st = (cudaStream_t)stream;
+  McDims d; int nblk; int* d_blk; int64_t* d_tot; int* d_vbase;
+  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);
+  if (rc) return rc;
+  rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, st);
+  if (rc) return rc;
+  const int64_t nv = ctx->h_counts[1], nf = ctx->h_counts[2];
+  if (nv > cap_v || nf > cap_f)
+    return avc_fail(ctx, AVC_ECAPACITY, "avc_mc_emit: need %lld vertices / %lld faces, capacity %lld / %lld", (long long)nv, (long long)nf,
+                    (long long)cap_v, (long long)cap_f);
+  if (ctx->h_counts[0] > 0x7fffffffLL || nf > 0x7fffffffLL) return avc_fail(ctx, AVC_EINVAL, "mesh too large for int32 indices");
+  if (nv == 0 && nf == 0) return AVC_OK;
+  mc_vbase_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk, d_vbase);
+  AVC_LAUNCH_CHECK(ctx, "mc_vbase_kernel");
+  McEmit e;
+  const int gres[3] = {gres_x, res[1], res[2]};
+  for (int c = 0; c < 3; ++c) {
+    e.bmin[c] = bounds[c]; e.len[c] = bounds[3 + c] - bounds[c]; e.gres[c] = gres[c];
+    e.vox[c] = e.len[c] / (float)gres[c];                                   // recon_util.py:60-61
+  }
+  e.x_origin = x_origin; e.verts = verts; e.normals = normals; e.faces = faces;
+  mc_emit_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, e, d_blk, d_vbase);
+  AVC_LAUNCH_CHECK(ctx, "mc_emit_kernel");
+  return AVC_OK;
+}

@@ -1,0 +1,268 @@
+"""Thin torch-tensor front end over the C ABI: one `Engine` per CUDA device.
+
+PyTorch is used for device memory, streams and (in shard.py) torch.distributed only; all arithmetic of the hot path
+runs in libavatarcap_b200.so. Every method enqueues on the caller's current CUDA stream
+(`torch.cuda.current_stream()`), as the reference's single-stream code expects.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, packer
+from ._lib import AvcError, IMPL_AUTO, IMPL_SIMT, IMPL_TC, IF_SDF, IF_OCCUPANCY, MAP_POSE, MAP_IMAGE
+
+_IMPL = {'auto': IMPL_AUTO, 'simt': IMPL_SIMT, 'tc': IMPL_TC}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, device: Optional[torch.device] = None, impl: str = 'auto'):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('avatarcap_b200 needs a CUDA device (B200); there is no CPU fallback')
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        self.device = dev
+        self.impl = impl
+        h = C.c_void_p()
+        rc = self.lib.avc_ctx_create(dev.index, C.byref(h))
+        if rc:
+            raise AvcError(rc, self.lib.avc_last_error(None).decode())
+        self._h = h
+        self._keep: Dict[str, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self) -> None:
+        if getattr(self, '_h', None):
+            self.lib.avc_ctx_destroy(self._h); self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc:
+            msg = self.lib.avc_last_error(self._h).decode()
+            if rc == _lib.EVALUE:
+                raise ValueError(msg)            # same exception class as the reference (config.py:22, skimage)
+            raise AvcError(rc, msg)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, shape_last: Optional[int] = None) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t))
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        if shape_last is not None and t.shape[-1] != shape_last:
+            raise ValueError('expected last dimension %d, got shape %s' % (shape_last, tuple(t.shape)))
+        return t
+
+    def _impl(self, impl: Optional[str]) -> int:
+        return _IMPL[impl or self.impl]
+
+    @property
+    def has_tensor_core_path(self) -> bool:
+        return bool(self.lib.avc_has_tensor_core_path(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.avc_launch_count(self._h))
+
+    def reset_launch_count(self) -> None:
+        self.lib.avc_reset_launch_count(self._h)
+
+    # ------------------------------------------------------------------ weights / feature maps
+    def load_avatar(self, state_dict) -> None:
+        blob = packer.pack_avatar(state_dict)
+        self._check(self.lib.avc_load_avatar_weights(self._h, blob, len(blob)))
+
+    def load_recon(self, state_dict) -> None:
+        blob = packer.pack_recon(state_dict)
+        self._check(self.lib.avc_load_recon_weights(self._h, blob, len(blob)))
+
+    def set_feature_map(self, which: int, fmap) -> None:
+        t = self._f32(fmap)
+        if t.dim() == 4:
+            if t.shape[0] != 1:
+                raise ValueError('feature map batch must be 1 per call')
+            t = t[0]
+        Cc, H, W = t.shape
+        self._check(self.lib.avc_set_feature_map(self._h, which, _ptr(t), Cc, H, W, self._stream()))
+
+    def set_pose_feature_map(self, fmap) -> None:
+        """WarpingField.pose_feat_map (1,64,H,W) produced by precompute_conv (arch_avatar.py:109-111)."""
+        self.set_feature_map(MAP_POSE, fmap)
+
+    def set_image_feature_map(self, fmap) -> None:
+        """HGFilter output (1,32,H,W) (arch_recon.py:51-52)."""
+        self.set_feature_map(MAP_IMAGE, fmap)
+
+    # ------------------------------------------------------------------ field evaluation (device tensors)
+    def eval_occupancy(self, pts, center, want_offsets: bool = True, want_texture: bool = False, if_type: str = 'sdf',
+                       impl: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        """OccupancyNet.query body for one batch element: pts (N,3), center (3,) -> occ (N,), off (N,3)[, rgb (N,3), alpha (N,)]."""
+        if if_type not in ('sdf', 'occupancy'):
+            raise ValueError('Invalid config.if_type!')
+        p = self._f32(pts, 3)
+        n = p.shape[0]
+        occ = torch.empty(n, device=self.device, dtype=torch.float32)
+        off = torch.empty((n, 3), device=self.device, dtype=torch.float32) if want_offsets else None
+        rgb = torch.empty((n, 3), device=self.device, dtype=torch.float32) if want_texture else None
+        alpha = torch.empty(n, device=self.device, dtype=torch.float32) if want_texture else None
+        c = _lib.f3(center.detach().cpu().tolist() if isinstance(center, torch.Tensor) else center)
+        self._check(self.lib.avc_eval_occupancy(self._h, _ptr(p), n, c, _ptr(occ), _ptr(off), _ptr(rgb), _ptr(alpha),
+                                                IF_SDF if if_type == 'sdf' else IF_OCCUPANCY, self._impl(impl), self._stream()))
+        out = {'occ': occ}
+        if off is not None:
+            out['off'] = off
+        if want_texture:
+            out['rgb'] = rgb; out['alpha'] = alpha
+        return out
+
+    def eval_warp(self, pts, center, impl: Optional[str] = None) -> torch.Tensor:
+        p = self._f32(pts, 3); n = p.shape[0]
+        off = torch.empty((n, 3), device=self.device, dtype=torch.float32)
+        c = _lib.f3(center.detach().cpu().tolist() if isinstance(center, torch.Tensor) else center)
+        self._check(self.lib.avc_eval_warp(self._h, _ptr(p), n, c, _ptr(off), self._impl(impl), self._stream()))
+        return off
+
+    def eval_template(self, pts, if_type: str = 'sdf', impl: Optional[str] = None):
+        """DoubleTNet.forward for (N,3) points -> rgb (N,3), alpha (N,), occ (N,)."""
+        if if_type not in ('sdf', 'occupancy'):
+            raise ValueError('Invalid config.if_type!')
+        p = self._f32(pts, 3); n = p.shape[0]
+        rgb = torch.empty((n, 3), device=self.device, dtype=torch.float32)
+        alpha = torch.empty(n, device=self.device, dtype=torch.float32)
+        occ = torch.empty(n, device=self.device, dtype=torch.float32)
+        self._check(self.lib.avc_eval_template(self._h, _ptr(p), n, _ptr(rgb), _ptr(alpha), _ptr(occ),
+                                               IF_SDF if if_type == 'sdf' else IF_OCCUPANCY, self._impl(impl), self._stream()))
+        return rgb, alpha, occ
+
+    def eval_recon(self, pts, center, impl: Optional[str] = None) -> torch.Tensor:
+        p = self._f32(pts, 3); n = p.shape[0]
+        ov = torch.empty(n, device=self.device, dtype=torch.float32)
+        c = _lib.f3(center.detach().cpu().tolist() if isinstance(center, torch.Tensor) else center)
+        self._check(self.lib.avc_eval_recon(self._h, _ptr(p), n, c, _ptr(ov), self._impl(impl), self._stream()))
+        return ov
+
+    # ------------------------------------------------------------------ host-buffer (end-to-end) entry points
+    def eval_occupancy_host(self, pts_host: np.ndarray, center, out_occ: np.ndarray, out_off: Optional[np.ndarray] = None,
+                            if_type: str = 'sdf', impl: Optional[str] = None) -> None:
+        assert pts_host.dtype == np.float32 and pts_host.flags.c_contiguous and out_occ.dtype == np.float32
+        n = pts_host.shape[0]
+        self._check(self.lib.avc_eval_occupancy_host(self._h, pts_host.ctypes.data_as(C.c_void_p), n, _lib.f3(center),
+                                                     out_occ.ctypes.data_as(C.c_void_p),
+                                                     None if out_off is None else out_off.ctypes.data_as(C.c_void_p),
+                                                     IF_SDF if if_type == 'sdf' else IF_OCCUPANCY, self._impl(impl)))
+
+    def eval_recon_host(self, pts_host: np.ndarray, center, out_ov: np.ndarray, impl: Optional[str] = None) -> None:
+        assert pts_host.dtype == np.float32 and pts_host.flags.c_contiguous and out_ov.dtype == np.float32
+        self._check(self.lib.avc_eval_recon_host(self._h, pts_host.ctypes.data_as(C.c_void_p), pts_host.shape[0], _lib.f3(center),
+                                                 out_ov.ctypes.data_as(C.c_void_p), self._impl(impl)))
+
+    # ------------------------------------------------------------------ grid / scatter
+    def make_grid(self, bounds, res, x_first: int = 0, x_count: Optional[int] = None) -> torch.Tensor:
+        x_count = res[0] - x_first if x_count is None else x_count
+        out = torch.empty((x_count * res[1] * res[2], 3), device=self.device, dtype=torch.float32)
+        b = np.asarray(bounds, dtype=np.float32).reshape(6)
+        self._check(self.lib.avc_make_grid(self._h, _lib.f6(b), _lib.i3(res), x_first, x_count, _ptr(out), self._stream()))
+        return out
+
+    def scatter_fill(self, flag: torch.Tensor, vals: torch.Tensor, fill: torch.Tensor) -> torch.Tensor:
+        flag = flag.to(self.device).contiguous()
+        f8 = flag.view(torch.uint8) if flag.dtype == torch.bool else flag.to(torch.uint8)
+        vals = self._f32(vals).reshape(-1); fill = self._f32(fill).reshape(-1)
+        out = torch.empty(f8.numel(), device=self.device, dtype=torch.float32)
+        self._check(self.lib.avc_scatter_fill(self._h, _ptr(f8), f8.numel(), _ptr(vals), _ptr(fill), _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ mesh extraction
+    def mc_count(self, vol: torch.Tensor, iso: float, halo_lo: int = 0, halo_hi: int = 0) -> Tuple[int, int]:
+        vol = self._f32(vol)
+        nv, nf = C.c_int64(), C.c_int64()
+        self._check(self.lib.avc_mc_count(self._h, _ptr(vol), _lib.i3(vol.shape), float(iso), halo_lo, halo_hi, C.byref(nv), C.byref(nf),
+                                          self._stream()))
+        return nv.value, nf.value
+
+    def extract_mesh(self, vol: torch.Tensor, bounds, iso: float, with_normals: bool = True, halo_lo: int = 0, halo_hi: int = 0,
+                     x_origin: int = 0, gres_x: Optional[int] = None):
+        """-> verts (V,3) f32, faces (F,3) i32, normals (V,3) f32 | None, all on the device, in the reference's conventions."""
+        vol = self._f32(vol)
+        if vol.dim() != 3:
+            raise ValueError('volume must be (Rx,Ry,Rz)')
+        nv, nf = self.mc_count(vol, iso, halo_lo, halo_hi)
+        verts = torch.empty((nv, 3), device=self.device, dtype=torch.float32)
+        faces = torch.empty((nf, 3), device=self.device, dtype=torch.int32)
+        normals = torch.empty((nv, 3), device=self.device, dtype=torch.float32) if with_normals else None
+        b = np.asarray(bounds, dtype=np.float32).reshape(6)
+        gx = vol.shape[0] if gres_x is None else gres_x
+        self._check(self.lib.avc_mc_emit(self._h, _ptr(vol), _lib.i3(vol.shape), _lib.f6(b), float(iso), halo_lo, halo_hi, x_origin, gx,
+                                         _ptr(verts), _ptr(normals), _ptr(faces), max(nv, 1), max(nf, 1), self._stream()))
+        return verts, faces, normals
+
+    # ------------------------------------------------------------------ KNN / LBS
+    def knn(self, query, ref, K: int = 1):
+        q = self._f32(query, 3); r = self._f32(ref, 3)
+        n = q.shape[0]
+        d2 = torch.empty((n, K), device=self.device, dtype=torch.float32)
+        idx = torch.empty((n, K), device=self.device, dtype=torch.int64)
+        self._check(self.lib.avc_knn(self._h, _ptr(q), n, _ptr(r), r.shape[0], K, _ptr(d2), _ptr(idx), self._stream()))
+        return d2, idx
+
+    def lbs_weights(self, pts, cano_verts, skin_weights) -> torch.Tensor:
+        p = self._f32(pts, 3); v = self._f32(cano_verts, 3); w = self._f32(skin_weights, 24)
+        out = torch.empty((p.shape[0], 24), device=self.device, dtype=torch.float32)
+        self._check(self.lib.avc_lbs_weights(self._h, _ptr(p), p.shape[0], _ptr(v), v.shape[0], _ptr(w), _ptr(out), self._stream()))
+        return out
+
+    def skin_points(self, pts, lbs, jnt_mats, return_pt_mats: bool = False):
+        p = self._f32(pts, 3); l = self._f32(lbs, 24); J = self._f32(jnt_mats).reshape(24, 16)
+        out = torch.empty_like(p)
+        mats = torch.empty((p.shape[0], 4, 4), device=self.device, dtype=torch.float32) if return_pt_mats else None
+        self._check(self.lib.avc_skin_points(self._h, _ptr(p), _ptr(l), _ptr(J), p.shape[0], _ptr(out), _ptr(mats), self._stream()))
+        return (out, mats) if return_pt_mats else out
+
+    def skin_normals(self, normals, lbs, jnt_mats) -> torch.Tensor:
+        nrm = self._f32(normals, 3); l = self._f32(lbs, 24); J = self._f32(jnt_mats).reshape(24, 16)
+        out = torch.empty_like(nrm)
+        self._check(self.lib.avc_skin_normals(self._h, _ptr(nrm), _ptr(l), _ptr(J), nrm.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def skin_mesh(self, verts, normals, cano_verts, skin_weights, jnt_mats):
+        v = self._f32(verts, 3); nrm = None if normals is None else self._f32(normals, 3)
+        cv = self._f32(cano_verts, 3); w = self._f32(skin_weights, 24); J = self._f32(jnt_mats).reshape(24, 16)
+        ov = torch.empty_like(v); on = None if nrm is None else torch.empty_like(nrm)
+        self._check(self.lib.avc_skin_mesh(self._h, _ptr(v), _ptr(nrm), v.shape[0], _ptr(cv), cv.shape[0], _ptr(w), _ptr(J), _ptr(ov), _ptr(on),
+                                           self._stream()))
+        return ov, on
+
+    def posed_to_cano(self, wpts, live_verts, skin_weights, live2cano_mats, bounds, weight_volume):
+        p = self._f32(wpts, 3); lv = self._f32(live_verts, 3); w = self._f32(skin_weights, 24)
+        J = self._f32(live2cano_mats).reshape(24, 16); vol = self._f32(weight_volume, 24)
+        cano = torch.empty_like(p); near = torch.empty(p.shape[0], device=self.device, dtype=torch.uint8)
+        b = np.asarray(bounds.detach().cpu().numpy() if isinstance(bounds, torch.Tensor) else bounds, dtype=np.float32).reshape(6)
+        self._check(self.lib.avc_posed_to_cano(self._h, _ptr(p), p.shape[0], _ptr(lv), lv.shape[0], _ptr(w), _ptr(J), _lib.f6(b), _ptr(vol),
+                                               _lib.i3(vol.shape[:3]), _ptr(cano), _ptr(near), self._stream()))
+        return cano, near.bool()
+
+
+_default: Dict[int, Engine] = {}
+
+
+def default_engine(device: Optional[torch.device] = None) -> Engine:
+    """Process-wide engine per device (what patch.install() uses)."""
+    idx = torch.cuda.current_device() if device is None or torch.device(device).index is None else torch.device(device).index
+    if idx not in _default:
+        _default[idx] = Engine(torch.device('cuda', idx))
+    return _default[idx]

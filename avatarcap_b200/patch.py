@@ -1,0 +1,137 @@
+"""Drop-in installation into an unmodified AvatarCap checkout.
+
+    import avatarcap_b200.patch as avc_patch
+    avc_patch.install()            # before main.run_avatarcap(...); `python main.py -c cfg -m test` is unchanged
+
+`install()` re-binds the reference's hot-path call sites to the CUDA library. The replacements are active only while
+autograd is disabled (`torch.no_grad()` / inference), because the training loop (main.py:97-116) differentiates
+through the same modules; with grad enabled every patched method falls through to the original PyTorch code.
+
+    network.arch_avatar.OccupancyNet.query      (arch_avatar.py:356)
+    network.arch_avatar.WarpingField.query      (arch_avatar.py:113)
+    network.arch_avatar.DoubleTNet.forward      (arch_avatar.py:65)
+    network.arch_avatar.GeoTexAvatar.forward    (arch_avatar.py:178)
+    network.arch_recon.ReconNetwork.infer       (arch_recon.py:45)
+    utils.recon_util.recon_mesh                 (recon_util.py:51)
+    utils.smpl_util.SmplUtil.calculate_lbs / skinning / skinning_normal   (smpl_util.py:24,58,76)
+"""
+from __future__ import annotations
+
+import importlib
+from typing import Dict, Optional
+
+import torch
+
+from . import api
+from .engine import Engine, default_engine
+
+_originals: Dict[str, object] = {}
+_state: Dict[str, object] = {}
+
+
+def _engine() -> Engine:
+    return _state.get('engine') or default_engine()
+
+
+def _avatar_loaded(net) -> None:
+    """(Re)pack the avatar weights when the module's parameters changed (main.py loads two checkpoints, :304-315)."""
+    key = (id(net), sum(int(p._version) for p in net.parameters()))
+    if _state.get('avatar_key') != key:
+        _engine().load_avatar(net.state_dict()); _state['avatar_key'] = key
+
+
+def _recon_loaded(net) -> None:
+    key = (id(net), sum(int(p._version) for p in net.parameters()))
+    if _state.get('recon_key') != key:
+        _engine().load_recon(net.state_dict()); _state['recon_key'] = key
+
+
+def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules: Optional[Dict[str, object]] = None) -> None:
+    """Patch the reference modules in sys.path (or the ones passed in `modules`, keyed by dotted name)."""
+    if _originals:
+        return
+    _state['engine'] = engine
+    get = (lambda name: modules[name]) if modules else importlib.import_module
+    arch_avatar = get('network.arch_avatar'); arch_recon = get('network.arch_recon')
+    recon_util = get('utils.recon_util'); smpl_util_mod = get('utils.smpl_util')
+
+    def keep(owner, name):
+        _originals[owner.__name__ + '.' + name] = (owner, name, getattr(owner, name))
+        return getattr(owner, name)
+
+    o_query = keep(arch_avatar.OccupancyNet, 'query')
+    def query(self, batch):
+        if torch.is_grad_enabled():
+            return o_query(self, batch)
+        _avatar_loaded(self.net)
+        return api.occupancy_query(_engine(), batch, self.net.warping_field.pose_feat_map, impl=impl)
+    arch_avatar.OccupancyNet.query = query
+
+    o_wq = keep(arch_avatar.WarpingField, 'query')
+    def wquery(self, pts, batch):
+        if torch.is_grad_enabled() or _state.get('avatar_key') is None:
+            return o_wq(self, pts, batch)
+        return api.warping_field_query(_engine(), pts, batch, self.pose_feat_map, impl=impl)
+    arch_avatar.WarpingField.query = wquery
+
+    o_tf = keep(arch_avatar.DoubleTNet, 'forward')
+    def tforward(self, pts):
+        if torch.is_grad_enabled() or _state.get('avatar_key') is None:
+            return o_tf(self, pts)
+        return api.template_forward(_engine(), pts, impl=impl)
+    arch_avatar.DoubleTNet.forward = tforward
+
+    o_gf = keep(arch_avatar.GeoTexAvatar, 'forward')
+    def gforward(self, wpts, viewdirs, dists, batch, pts_space='posed'):
+        if torch.is_grad_enabled():
+            return o_gf(self, wpts, viewdirs, dists, batch, pts_space)
+        _avatar_loaded(self)
+        su = smpl_util_mod.smpl_util
+        wv = self.cano_weight_volume.base_weight_volume[0].permute(1, 2, 3, 0).contiguous()      # (X,Y,Z,24)
+        return api.geotex_forward(_engine(), wpts, dists, batch, self.warping_field.pose_feat_map, su.smpl_skinning_weights,
+                                  su.cano_smpl_vertices, wv, pts_space, impl=impl)
+    arch_avatar.GeoTexAvatar.forward = gforward
+
+    o_inf = keep(arch_recon.ReconNetwork, 'infer')
+    def infer(self, items):
+        with torch.no_grad():
+            _recon_loaded(self)
+            imgs = torch.cat([items['front_normal'], items['back_normal']], dim=1)            # arch_recon.py:51
+            fmap = self.get_feat_maps(imgs)[-1]                                                 # HGFilter stays in PyTorch
+            return api.recon_infer(_engine(), items, fmap, impl=impl)
+    arch_recon.ReconNetwork.infer = infer
+
+    o_rm = keep(recon_util, 'recon_mesh')
+    def recon_mesh(occ_volume, volume_res, bounds, iso_value=0.5):
+        return api.recon_mesh(_engine(), occ_volume, volume_res, bounds, iso_value)
+    recon_util.recon_mesh = recon_mesh
+
+    SU = smpl_util_mod.SmplUtil
+    o_lbs = keep(SU, 'calculate_lbs'); o_sk = keep(SU, 'skinning'); o_sn = keep(SU, 'skinning_normal')
+    def calculate_lbs(self, points):
+        if torch.is_grad_enabled() and points.requires_grad:
+            return o_lbs(self, points)
+        if self.cano_smpl_vertices is None:
+            raise ValueError('Canonical smpl vertices are invalid!')
+        e = _engine()
+        return torch.stack([e.lbs_weights(points[b], self.cano_smpl_vertices, self.smpl_skinning_weights) for b in range(points.shape[0])], 0)
+    def skinning(self, points, lbs, jnt_mats, return_pt_mats=False):
+        if torch.is_grad_enabled() and (points.requires_grad or lbs.requires_grad):
+            return o_sk(self, points, lbs, jnt_mats, return_pt_mats)
+        e = _engine()
+        outs = [e.skin_points(points[b], lbs[b], jnt_mats[b], return_pt_mats) for b in range(points.shape[0])]
+        if return_pt_mats:
+            return torch.stack([o[0] for o in outs], 0), torch.stack([o[1] for o in outs], 0)
+        return torch.stack(outs, 0)
+    def skinning_normal(self, normals, lbs, cano2live_jnt_mats):
+        if torch.is_grad_enabled() and (normals.requires_grad or lbs.requires_grad):
+            return o_sn(self, normals, lbs, cano2live_jnt_mats)
+        e = _engine()
+        return torch.stack([e.skin_normals(normals[b], lbs[b], cano2live_jnt_mats[b]) for b in range(normals.shape[0])], 0)
+    SU.calculate_lbs = calculate_lbs; SU.skinning = skinning; SU.skinning_normal = skinning_normal
+
+
+def uninstall() -> None:
+    for owner, name, fn in _originals.values():
+        setattr(owner, name, fn)
+    _originals.clear(); _state.clear()

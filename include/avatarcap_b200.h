@@ -1,0 +1,179 @@
+/*
+ * avatarcap_b200 -- C ABI of the B200-native implementation of AvatarCap's dense implicit-surface path.
+ *
+ * The reference (lizhe00/AvatarCap) has no FFI: its seams are Python call sites. Each entry point below
+ * names the reference call (file:line, relative to the reference root) whose arithmetic it replaces; the
+ * Python mirror that re-binds those call sites lives in avatarcap_b200/patch.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative AVC_E* code otherwise; avc_last_error() gives the text.
+ *     No C++ exception crosses this boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Work is enqueued
+ *     asynchronously on it; functions that must return a data-dependent count say that they synchronise it.
+ *   - pointers marked [dev] are device pointers on the context's device, caller-owned, never retained past
+ *     the call (exception: avc_set_feature_map copies into a library-owned buffer). [host] pointers are
+ *     ordinary host memory.
+ *   - all floating-point data is IEEE float32; points are (n,3) row-major xyz; volumes are (Rx,Ry,Rz)
+ *     row-major with z fastest, i.e. flat = (i*Ry + j)*Rz + k  (dataset/avatarcap_dataset.py:317-321, main.py:364).
+ *   - one context per device; a context is not re-entrant.
+ */
+#ifndef AVATARCAP_B200_H
+#define AVATARCAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVC_OK            0
+#define AVC_EINVAL       -1   /* bad argument (NULL pointer, bad shape, bad flag)              */
+#define AVC_ECUDA        -2   /* a CUDA runtime call or kernel launch failed                   */
+#define AVC_ESTATE       -3   /* missing prerequisite (weights / feature map not loaded)       */
+#define AVC_ECAPACITY    -4   /* caller-provided output capacity too small (never truncates)   */
+#define AVC_EFORMAT      -5   /* weight blob malformed / wrong architecture                    */
+#define AVC_EVALUE       -6   /* value error mirrored from the reference (e.g. iso outside the volume's range) */
+
+typedef struct avc_ctx avc_ctx;
+
+/* which implementation of the field evaluation to run */
+#define AVC_IMPL_AUTO   0     /* tensor-core kernel when available, else SIMT                  */
+#define AVC_IMPL_SIMT   1     /* fp32 CUDA-core kernel (bit-near the reference's fp32 math)    */
+#define AVC_IMPL_TC     2     /* tcgen05 kernel, fp16 hi/lo split operands, fp32 accumulate     */
+
+/* implicit-field type, config.py:12-22 */
+#define AVC_IF_SDF        0
+#define AVC_IF_OCCUPANCY  1
+
+/* feature-map slots */
+#define AVC_MAP_POSE   0      /* WarpingField.pose_feat_map, (64,H,W)  arch_avatar.py:109-111   */
+#define AVC_MAP_IMAGE  1      /* ReconNetwork HGFilter output, (32,H,W) arch_recon.py:51-52     */
+
+/* ---------------------------------------------------------------------------------------------- */
+/* context                                                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+int  avc_ctx_create(int device, avc_ctx** out);
+void avc_ctx_destroy(avc_ctx* ctx);
+/* text of the last error on this context (or of the last failed avc_ctx_create when ctx == NULL) */
+const char* avc_last_error(const avc_ctx* ctx);
+/* ABI version of the library (bumped on any signature change) */
+int  avc_abi_version(void);
+/* 1 if the tcgen05 kernels were compiled in and the device is sm_100 */
+int  avc_has_tensor_core_path(const avc_ctx* ctx);
+/* number of kernel launches issued by this context since creation / last reset (for bench.py's gpu_launches) */
+int64_t avc_launch_count(const avc_ctx* ctx);
+void    avc_reset_launch_count(avc_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* weights -- replaces torch.load(...)['network'] + nn.Module parameters (main.py:302-320)        */
+/* The blob is produced by avatarcap_b200.packer from the reference's state_dict:
+ * BatchNorm(eval) and weight-norm folded into a per-channel scale/bias, skip-concat columns reordered,
+ * K padded to the MMA granule, fp16 hi/lo planes in the tcgen05 canonical K-major core-matrix layout.
+ * The library copies it ([host] pointer) into device memory it owns.                               */
+/* ---------------------------------------------------------------------------------------------- */
+int avc_load_avatar_weights(avc_ctx* ctx, const void* blob /*[host]*/, size_t nbytes);
+int avc_load_recon_weights(avc_ctx* ctx, const void* blob /*[host]*/, size_t nbytes);
+
+/* per-frame encoder output (stays in PyTorch; WarpingField.precompute_conv arch_avatar.py:109-111,
+ * ReconNetwork.get_feat_maps arch_recon.py:41-43). `chw` is a [dev] (C,H,W) float32 tensor; the library
+ * transposes it into an owned (H,W,C) copy so that one bilinear tap is one contiguous read.            */
+int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw /*[dev]*/, int C, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* field evaluation                                                                               */
+/* ---------------------------------------------------------------------------------------------- */
+/* OccupancyNet.query (arch_avatar.py:356-381): off = WarpingField.query(p) (:113-140); (rgb,alpha,occ) =
+ * DoubleTNet.forward(p + off) (:65-83). out_occ (n) is required; out_off (n,3), out_rgb (n,3), out_alpha (n)
+ * may be NULL (the colour head is skipped when both out_rgb and out_alpha... see below are NULL).
+ * out_alpha is relu(geo[1]) as DoubleTNet.forward returns it. if_type selects raw / sigmoid occupancy.     */
+int avc_eval_occupancy(avc_ctx* ctx, const float* pts /*[dev] (n,3)*/, int64_t n, const float center[3] /*[host]*/,
+                       float* out_occ /*[dev]*/, float* out_off /*[dev]|NULL*/, float* out_rgb /*[dev]|NULL*/,
+                       float* out_alpha /*[dev]|NULL*/, int if_type, int impl, void* stream);
+
+/* WarpingField.query alone (arch_avatar.py:113-140): offsets (n,3) */
+int avc_eval_warp(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, const float center[3] /*[host]*/,
+                  float* out_off /*[dev] (n,3)*/, int impl, void* stream);
+
+/* DoubleTNet.forward alone (arch_avatar.py:65-83): rgb (n,3), alpha (n), occ (n); any output may be NULL */
+int avc_eval_template(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, float* out_rgb, float* out_alpha,
+                      float* out_occ, int if_type, int impl, void* stream);
+
+/* ReconNetwork.infer, per-point part (arch_recon.py:55-76): out_ov (n) = sigmoid(decoder([feat(x,-y), z])) */
+int avc_eval_recon(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, const float center[3] /*[host]*/,
+                   float* out_ov /*[dev]*/, int impl, void* stream);
+
+/* Same as avc_eval_occupancy / avc_eval_recon with HOST buffers: pinned staging, H2D, kernels and D2H are
+ * pipelined on internal streams and the call returns when the host outputs are complete. This is the
+ * end-to-end entry bench.py times as `e2e`.                                                              */
+int avc_eval_occupancy_host(avc_ctx* ctx, const float* pts /*[host]*/, int64_t n, const float center[3],
+                            float* out_occ /*[host]*/, float* out_off /*[host]|NULL*/, int if_type, int impl);
+int avc_eval_recon_host(avc_ctx* ctx, const float* pts /*[host]*/, int64_t n, const float center[3],
+                        float* out_ov /*[host]*/, int impl);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* grid, mask scatter                                                                             */
+/* ---------------------------------------------------------------------------------------------- */
+/* generate_volume_points (dataset/avatarcap_dataset.py:312-326): out (Rx*Ry*Rz,3), z fastest.
+ * x_first / x_count select a slab of i-planes [x_first, x_first+x_count) (multi-GPU sharding); the
+ * coordinates are those of the full grid.                                                         */
+int avc_make_grid(avc_ctx* ctx, const float bounds[6] /*[host] min xyz, max xyz*/, const int res[3],
+                  int x_first, int x_count, float* out_pts /*[dev]*/, void* stream);
+
+/* main.py:357,362-364 / 438,442-443: vol[flag] = vals (in order); vol[~flag] = fill (in order).
+ * flag: n_total bytes (bool); vals: count(flag) floats; fill: n_total - count(flag) floats.            */
+int avc_scatter_fill(avc_ctx* ctx, const uint8_t* flag /*[dev]*/, int64_t n_total, const float* vals /*[dev]*/,
+                     const float* fill /*[dev]*/, float* out_vol /*[dev]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* mesh extraction -- replaces recon_util.recon_mesh (utils/recon_util.py:51-70), including the
+ * skimage marching cubes call (:64), the Sobel normal volume (:9-29) and its trilinear sampling (:32-48).
+ * vol: [dev] (Rx,Ry,Rz). Outputs are in the reference's coordinates and conventions: vertices already
+ * shifted by bounds[0] + 0.5*voxel (:65), normals negated (:68), faces column-reversed (:69).
+ * Vertex order: ascending (owner voxel linear index, axis); face order: ascending (cell, case-table slot).
+ * x_halo_lo / x_halo_hi: number of leading / trailing i-planes of `vol` that are halo only (multi-GPU slabs):
+ * cells and vertices are emitted for owner voxels with x_halo_lo <= i < Rx - x_halo_hi, but the Sobel
+ * stencil reads the halo. x_origin is the global index of plane 0 and gres_x the global Rx (for coordinates;
+ * pass 0 and res[0] for a whole volume).
+ * Two-phase: avc_mc_count synchronises `stream` and returns the counts; avc_mc_emit fills caller buffers
+ * and fails with AVC_ECAPACITY (nothing written) if they are too small.                                   */
+int avc_mc_count(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], float iso, int x_halo_lo, int x_halo_hi,
+                 int64_t* n_verts /*[host]*/, int64_t* n_faces /*[host]*/, void* stream);
+int avc_mc_emit(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], const float bounds[6] /*[host]*/, float iso,
+                int x_halo_lo, int x_halo_hi, int x_origin, int gres_x,
+                float* verts /*[dev] (cap_v,3)*/, float* normals /*[dev] (cap_v,3)|NULL*/, int32_t* faces /*[dev] (cap_f,3)*/,
+                int64_t cap_v, int64_t cap_f, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* LBS -- replaces utils/smpl_util.py and the pytorch3d KNN it calls                              */
+/* ---------------------------------------------------------------------------------------------- */
+/* pytorch3d.ops.knn_points (K<=4) against a small reference set (m <= 16384): squared L2 ascending.
+ * out_d2 (n,K) float, out_idx (n,K) int64 (either may be NULL).                                        */
+int avc_knn(avc_ctx* ctx, const float* query /*[dev] (n,3)*/, int64_t n, const float* ref /*[dev] (m,3)*/, int m, int K,
+            float* out_d2 /*[dev]*/, int64_t* out_idx /*[dev]*/, void* stream);
+/* SmplUtil.calculate_lbs (smpl_util.py:24-39): out (n,24) */
+int avc_lbs_weights(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, const float* cano_verts /*[dev] (m,3)*/, int m,
+                    const float* skin_weights /*[dev] (m,24)*/, float* out_lbs /*[dev] (n,24)*/, void* stream);
+/* SmplUtil.skinning (smpl_util.py:58-74): out_pts (n,3), out_mats (n,4,4) or NULL */
+int avc_skin_points(avc_ctx* ctx, const float* pts /*[dev]*/, const float* lbs /*[dev] (n,24)*/,
+                    const float* jnt_mats /*[dev] (24,4,4)*/, int64_t n, float* out_pts, float* out_mats, void* stream);
+/* SmplUtil.skinning_normal (smpl_util.py:76-81): rotation block only */
+int avc_skin_normals(avc_ctx* ctx, const float* normals /*[dev]*/, const float* lbs /*[dev]*/,
+                     const float* jnt_mats /*[dev]*/, int64_t n, float* out_normals, void* stream);
+/* fused calculate_lbs + skinning (+ normals): what main.py:385-389 / 451-453 do per mesh */
+int avc_skin_mesh(avc_ctx* ctx, const float* verts /*[dev]*/, const float* normals /*[dev]|NULL*/, int64_t n,
+                  const float* cano_verts /*[dev]*/, int m, const float* skin_weights /*[dev]*/,
+                  const float* jnt_mats /*[dev]*/, float* out_verts, float* out_normals /*|NULL*/, void* stream);
+/* posed -> canonical warp of GeoTexAvatar.forward (arch_avatar.py:189-205): KNN-1 vs live SMPL, gather skin
+ * weights, inverse LBS, normalise to bounds, trilinear sample of the (X,Y,Z,24) blend-weight volume
+ * (CanoBlendWeightVolume.forward :152-165), inverse LBS again. live2cano = inv(cano2live) is computed by the caller.
+ * out_cano (n,3); out_near (n) uint8 = (d2 < 0.08^2).                                                     */
+int avc_posed_to_cano(avc_ctx* ctx, const float* wpts /*[dev]*/, int64_t n, const float* live_verts /*[dev] (m,3)*/, int m,
+                      const float* skin_weights /*[dev] (m,24)*/, const float* live2cano_mats /*[dev] (24,4,4)*/,
+                      const float bounds[6] /*[host]*/, const float* weight_volume /*[dev] (X,Y,Z,24)*/, const int vdims[3],
+                      float* out_cano /*[dev]*/, uint8_t* out_near /*[dev]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVATARCAP_B200_H */
