@@ -34,7 +34,7 @@ SIGNATURES = {
     'avc_eval_warp': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _i, _vp]),
     'avc_eval_template': (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp]),
     'avc_eval_recon': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _i, _vp]),
-    'avc_eval_occupancy_host': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _vp, _i, _i]),
+    'avc_eval_occupancy_host': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _vp, _vp, _vp, _i, _i]),
     'avc_eval_recon_host': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _i]),
     'avc_make_grid': (_i, [_vp, C.POINTER(_f), C.POINTER(_i), _i, _i, _vp, _vp]),
     'avc_scatter_fill': (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -204,7 +204,7 @@ extern "C" int avc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const f
 
 // -----------------------------------------------------------------------------------------------------------------
 // Host-buffer variants: chunked, double-buffered  H2D -> kernel -> D2H  on three internal streams.
-// Staging layout per slot: pts (chunk,3) | occ (chunk) | off (chunk,3)  in pinned host memory and in device memory.
+// Staging layout per slot: pts (chunk,3) | occ (chunk) | off (chunk,3) | rgb (chunk,3) | alpha (chunk)  in pinned host and device memory.
 static int ensure_staging(avc_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->pinned_cap && bytes <= ctx->stage_cap) return AVC_OK;
   if (ctx->h_pinned) { cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->pinned_cap = 0; }
@@ -214,14 +214,14 @@ static int ensure_staging(avc_ctx* ctx, size_t bytes) {
   return AVC_OK;
 }
 
-static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, const float center[3], float* out_a, float* out_off, int if_type,
-                     int impl) {
+static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, const float center[3], float* out_a, float* out_off, float* out_rgb,
+                     float* out_alpha, int if_type, int impl) {
   if (!ctx) return AVC_EINVAL;
   if (n < 0 || (n > 0 && (!pts || !out_a)) || !center) return avc_fail(ctx, AVC_EINVAL, "host eval: bad argument");
   if (n == 0) return AVC_OK;
   AVC_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t chunk = 1 << 21;                       // 2 Mi points per pipeline slot (24 MB in, 8..32 MB out)
-  const size_t slot_floats = (size_t)chunk * 7;
+  const size_t slot_floats = (size_t)chunk * 11;
   int rc = ensure_staging(ctx, 2 * slot_floats * sizeof(float));
   if (rc) return rc;
   cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
@@ -237,6 +237,8 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
       float* hp = (float*)ctx->h_pinned + (size_t)s * slot_floats;
       memcpy(out_a + b, hp + (size_t)chunk * 3, (size_t)m * sizeof(float));
       if (out_off) memcpy(out_off + b * 3, hp + (size_t)chunk * 4, (size_t)m * 3 * sizeof(float));
+      if (out_rgb) memcpy(out_rgb + b * 3, hp + (size_t)chunk * 7, (size_t)m * 3 * sizeof(float));
+      if (out_alpha) memcpy(out_alpha + b, hp + (size_t)chunk * 10, (size_t)m * sizeof(float));
     }
     if (c < n_chunks) {
       const int s = (int)(c & 1); const int64_t b = c * chunk; const int64_t m = (n - b < chunk) ? n - b : chunk;
@@ -247,13 +249,17 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
       cudaEventRecord(ev_in[s], ctx->s_copy_in);
       cudaStreamWaitEvent(ctx->s_compute, ev_in[s], 0);
       float* d_occ = dp + (size_t)chunk * 3; float* d_off = dp + (size_t)chunk * 4;
+      float* d_rgb = dp + (size_t)chunk * 7; float* d_alpha = dp + (size_t)chunk * 10;
       status = recon ? avc_eval_recon(ctx, dp, m, center, d_occ, impl, ctx->s_compute)
-                     : avc_eval_occupancy(ctx, dp, m, center, d_occ, out_off ? d_off : nullptr, nullptr, nullptr, if_type, impl, ctx->s_compute);
+                     : avc_eval_occupancy(ctx, dp, m, center, d_occ, out_off ? d_off : nullptr, out_rgb ? d_rgb : nullptr,
+                                          out_alpha ? d_alpha : nullptr, if_type, impl, ctx->s_compute);
       if (status != AVC_OK) break;
       cudaEventRecord(ev_k[s], ctx->s_compute);
       cudaStreamWaitEvent(ctx->s_copy_out, ev_k[s], 0);
       cudaMemcpyAsync(hp + (size_t)chunk * 3, d_occ, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       if (out_off) cudaMemcpyAsync(hp + (size_t)chunk * 4, d_off, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      if (out_rgb) cudaMemcpyAsync(hp + (size_t)chunk * 7, d_rgb, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      if (out_alpha) cudaMemcpyAsync(hp + (size_t)chunk * 10, d_alpha, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       cudaEventRecord(ev_out[s], ctx->s_copy_out);
       // the next use of this slot's device buffer (chunk c+2) must wait for this D2H
       cudaStreamWaitEvent(ctx->s_copy_in, ev_out[s], 0);
@@ -266,9 +272,9 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
 }
 
 extern "C" int avc_eval_occupancy_host(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
-                                       int if_type, int impl) {
-  return eval_host(ctx, false, pts, n, center, out_occ, out_off, if_type, impl);
+                                       float* out_rgb, float* out_alpha, int if_type, int impl) {
+  return eval_host(ctx, false, pts, n, center, out_occ, out_off, out_rgb, out_alpha, if_type, impl);
 }
 extern "C" int avc_eval_recon_host(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, int impl) {
-  return eval_host(ctx, true, pts, n, center, out_ov, nullptr, AVC_IF_SDF, impl);
+  return eval_host(ctx, true, pts, n, center, out_ov, nullptr, nullptr, nullptr, AVC_IF_SDF, impl);
 }

@@ -158,12 +158,15 @@ class Engine:
 
     # ------------------------------------------------------------------ host-buffer (end-to-end) entry points
     def eval_occupancy_host(self, pts_host: np.ndarray, center, out_occ: np.ndarray, out_off: Optional[np.ndarray] = None,
+                            out_rgb: Optional[np.ndarray] = None, out_alpha: Optional[np.ndarray] = None,
                             if_type: str = 'sdf', impl: Optional[str] = None) -> None:
         assert pts_host.dtype == np.float32 and pts_host.flags.c_contiguous and out_occ.dtype == np.float32
         n = pts_host.shape[0]
         self._check(self.lib.avc_eval_occupancy_host(self._h, pts_host.ctypes.data_as(C.c_void_p), n, _lib.f3(center),
                                                      out_occ.ctypes.data_as(C.c_void_p),
                                                      None if out_off is None else out_off.ctypes.data_as(C.c_void_p),
+                                                     None if out_rgb is None else out_rgb.ctypes.data_as(C.c_void_p),
+                                                     None if out_alpha is None else out_alpha.ctypes.data_as(C.c_void_p),
                                                      IF_SDF if if_type == 'sdf' else IF_OCCUPANCY, self._impl(impl)))
 
     def eval_recon_host(self, pts_host: np.ndarray, center, out_ov: np.ndarray, impl: Optional[str] = None) -> None:

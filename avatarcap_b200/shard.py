@@ -43,3 +43,28 @@ def merge_meshes(parts: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]]):
     verts = np.concatenate([p[0] for p in parts], 0)
     normals = np.concatenate([p[2] for p in parts], 0) if parts[0][2] is not None else None
     return verts, np.concatenate(faces, 0).astype(np.int32), normals
+
+
+def exchange_halo(slab, rank: int, world: int, rx: int):
+    """The path's one exchange step: a single all-gather of each rank's boundary planes (first HALO_HI, last HALO_LO),
+    after which every rank holds [lo halo | own planes | hi halo] (NCCL over NVLink on GPUs, gloo in the CPU tests).
+    `slab` is this rank's (nx, Ry, Rz) block of the volume; nx >= HALO_HI is required."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return slab
+    nx = slab.shape[0]
+    if nx < HALO_HI:
+        raise ValueError('slab of %d planes is thinner than the halo (%d)' % (nx, HALO_HI))
+    send = torch.cat([slab[:HALO_HI], slab[nx - HALO_LO:]], 0).contiguous()          # (HALO_HI + HALO_LO, Ry, Rz)
+    gathered = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(gathered, send)
+    start, end = slab_range(rx, world, rank)
+    lo, hi = halo_planes(rx, start, end)
+    parts = []
+    if lo:
+        parts.append(gathered[rank - 1][HALO_HI + (HALO_LO - lo):])                 # previous rank's last `lo` planes
+    parts.append(slab)
+    if hi:
+        parts.append(gathered[rank + 1][:hi])                                       # next rank's first `hi` planes
+    return torch.cat(parts, 0).contiguous()

@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- Mpoints/s of the dense implicit-field evaluation at 256^3 per GPU (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W                 # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference algorithm's CPU port (oracle), rank 0 only
+
+A "step" is one pass of the hot path over one batch of synthetic input: OccupancyNet.query + the texture head
+(BASELINE config[1]: warp MLP -> template MLP -> occ, offsets, rgb, alpha) over this rank's slab of the grid, all
+16 777 216 points of it, inputs already resident in HBM. N>1 shards the x axis of a proportionally larger grid
+(N=8: 512^3, BASELINE config[3]) with no data-path collective in the field evaluation ("weak" scaling); the one
+exchange step of the path (boundary planes for marching cubes) is timed separately as `mesh_extract_ms`.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PT = {'occ': 1_773_568, 'occ+tex': 1_970_944, 'recon': 387_072}     # SURVEY.md section 8 / BASELINE.md section 2
+GRIDS = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512, 512, 512)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index; self.samples = []; self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set(); self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace('.', '').isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            for nm, v in zip(names, s[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.samples)}
+
+
+def cpu_reference_rate(scene, pts: np.ndarray, seconds_budget: float, threads: int):
+    """Times the oracle port of OccupancyNet.query + texture head on `pts` (bounded sample). -> (Mpts/s, n_used, secs)."""
+    import torch
+    from oracle import field_oracle as fo
+    torch.set_num_threads(threads)
+    probe = pts[:16384]
+    t0 = time.perf_counter()
+    fo.occupancy_query(scene['avatar_sd'], probe, scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)
+    rate = len(probe) / (time.perf_counter() - t0)
+    n = int(min(len(pts), max(16384, rate * seconds_budget)))
+    sample = pts[:n]
+    t0 = time.perf_counter()
+    fo.occupancy_query(scene['avatar_sd'], sample, scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)
+    dt = time.perf_counter() - t0
+    return n / dt / 1e6, n, dt
+
+
+def build_scene():
+    from avatarcap_b200 import synth
+    body = synth.SynthBody()
+    frame = synth.make_frame(body, None)            # T-pose live body (BASELINE configs 1-4)
+    return {'body': body, 'frame': frame, 'avatar_sd': synth.avatar_state_dict(),
+            'pose_map': synth.feature_map(64, 256, 256, synth.SEED + 4)}
+
+
+def strided_sample(scene, res, count):
+    """`count` points of the full grid, spread evenly (the CPU arms evaluate the same workload, subsampled)."""
+    from avatarcap_b200 import synth
+    # regular sub-lattice of the grid keeps the spatial distribution of the full workload
+    n = int(round(count ** (1 / 3)))
+    sub = tuple(max(2, min(r, n)) for r in res)
+    return synth.volume_points(scene['frame']['cano_bounds'], sub)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    scene = build_scene()
+    res = GRIDS[args.gpus]
+    threads = os.cpu_count() or 1
+    total_budget = 150.0
+    per_step = total_budget / max(1, args.steps + args.warmup)
+    pts = strided_sample(scene, res, 64 ** 3)
+    import torch
+    from oracle import field_oracle as fo
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    fo.occupancy_query(scene['avatar_sd'], pts[:8192], scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)
+    rate = 8192 / (time.perf_counter() - t0)
+    n = int(min(len(pts), max(8192, rate * per_step)))
+    sample = pts[:n]
+    for _ in range(args.warmup):
+        fo.occupancy_query(scene['avatar_sd'], sample, scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fo.occupancy_query(scene['avatar_sd'], sample, scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt / 1e6
+    line = {
+        'impl': 'reference', 'metric': 'Mpoints/s implicit-field eval @256^3 per GPU (occupancy+texture)', 'value': value, 'unit': 'Mpoints/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'OccupancyNet.query + texture head over a dense %dx%dx%d canonical grid (BASELINE config[1]); '
+                               'reference arm: CPU port of the reference algorithm on a bounded %d-point sub-lattice per step' % (res + (n,)),
+                   'grid': list(res), 'points_per_step': n},
+        'cpu_baseline': {'value': value, 'unit': 'Mpoints/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d-point sub-lattice of the grid per step, torch CPU f32, %d threads' % (n, threads)},
+        'e2e': {'value': value, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from avatarcap_b200.engine import Engine
+    from avatarcap_b200 import shard
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    eng = Engine(dev)
+    impl = args.kernel
+    if impl == 'auto':
+        impl = 'tc' if eng.has_tensor_core_path else 'simt'
+    scene = build_scene()
+    frame = scene['frame']
+    eng.load_avatar(scene['avatar_sd']); eng.set_pose_feature_map(scene['pose_map'])
+    res = GRIDS[args.gpus] if args.res is None else (args.res * (2 if args.gpus >= 2 else 1), args.res * (2 if args.gpus >= 4 else 1), args.res * (2 if args.gpus >= 8 else 1))
+    x0, x1 = shard.slab_range(res[0], world, rank)
+    pts = eng.make_grid(frame['cano_bounds'], res, x0, x1 - x0)          # resident in HBM; 201 MB > L2 (126 MB)
+    n = pts.shape[0]
+    center = frame['cano_smpl_center']
+    n_out = {'occ': None}
+
+    def step():
+        n_out['o'] = eng.eval_occupancy(pts, center, want_offsets=True, want_texture=True, impl=impl)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    eng.reset_launch_count()
+    sampler = ClockSampler(local); sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for a, b in evs:
+        a.record(); step(); b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    launches = eng.launch_count
+    total_ms = evs[0][0].elapsed_time(evs[-1][1])
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    t = torch.tensor([total_ms, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(t[0]), float(t[1])
+    n_all = n
+    if world > 1:
+        nt = torch.tensor([n], device=dev, dtype=torch.int64); dist.all_reduce(nt); n_all = int(nt[0])
+    value = n_all * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- mesh extraction (ms/frame): halo exchange (the path's one collective) + marching cubes + normals, per shard
+    occ = n_out['o']['occ'].reshape(x1 - x0, res[1], res[2])
+    lo, hi = shard.halo_planes(res[0], x0, x1)
+
+    def mesh_step():
+        vol = shard.exchange_halo(occ, rank, world, res[0]) if world > 1 else occ
+        return eng.extract_mesh(vol, frame['cano_bounds'], 0.0, True, lo, hi, x0 - lo, res[0])
+
+    mesh_step(); barrier()
+    m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
+    m0.record()
+    reps = 3
+    for _ in range(reps):
+        v, f, nrm = mesh_step()
+    m1.record(); barrier()
+    mesh_ms = m0.elapsed_time(m1) / reps
+    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    cv = torch.from_numpy(frame['cano_smpl_v']).to(dev); sw = torch.from_numpy(frame['smpl_skinning_weights']).to(dev)
+    jm = torch.from_numpy(frame['cano2live_jnt_mats']).to(dev)
+    eng.skin_mesh(v, nrm, cv, sw, jm); torch.cuda.synchronize()
+    s0.record(); eng.skin_mesh(v, nrm, cv, sw, jm); s1.record(); torch.cuda.synchronize()
+    lbs_ms = s0.elapsed_time(s1)
+    mt = torch.tensor([mesh_ms, lbs_ms], device=dev, dtype=torch.float64)
+    nv = torch.tensor([v.shape[0], f.shape[0]], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(mt, op=dist.ReduceOp.MAX); dist.all_reduce(nv)
+
+    # ---- end to end through the host-buffer C-ABI entry: H2D of the points and D2H of every output inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pts_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        pts_h.copy_(pts.cpu())
+        occ_h = np.empty(n, np.float32); off_h = np.empty((n, 3), np.float32); rgb_h = np.empty((n, 3), np.float32); al_h = np.empty(n, np.float32)
+        ph = pts_h.numpy()
+        eng.eval_occupancy_host(ph, center, occ_h, off_h, rgb_h, al_h, impl=impl)       # warm-up
+        barrier()
+        k2 = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            eng.eval_occupancy_host(ph, center, occ_h, off_h, rgb_h, al_h, impl=impl)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {'value': n_all * k2 / float(tt[0]) / 1e6, 'unit': 'Mpoints/s', 'h2d_bytes_per_step': int(n_all * 12),
+               'd2h_bytes_per_step': int(n_all * 32), 'steps': k2, 'api': 'avc_eval_occupancy_host (pinned staging, 3-stream pipeline)'}
+        assert float(np.abs(occ_h - n_out['o']['occ'].cpu().numpy()).max()) == 0.0
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        flop = FLOP_PER_PT['occ+tex']
+        ach = n * flop / (kernel_ms * 1e-3) / 1e12
+        peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
+        line = {
+            'metric': 'Mpoints/s implicit-field eval @256^3 per GPU (occupancy+texture)', 'value': value, 'unit': 'Mpoints/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16x2 split operands (hi/lo, 3 MMA passes), f32 accumulate' if impl == 'tc' else 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'OccupancyNet.query + texture head (warp MLP, template MLP, geo + colour heads) over a dense '
+                                   '%dx%dx%d canonical grid, x-slabs over %d GPU(s); BASELINE config[1] per GPU' % (res + (world,)),
+                       'grid': list(res), 'points_per_gpu': n, 'kernel': impl, 'flop_per_point': flop,
+                       'l2_policy': 'inputs (201 MB of points) + outputs (537 MB) exceed the 126 MB L2 every step'},
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                         'traffic': None, 'peak_source': peak_src + ', sustained bf16 (kernel timed inside a long step)',
+                         'note': 'algorithmic FLOPs (1x); the tcgen05 kernel issues 3x that as fp16 hi/lo passes'},
+            'mesh_extract_ms': float(mt[0]), 'lbs_skin_ms': float(mt[1]), 'mesh_vertices': int(nv[0]), 'mesh_faces': int(nv[1]),
+            'clocks': clocks, 'gpu_launches': int(launches), 'wall_s': t_wall,
+        }
+        if e2e:
+            line['e2e'] = e2e
+        if args.gpus == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sub = strided_sample(scene, res, 64 ** 3)
+            v_cpu, n_cpu, secs = cpu_reference_rate(scene, sub, 12.0, threads)
+            line['cpu_baseline'] = {'value': v_cpu, 'unit': 'Mpoints/s', 'cores': threads, 'kind': 'port',
+                                    'sample': '%d-point sub-lattice of the same grid, %.1f s, torch CPU f32 oracle port' % (n_cpu, secs)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--res', type=int, default=None, help='override the per-GPU grid edge (debug only; the metric is quoted at 256)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.gpus not in GRIDS:
+        raise SystemExit('--gpus must be one of 1, 2, 4, 8')
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -107,7 +107,8 @@ int avc_eval_recon(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, const fl
  * pipelined on internal streams and the call returns when the host outputs are complete. This is the
  * end-to-end entry bench.py times as `e2e`.                                                              */
 int avc_eval_occupancy_host(avc_ctx* ctx, const float* pts /*[host]*/, int64_t n, const float center[3],
-                            float* out_occ /*[host]*/, float* out_off /*[host]|NULL*/, int if_type, int impl);
+                            float* out_occ /*[host]*/, float* out_off /*[host]|NULL*/, float* out_rgb /*[host]|NULL*/,
+                            float* out_alpha /*[host]|NULL*/, int if_type, int impl);
 int avc_eval_recon_host(avc_ctx* ctx, const float* pts /*[host]*/, int64_t n, const float center[3],
                         float* out_ov /*[host]*/, int impl);
 

@@ -1,0 +1,179 @@
+"""CPU: host-side logic -- packer layout, ABI surface, slab sharding / halo exchange (gloo, world_size 2), MC tables."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from avatarcap_b200 import packer, synth, shard, mc_tables
+from helpers import ROOT
+
+
+def test_packer_layout_and_folding():
+    sd = synth.avatar_state_dict()
+    blob = packer.pack_avatar(sd)
+    h = packer.parse_header(blob)
+    assert h['magic'] == packer.MAGIC and h['n_layers'] == 20 and h['kind'] == packer.KIND_AVATAR
+    f32 = np.frombuffer(blob, np.float32, h['f32_bytes'] // 4, h['f32_off'])
+    # layer 4 = conv5: concat order input(67) FIRST then x4(256)  (mlp.py:106)
+    L = h['layers'][4]
+    assert (L['k0'], L['k1'], L['k0p'], L['k1p'], L['n']) == (67, 256, 80, 256, 256)
+    W = sd['warping_field.mlp.conv5.weight'][:, :, 0]
+    Wt = f32[L['wt_off']:L['wt_off'] + 323 * 256].reshape(323, 256)
+    assert np.array_equal(Wt, W.T)
+    # BN fold: scale*(Wx) + bias == BN(Wx + b)
+    x = np.random.RandomState(0).normal(0, 1, 323).astype(np.float64)
+    y_ref = (W.astype(np.float64) @ x + sd['warping_field.mlp.conv5.bias'] - sd['warping_field.mlp.bn5.running_mean']) / \
+        np.sqrt(sd['warping_field.mlp.bn5.running_var'].astype(np.float64) + 1e-5) * sd['warping_field.mlp.bn5.weight'] + sd['warping_field.mlp.bn5.bias']
+    sc = f32[L['sb_off']:L['sb_off'] + 256]; bi = f32[L['sb_off'] + 256:L['sb_off'] + 512]
+    assert np.abs((W.astype(np.float64) @ x) * sc + bi - y_ref).max() < 1e-5
+    # layer 12 = shared fc4: activations(256) first, then PE(63)  (mlp.py:60-61)
+    L = h['layers'][12]
+    assert (L['k0'], L['k1'], L['k0p'], L['k1p']) == (256, 63, 256, 64)
+    # fp16 hi/lo slabs reconstruct W * 2^shift to ~2^-21 relative; canonical core-matrix order
+    f16 = np.frombuffer(blob, np.float16, h['f16_bytes'] // 2, h['f16_off'])
+    L = h['layers'][1]
+    W = sd['warping_field.mlp.conv2.weight'][:, :, 0]
+    n, ks = 256, 3
+    off = L['tc_w_off'] // 2 + ks * 2 * n * 16
+    hi = f16[off:off + n * 16].reshape(n // 8, 2, 8, 8).transpose(0, 2, 1, 3).reshape(n, 16).astype(np.float64)
+    lo = f16[off + n * 16:off + 2 * n * 16].reshape(n // 8, 2, 8, 8).transpose(0, 2, 1, 3).reshape(n, 16).astype(np.float64)
+    ref = W[:, 16 * ks:16 * ks + 16].astype(np.float64) * 2.0 ** L['shift']
+    assert np.abs(hi + lo - ref).max() <= np.abs(ref).max() * 2.0 ** -20
+    tsc = f32[L['tc_sb_off']:L['tc_sb_off'] + 256]
+    assert np.allclose(tsc * 2.0 ** L['shift'], f32[L['sb_off']:L['sb_off'] + 256], rtol=1e-7)
+
+
+def test_packer_recon_weight_norm():
+    sd = synth.recon_state_dict()
+    h = packer.parse_header(packer.pack_recon(sd))
+    assert [l['n'] for l in h['layers']] == [512, 256, 128, 1]
+    assert [(l['k0'], l['k1']) for l in h['layers']] == [(33, 0), (512, 33), (256, 33), (128, 0)]
+    L = packer.recon_layers(sd)[1]
+    v = sd['image_decoder.fc_list.1.0.weight_v'][:, :, 0].astype(np.float64); g = sd['image_decoder.fc_list.1.0.weight_g'][:, 0, 0]
+    W = v * (g / np.sqrt((v * v).sum(1)))[:, None]
+    assert np.abs(L.W * L.scale[:, None] - W).max() < 1e-6
+
+
+def test_packer_rejects_other_architectures():
+    sd = synth.avatar_state_dict()
+    sd['cano_template.shared_mlp.fc_list.0.0.weight'] = np.zeros((256, 39, 1), np.float32)      # pos_encoding 6
+    with pytest.raises(ValueError):
+        packer.pack_avatar(sd)
+
+
+def test_split_precision_scheme_meets_tolerance():
+    """Emulates the tensor-core arithmetic on the CPU: fp16 hi/lo operands, 3 products (hi*hi + hi*lo + lo*hi), wide accumulate,
+    activations re-split every layer. The scheme must keep the occupancy well inside the 1e-4 budget of the reference."""
+    from oracle import field_oracle as fo
+    sd = synth.avatar_state_dict()
+    layers = packer.avatar_layers(sd)
+    rs = np.random.RandomState(1)
+    pts = rs.uniform(-0.8, 0.8, (4000, 3)).astype(np.float32)
+
+    def split(x):
+        hi = x.astype(np.float16).astype(np.float64)
+        lo = (x - hi).astype(np.float16).astype(np.float64)
+        return hi, lo
+
+    def lin(L, x):      # x (K,N) float32
+        wh, wl = split(L.W.astype(np.float32)); xh, xl = split(x.astype(np.float32))
+        acc = wh @ xh + wh @ xl + wl @ xh
+        return (acc * L.scale[:, None].astype(np.float64) + L.bias[:, None].astype(np.float64)).astype(np.float32)
+
+    e = fo.embed(torch.from_numpy(pts), 10).numpy().T.astype(np.float32)
+    x = e
+    for i, L in enumerate(layers[8:15]):
+        inp = np.concatenate([x, e], 0) if i == 4 else x
+        x = lin(L, inp)
+        if i < 6:
+            x = np.maximum(x, 0)
+    g = lin(layers[15], x); g = np.where(g > 0, g, g * np.float32(0.02))
+    occ = lin(layers[16], g)[0]
+    _, _, ref = fo.template_forward(sd, torch.from_numpy(pts).double())
+    err = np.abs(occ - ref.numpy()[:, 0]).max()
+    assert err < 3e-5, err
+
+
+def test_abi_header_matches_binding():
+    """every function the header declares is bound by _lib.SIGNATURES (and vice versa) and exported by the built library"""
+    from avatarcap_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'avatarcap_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(avc_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip('library not built (python -c "import __graft_entry__ as g; g.build()")')
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.avc_abi_version() == 2
+
+
+def test_engine_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip('has a GPU')
+    from avatarcap_b200.engine import Engine
+    with pytest.raises((RuntimeError, ImportError)):
+        Engine()
+
+
+def test_mc_tables_consistency():
+    assert mc_tables.MAX_TRI == 5 and int(mc_tables.NTRI.sum()) == 820
+    for c in range(256):
+        cut = 0
+        for e, (a, b) in enumerate(mc_tables.EDGES):
+            if ((c >> a) & 1) != ((c >> b) & 1):
+                cut |= 1 << e
+        assert mc_tables.EDGE_MASK[c] == cut
+        assert mc_tables.EDGE_MASK[c] == mc_tables.EDGE_MASK[255 - c]     # complementary case cuts the same edges
+    inc = open(os.path.join(ROOT, 'avatarcap_b200', 'csrc', 'mc_tables.inc')).read()
+    row = ','.join(str(int(x)) for x in mc_tables.TRI[37])
+    assert '{%s}' % row in inc                                             # the committed CUDA include is up to date
+
+
+def test_slab_ranges_and_merge():
+    for rx in (5, 37, 256, 512):
+        for world in (1, 2, 3, 8):
+            if rx < world:
+                continue
+            r = [shard.slab_range(rx, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == rx and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+            assert max(e - s for s, e in r) - min(e - s for s, e in r) <= 1
+    assert shard.halo_planes(512, 0, 64) == (0, 3) and shard.halo_planes(512, 448, 512) == (2, 0) and shard.halo_planes(512, 64, 128) == (2, 3)
+    # merge: indices past a rank's own vertices point into the next rank
+    a = (np.zeros((3, 3), np.float32), np.array([[0, 1, 2], [2, 3, 4]], np.int32), np.zeros((3, 3), np.float32))
+    b = (np.ones((2, 3), np.float32), np.array([[0, 1, 1]], np.int32), np.ones((2, 3), np.float32))
+    v, f, n = shard.merge_meshes([a, b])
+    assert v.shape == (5, 3) and f.tolist() == [[0, 1, 2], [2, 3, 4], [3, 4, 4]]
+
+
+_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from avatarcap_b200 import shard
+rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% os.environ['MASTER_PORT'], rank=rank, world_size=world)
+rs = np.random.RandomState(0); res = (11, 4, 5)
+vol = torch.from_numpy(rs.normal(0, 1, res).astype(np.float32))
+s, e = shard.slab_range(res[0], world, rank)
+out = shard.exchange_halo(vol[s:e].contiguous(), rank, world, res[0])
+lo, hi = shard.halo_planes(res[0], s, e)
+assert torch.equal(out, vol[s - lo:e + hi]), (rank, out.shape)
+dist.barrier(); dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+def test_halo_exchange_gloo_world2(tmp_path):
+    script = tmp_path / 'w.py'
+    script.write_text(_WORKER % ROOT)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', MASTER_PORT='29631', MASTER_ADDR='127.0.0.1')
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
