@@ -205,6 +205,9 @@ class Engine:
         if vol.dim() != 3:
             raise ValueError('volume must be (Rx,Ry,Rz)')
         nv, nf = self.mc_count(vol, iso, halo_lo, halo_hi)
+        if nv == 0 and nf == 0:
+            z = torch.zeros((0, 3), device=self.device, dtype=torch.float32)
+            return z, torch.zeros((0, 3), device=self.device, dtype=torch.int32), (z.clone() if with_normals else None)
         verts = torch.empty((nv, 3), device=self.device, dtype=torch.float32)
         faces = torch.empty((nf, 3), device=self.device, dtype=torch.int32)
         normals = torch.empty((nv, 3), device=self.device, dtype=torch.float32) if with_normals else None

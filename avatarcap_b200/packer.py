@@ -47,6 +47,7 @@ class _Layer:
         self.W = W.astype(np.float32); self.scale = scale.astype(np.float32); self.bias = bias.astype(np.float32)
         self.k0, self.k1, self.act = k0, k1, act
         self.n = W.shape[0]
+        self.tc_perm0 = None      # optional column permutation of segment 0 for the tensor-core section
 
 
 def _plain(sd, prefix: str, k0: int, k1: int, act: int) -> _Layer:
@@ -83,6 +84,9 @@ def avatar_layers(sd) -> List[_Layer]:
     for i in range(1, 8):
         k0, k1 = (67, 0) if i == 1 else ((67, 256) if i == 5 else (256, 0))
         L.append(_bn_folded(sd, '%s.conv%d' % (p, i), '%s.bn%d' % (p, i), k0, k1))
+        if k0 == 67:
+            # tensor-core kernel stages h0 as [f0..f63, x, y, z] so the 64 gathered channels are 16-byte aligned k-groups
+            L[-1].tc_perm0 = np.concatenate([np.arange(3, 67), np.arange(0, 3)])
     L.append(_plain(sd, 'warping_field.out_layer_coord_affine', 256, 0, ACT_NONE))
     p = 'cano_template.shared_mlp.fc_list'
     if _np(sd, p + '.0.0.weight').shape[1] != 63:
@@ -150,7 +154,7 @@ def pack(layers: List[_Layer], kind: int) -> bytes:
         amax = float(np.abs(L.W).max())
         shift = int(np.clip(np.floor(np.log2(1000.0 / max(amax, 1e-30))), 0, 14))
         Wp = np.zeros((npad, k0p + k1p), np.float32)
-        Wp[:n, :L.k0] = L.W[:, :L.k0]
+        Wp[:n, :L.k0] = L.W[:, :L.k0] if L.tc_perm0 is None else L.W[:, :L.k0][:, L.tc_perm0]
         if L.k1:
             Wp[:n, k0p:k0p + L.k1] = L.W[:, L.k0:]
         Wp = Wp * np.float32(2.0 ** shift)

@@ -30,6 +30,18 @@ FLOP_PER_PT = {'occ': 1_773_568, 'occ+tex': 1_970_944, 'recon': 387_072}     # S
 GRIDS = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512, 512, 512)}
 
 
+def host_cores() -> int:
+    """Usable host threads: min(affinity mask, cgroup cpu quota) -- os.cpu_count() over-reports inside containers."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, p = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -112,7 +124,7 @@ def run_reference(args):
         return
     scene = build_scene()
     res = GRIDS[args.gpus]
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     total_budget = 150.0
     per_step = total_budget / max(1, args.steps + args.warmup)
     pts = strided_sample(scene, res, 64 ** 3)
@@ -283,7 +295,7 @@ def run_ours(args):
         if e2e:
             line['e2e'] = e2e
         if args.gpus == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
+            threads = host_cores()
             sub = strided_sample(scene, res, 64 ** 3)
             v_cpu, n_cpu, secs = cpu_reference_rate(scene, sub, 12.0, threads)
             line['cpu_baseline'] = {'value': v_cpu, 'unit': 'Mpoints/s', 'cores': threads, 'kind': 'port',
