@@ -152,17 +152,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t r[16]) 
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ math helpers
-__device__ __forceinline__ float act_tc(float v, int act) {
-  switch (act) {
-    case AVC_ACT_RELU: return fmaxf(v, 0.f);
-    case AVC_ACT_LRELU: return v > 0.f ? v : v * 0.02f;
-    case AVC_ACT_SOFTPLUS: {
-      // softplus(v) = max(v,0) + log1p(exp(-|v|)); exact to ~1e-7 abs, and == v for v > 20 like nn.Softplus(threshold=20)
-      const float t = exp2f(-fabsf(v) * 1.4426950408889634f);
-      return fmaxf(v, 0.f) + __logf(1.f + t);
-    }
-    default: return v;
+template <int ACT>
+__device__ __forceinline__ float act_tc(float v) {
+  if (ACT == AVC_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == AVC_ACT_LRELU) return fmaxf(v, v * 0.02f);          // == v > 0 ? v : 0.02 v   (nn.LeakyReLU(0.02), mlp.py:11)
+  if (ACT == AVC_ACT_SOFTPLUS) {
+    // softplus(v) = max(v,0) + log1p(exp(-|v|)); exact to ~1e-7 abs, and == v for v > 20 like nn.Softplus(threshold=20)
+    const float t = exp2f(-fabsf(v) * 1.4426950408889634f);
+    return fmaf(__log2f(1.f + t), 0.6931471805599453f, fmaxf(v, 0.f));
   }
+  return v;
 }
 // split (v0, v1) into packed fp16 hi and lo words (element with the lower k index in the low 16 bits)
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
@@ -180,6 +179,25 @@ __device__ __forceinline__ void skip_store8(unsigned char* skip, int r, int g, c
   unsigned char* base = skip + (g >> 1) * 8192 + (r >> 3) * 256 + (g & 1) * 128 + (r & 7) * 16;
   *reinterpret_cast<uint4*>(base) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(base + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// One 32-column accumulator chunk: TMEM -> scale/bias/activation -> fp16 hi/lo -> TMEM, in place (A operand of the next layer).
+// sbc points at {scale,bias} pairs of the chunk's 32 channels.
+template <int ACT>
+__device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __restrict__ sbc) {
+  float v[32];
+  tmem_ld32(taddr, v);
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float4 s4 = *reinterpret_cast<const float4*>(sbc + 4 * i);   // {scale0, bias0, scale1, bias1}
+    const float v0 = act_tc<ACT>(fmaf(v[2 * i], s4.x, s4.y));
+    const float v1 = act_tc<ACT>(fmaf(v[2 * i + 1], s4.z, s4.w));
+    split2(v0, v1, hi[i], lo[i]);
+  }
+  tmem_st16(taddr, hi);            // k-steps 2c, 2c+1: hi in columns [0,16) of the chunk
+  tmem_st16(taddr + 16u, lo);      //                   lo in columns [16,32)
+  tmem_st_wait();
 }
 
 struct Taps { int i00, i01, i10, i11; float w00, w01, w10, w11; };
@@ -448,20 +466,14 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
           const float* sb = s_sb + o.sb_off;
           const int n_chunks = o.n >> 5;
           for (int c = grp; c < n_chunks; c += 2) {
-            float v[32];
             const uint32_t taddr = t_lane + (uint32_t)(o.d_col + c * 32);
-            tmem_ld32(taddr, v);
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float4 s4 = *reinterpret_cast<const float4*>(sb + 2 * (c * 32 + 2 * i));   // {scale0, bias0, scale1, bias1}
-              const float v0 = act_tc(fmaf(v[2 * i], s4.x, s4.y), o.act);
-              const float v1 = act_tc(fmaf(v[2 * i + 1], s4.z, s4.w), o.act);
-              split2(v0, v1, hi[i], lo[i]);
+            const float* sbc = sb + 64 * c;
+            switch (o.act) {                                 // one branch per chunk, none per value
+              case AVC_ACT_RELU: hidden_chunk<AVC_ACT_RELU>(taddr, sbc); break;
+              case AVC_ACT_LRELU: hidden_chunk<AVC_ACT_LRELU>(taddr, sbc); break;
+              case AVC_ACT_SOFTPLUS: hidden_chunk<AVC_ACT_SOFTPLUS>(taddr, sbc); break;
+              default: hidden_chunk<AVC_ACT_NONE>(taddr, sbc); break;
             }
-            tmem_st16(taddr, hi);            // k-steps 2c, 2c+1: hi in columns [0,16) of the chunk
-            tmem_st16(taddr + 16u, lo);      //                   lo in columns [16,32)
-            tmem_st_wait();
             tc_fence_before(); __syncwarp();
             if (lane == 0) mbar_arrive(&S.a_ready[c]);
           }

@@ -1,0 +1,62 @@
+"""Per-frame geometry pipeline on the device: the hot-path part of main.run_avatarcap steps 1 and 3
+(main.py:357-367, 383-389, 438-453) as one function each, built only from Engine calls.
+
+    canonical avatar : OccupancyNet.query -> mask scatter (+-1 fill) -> recon_mesh(iso = config.iso_value = 0) -> LBS to live space
+    reconstruction   : ReconNetwork.infer -> mask scatter -> recon_mesh(iso = 0.5) -> LBS (+ normals)
+
+Everything stays in HBM between the stages (the reference copies the volume to the host for skimage and the vertices
+back, recon_util.py:64, main.py:383). Also holds the dataset-side precompute of SURVEY.md section 8 row a15 (validity
+flag by KNN-1, avatarcap_dataset.py:114-116).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine
+
+
+def valid_points_flag(engine: Engine, vol_pts: torch.Tensor, cano_smpl_v, thres: float = 0.1) -> torch.Tensor:
+    """infer_pts_flag = knn_points(vol_pts, cano_smpl_v, K=1).dists < 0.1**2   (avatarcap_dataset.py:114-116)."""
+    d2, _ = engine.knn(vol_pts, cano_smpl_v, 1)
+    return d2[:, 0] < thres ** 2
+
+
+def _mesh_to_live(engine: Engine, verts, normals, frame: Dict):
+    return engine.skin_mesh(verts, normals, frame['cano_smpl_v'], frame['smpl_skinning_weights'], frame['cano2live_jnt_mats'])
+
+
+def avatar_frame(engine: Engine, frame: Dict, pose_feat_map, vol_res, flag: Optional[torch.Tensor] = None,
+                 pts: Optional[torch.Tensor] = None, fill: Optional[torch.Tensor] = None, iso: float = 0.0,
+                 impl: Optional[str] = None) -> Dict[str, torch.Tensor]:
+    """Step 1 of run_avatarcap for one frame. `frame` holds cano_bounds (2,3), cano_smpl_center (3,), cano_smpl_v,
+    smpl_skinning_weights, cano2live_jnt_mats. Dense mode: flag/pts/fill None -> all Rx*Ry*Rz grid points are evaluated.
+    Masked mode (the reference's): pts = grid[flag], fill = +-1 for the other voxels (main.py:362-363)."""
+    bounds = np.asarray(frame['cano_bounds'], dtype=np.float32)
+    engine.set_pose_feature_map(pose_feat_map)
+    if flag is None:
+        pts = engine.make_grid(bounds, vol_res)
+    out = engine.eval_occupancy(pts, frame['cano_smpl_center'], want_offsets=True, impl=impl)
+    vol = out['occ'] if flag is None else engine.scatter_fill(flag, out['occ'], fill)
+    vol = vol.reshape(tuple(vol_res))
+    v, f, n = engine.extract_mesh(vol, bounds, iso)
+    lv, ln = _mesh_to_live(engine, v, n, frame)
+    return {'volume': vol, 'offsets': out['off'], 'verts': v, 'faces': f, 'normals': n, 'live_verts': lv, 'live_normals': ln}
+
+
+def recon_frame(engine: Engine, frame: Dict, img_feat_map, vol_res, flag: Optional[torch.Tensor] = None,
+                pts: Optional[torch.Tensor] = None, fill: Optional[torch.Tensor] = None, iso: float = 0.5,
+                impl: Optional[str] = None) -> Dict[str, torch.Tensor]:
+    """Step 3 of run_avatarcap (main.py:438-453): decoder over the grid, scatter, recon_mesh(iso 0.5), skinning."""
+    bounds = np.asarray(frame['cano_bounds'], dtype=np.float32)
+    engine.set_image_feature_map(img_feat_map)
+    if flag is None:
+        pts = engine.make_grid(bounds, vol_res)
+    ov = engine.eval_recon(pts, frame['cano_smpl_center'], impl=impl)
+    vol = ov if flag is None else engine.scatter_fill(flag, ov, fill)
+    vol = vol.reshape(tuple(vol_res))
+    v, f, n = engine.extract_mesh(vol, bounds, iso)
+    lv, ln = _mesh_to_live(engine, v, n, frame)
+    return {'volume': vol, 'verts': v, 'faces': f, 'normals': n, 'live_verts': lv, 'live_normals': ln}

@@ -155,6 +155,18 @@ class SynthBody:
         return pv.astype(np.float32), mats
 
 
+def body_inside(points: np.ndarray, pose75: np.ndarray) -> np.ndarray:
+    """Analytic inside test of the capsule body in pose `pose75` -> bool (N,). Stand-in for the reference's
+    `trimesh.contains` on the SMPL mesh (avatarcap_dataset.py:121-123), which needs the licensed SMPL faces."""
+    mats = joint_affine_mats(pose75)
+    pj = np.einsum('jab,jb->ja', mats[:, :3, :3], _REST_JOINTS) + mats[:, :3, 3]
+    p = np.asarray(points, dtype=np.float64)
+    inside = np.zeros(len(p), dtype=bool)
+    for j in range(1, N_JOINTS):
+        inside |= _point_segment_dist(p, pj[PARENTS[j]], pj[j]) < _BONE_RADIUS[j]
+    return inside
+
+
 def random_pose(seed: int, max_abs: float = 0.5) -> np.ndarray:
     rs = np.random.RandomState(seed)
     p = np.zeros(75)

@@ -307,3 +307,44 @@ def test_config2_dense_256_properties(eng, impl):
     assert maxabs(o['occ'][sel_t].cpu().numpy(), ref['cano_pts_ov'][:, 0]) < 1e-4
     assert maxabs(o['rgb'][sel_t].cpu().numpy(), ref['rgb']) < 1e-5
     assert maxabs(o['alpha'][sel_t].cpu().numpy(), ref['alpha'][:, 0]) < 1e-4
+
+
+@pytest.mark.parametrize('res', [(96, 96, 48)])
+def test_config3_full_frame_masked(eng, res):
+    """BASELINE config 3 (reduced grid so the CPU oracle finishes in seconds): masked query -> scatter (+-1 fill) ->
+    recon_mesh(iso 0) -> LBS, and recon decoder -> scatter -> recon_mesh(iso 0.5) -> LBS, vs the oracle pipeline."""
+    from oracle import field_oracle as fo
+    from oracle import mesh_oracle as mo
+    from avatarcap_b200 import pipeline
+    s = tpose_scene(128)
+    s['frame'] = synth.make_frame(s['body'], synth.random_pose(3, 0.3))
+    fr = s['frame']
+    eng.load_avatar(s['avatar_sd']); eng.load_recon(s['recon_sd'])
+    grid = eng.make_grid(fr['cano_bounds'], res)
+    flag = pipeline.valid_points_flag(eng, grid, fr['cano_smpl_v'])
+    ref_flag = fo.valid_points_flag(grid.cpu().numpy(), fr['cano_smpl_v'])
+    assert np.array_equal(flag.cpu().numpy(), ref_flag)
+    inside = synth.body_inside(grid.cpu().numpy()[~ref_flag], synth.cano_pose())
+    fill = (2.0 * inside.astype(np.float32) - 1.0)                                   # avatarcap_dataset.py:123-124
+    pts = grid[flag]
+    frame_dev = {k: torch.from_numpy(fr[k]).to(eng.device) for k in ('cano_smpl_v', 'smpl_skinning_weights', 'cano2live_jnt_mats')}
+    frame_dev.update(cano_bounds=fr['cano_bounds'], cano_smpl_center=fr['cano_smpl_center'])
+    for kind in ('avatar', 'recon'):
+        if kind == 'avatar':
+            out = pipeline.avatar_frame(eng, frame_dev, s['pose_map'], res, flag, pts, torch.from_numpy(fill), iso=0.0)
+            rvals = fo.occupancy_query(s['avatar_sd'], pts.cpu().numpy(), s['pose_map'], fr['cano_smpl_center'])['cano_pts_ov'][:, 0]
+            iso = 0.0
+        else:
+            out = pipeline.recon_frame(eng, frame_dev, s['image_map'], res, flag, pts, torch.from_numpy(fill), iso=0.5)
+            rvals = fo.recon_infer(s['recon_sd'], pts.cpu().numpy(), s['image_map'], fr['cano_smpl_center'])
+            iso = 0.5
+        rvol = fo.scatter_fill(ref_flag, rvals, fill, res)
+        assert maxabs(out['volume'].cpu().numpy(), rvol) < 1e-4
+        rv, rf, rn = mo.recon_mesh(rvol, res, fr['cano_bounds'], iso)
+        nv = out['verts'].shape[0]
+        print('%s frame: valid %.1f%%, verts %d (oracle %d), faces %d (oracle %d)' % (kind, 100 * ref_flag.mean(), nv, rv.shape[0], out['faces'].shape[0], rf.shape[0]))
+        assert abs(nv - rv.shape[0]) <= 1e-3 * rv.shape[0] + 1
+        assert mo.chamfer(out['verts'].cpu().numpy(), rv) < 1e-3
+        lbs = fo.calculate_lbs(rv, fr['cano_smpl_v'], fr['smpl_skinning_weights'])
+        live, _ = fo.skinning(rv, lbs, fr['cano2live_jnt_mats'])
+        assert mo.chamfer(out['live_verts'].cpu().numpy(), live) < 1e-3
