@@ -26,8 +26,8 @@ namespace {
 
 constexpr int TILE = 128;                 // points per tile == UMMA M
 constexpr int NT = 320;                   // 8 compute warps + MMA warp + producer warp
-constexpr int N_STAGES = 8;
-constexpr int STAGE_BYTES = 16384;        // one k-step of weights: hi (N*32 B) + lo (N*32 B), N <= 256
+constexpr int N_STAGES = 12;
+constexpr int STAGE_BYTES = 8192;         // one k-step of one N-half: hi (128 rows * 32 B) + lo (128 rows * 32 B)
 constexpr int SKIP_KSTEPS = 5;            // up to K=80 of skip input
 constexpr int SKIP_BYTES = SKIP_KSTEPS * 8192;   // per k-step: hi slab 4 KB + lo slab 4 KB (128 rows x 16 k x 2 B)
 constexpr int MAX_OPS = 24;
@@ -65,7 +65,7 @@ struct TcArgs {
 struct __align__(16) TcShared {
   unsigned long long full[N_STAGES], empty[N_STAGES];
   unsigned long long a_ready[8];
-  unsigned long long d_ready, epi_done;
+  unsigned long long d_ready[2], epi_done;   // d_ready[h]: N-half h of the current op is complete
   unsigned int tmem_base; int n_ops; int pad[2];
   TcOp ops[MAX_OPS];
 };
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
   if (tid == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
     for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 4);
-    mbar_init(&S.d_ready, 1); mbar_init(&S.epi_done, 8);
+    mbar_init(&S.d_ready[0], 1); mbar_init(&S.d_ready[1], 1); mbar_init(&S.epi_done, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int sbt; build_ops(S, a.hdr, a.kind, a.mode, texture, &sbt); s_sb_total = sbt;
   }
@@ -335,17 +335,21 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = S.ops[oi];
           const AvcLayerDesc& L = a.hdr->layers[o.layer];
-          const uint32_t half_bytes = (uint32_t)o.n * 32u;
+          const int n_halves = o.n == 256 ? 2 : 1;          // 256-wide layers run as two N=128 halves (see the MMA issuer)
+          const uint32_t rows = (uint32_t)(o.n / n_halves);
+          const uint32_t part_bytes = rows * 32u;
           const int ks = o.ks_smem + o.ks_tmem;
-          for (int j = 0; j < ks; ++j) {
-            const int wk = j < o.ks_smem ? o.ks_smem_w0 + j : o.ks_tmem_w0 + (j - o.ks_smem);
-            mbar_wait(&S.empty[stage], phase ^ 1);
-            mbar_expect_tx(&S.full[stage], 2 * half_bytes);
-            const unsigned char* src = a.w16 + (size_t)L.tc_w_off + (size_t)wk * ((size_t)o.np * 64) + (size_t)o.n_row_off * 32;
-            unsigned char* dst = ring + stage * STAGE_BYTES;
-            bulk_g2s(dst, src, half_bytes, &S.full[stage]);                                   // hi rows
-            bulk_g2s(dst + half_bytes, src + (size_t)o.np * 32, half_bytes, &S.full[stage]);  // lo rows
-            if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+          for (int h = 0; h < n_halves; ++h) {
+            for (int j = 0; j < ks; ++j) {
+              const int wk = j < o.ks_smem ? o.ks_smem_w0 + j : o.ks_tmem_w0 + (j - o.ks_smem);
+              mbar_wait(&S.empty[stage], phase ^ 1);
+              mbar_expect_tx(&S.full[stage], 2 * part_bytes);
+              const unsigned char* src = a.w16 + (size_t)L.tc_w_off + (size_t)wk * ((size_t)o.np * 64) + (size_t)(o.n_row_off + h * 128) * 32;
+              unsigned char* dst = ring + stage * STAGE_BYTES;
+              bulk_g2s(dst, src, part_bytes, &S.full[stage]);                                   // hi rows
+              bulk_g2s(dst + part_bytes, src + (size_t)o.np * 32, part_bytes, &S.full[stage]);  // lo rows
+              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -359,33 +363,40 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = S.ops[oi];
-          const uint32_t idesc = make_idesc(o.n);
-          const uint32_t d_addr = tmem + (uint32_t)o.d_col;
-          const uint32_t half_bytes = (uint32_t)o.n * 32u;
+          // A 256-wide layer is issued as two N=128 halves, each over the full K. The epilogue of half 0 (accumulator columns
+          // 0..127 -> A chunks 0..3 of the next layer) then overlaps the MMAs of half 1, and the next layer's half 0 can start on
+          // chunks 0..3 the moment this layer's half 1 has been issued: the tensor pipe never waits for the epilogue.
+          const int n_halves = o.n == 256 ? 2 : 1;
+          const int rows = o.n / n_halves;
+          const uint32_t idesc = make_idesc(rows);
+          const uint32_t part_bytes = (uint32_t)rows * 32u;
           if (o.wait_epi) { mbar_wait(&S.epi_done, ph_epi); ph_epi ^= 1; tc_fence_after(); }
-          uint32_t acc = o.accumulate ? 1u : 0u;
-          for (int j = 0; j < o.ks_smem; ++j) {
-            mbar_wait(&S.full[stage], phase); tc_fence_after();
-            const uint64_t b_hi = make_desc(ring_addr + stage * STAGE_BYTES), b_lo = make_desc(ring_addr + stage * STAGE_BYTES + half_bytes);
-            const uint64_t a_hi = make_desc(skip_addr + j * 8192), a_lo = make_desc(skip_addr + j * 8192 + 4096);
-            mma_ss(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-            mma_ss(d_addr, a_lo, b_hi, idesc, 1u);
-            mma_ss(d_addr, a_hi, b_lo, idesc, 1u);
-            tc_commit(&S.empty[stage]);
-            if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+          for (int h = 0; h < n_halves; ++h) {
+            const uint32_t d_addr = tmem + (uint32_t)(o.d_col + h * 128);
+            uint32_t acc = o.accumulate ? 1u : 0u;
+            for (int j = 0; j < o.ks_smem; ++j) {
+              mbar_wait(&S.full[stage], phase); tc_fence_after();
+              const uint64_t b_hi = make_desc(ring_addr + stage * STAGE_BYTES), b_lo = make_desc(ring_addr + stage * STAGE_BYTES + part_bytes);
+              const uint64_t a_hi = make_desc(skip_addr + j * 8192), a_lo = make_desc(skip_addr + j * 8192 + 4096);
+              mma_ss(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
+              mma_ss(d_addr, a_lo, b_hi, idesc, 1u);
+              mma_ss(d_addr, a_hi, b_lo, idesc, 1u);
+              tc_commit(&S.empty[stage]);
+              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+            }
+            for (int j = 0; j < o.ks_tmem; ++j) {
+              if (o.wait_a && h == 0 && (j & 1) == 0) { const int c = j >> 1; mbar_wait(&S.a_ready[c], (ph_a >> c) & 1u); ph_a ^= (1u << c); tc_fence_after(); }
+              mbar_wait(&S.full[stage], phase); tc_fence_after();
+              const uint64_t b_hi = make_desc(ring_addr + stage * STAGE_BYTES), b_lo = make_desc(ring_addr + stage * STAGE_BYTES + part_bytes);
+              const uint32_t a_hi = tmem + (uint32_t)o.a_col + (uint32_t)((j >> 1) * 32 + (j & 1) * 8), a_lo = a_hi + 16u;
+              mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
+              mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
+              mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+              tc_commit(&S.empty[stage]);
+              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (o.commit_d) tc_commit(&S.d_ready[h]);
           }
-          for (int j = 0; j < o.ks_tmem; ++j) {
-            if (o.wait_a && (j & 1) == 0) { const int c = j >> 1; mbar_wait(&S.a_ready[c], (ph_a >> c) & 1u); ph_a ^= (1u << c); tc_fence_after(); }
-            mbar_wait(&S.full[stage], phase); tc_fence_after();
-            const uint64_t b_hi = make_desc(ring_addr + stage * STAGE_BYTES), b_lo = make_desc(ring_addr + stage * STAGE_BYTES + half_bytes);
-            const uint32_t a_hi = tmem + (uint32_t)o.a_col + (uint32_t)((j >> 1) * 32 + (j & 1) * 8), a_lo = a_hi + 16u;
-            mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-            mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
-            mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
-            tc_commit(&S.empty[stage]);
-            if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
-          }
-          if (o.commit_d) tc_commit(&S.d_ready);
         }
       }
     }
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
     const int quad = warp & 3, grp = warp >> 2;        // TMEM lane quadrant; column-group (0: even chunks, 1: odd chunks)
     const int row = quad * 32 + lane;                  // point within the tile == TMEM lane
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t ph_d = 0;
+    uint32_t ph_d0 = 0, ph_d1 = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t g = tile * TILE + row;
       const bool valid = g < a.n;
@@ -461,11 +472,12 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
         if (oi == n_ops) break;
         const TcOp& o = S.ops[oi];
         if (!o.commit_d) continue;
-        mbar_wait(&S.d_ready, ph_d); ph_d ^= 1; tc_fence_after();
+        mbar_wait(&S.d_ready[0], ph_d0); ph_d0 ^= 1; tc_fence_after();
         if (o.epi == EPI_HIDDEN) {
           const float* sb = s_sb + o.sb_off;
           const int n_chunks = o.n >> 5;
           for (int c = grp; c < n_chunks; c += 2) {
+            if (c == 4 + grp) { mbar_wait(&S.d_ready[1], ph_d1); ph_d1 ^= 1; tc_fence_after(); }   // second N-half (only 256-wide ops get here)
             const uint32_t taddr = t_lane + (uint32_t)(o.d_col + c * 32);
             const float* sbc = sb + 64 * c;
             switch (o.act) {                                 // one branch per chunk, none per value
