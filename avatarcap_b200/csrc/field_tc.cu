@@ -26,8 +26,9 @@ namespace {
 
 constexpr int TILE = 128;                 // points per tile == UMMA M
 constexpr int NT = 320;                   // 8 compute warps + MMA warp + producer warp
-constexpr int N_STAGES = 12;
-constexpr int STAGE_BYTES = 8192;         // one k-step of one N-half: hi (128 rows * 32 B) + lo (128 rows * 32 B)
+constexpr int N_STAGES = 8;
+constexpr int STAGE_KSTEPS = 2;           // k-steps per ring stage (== one 32-column A chunk)
+constexpr int STAGE_BYTES = STAGE_KSTEPS * 8192;   // per k-step of one N-half: hi (128 rows * 32 B) + lo (128 rows * 32 B)
 constexpr int SKIP_KSTEPS = 5;            // up to K=80 of skip input
 constexpr int SKIP_BYTES = SKIP_KSTEPS * 8192;   // per k-step: hi slab 4 KB + lo slab 4 KB (128 rows x 16 k x 2 B)
 constexpr int MAX_OPS = 24;
@@ -106,6 +107,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -338,34 +344,41 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
           const int n_halves = o.n == 256 ? 2 : 1;          // 256-wide layers run as two N=128 halves (see the MMA issuer)
           const uint32_t rows = (uint32_t)(o.n / n_halves);
           const uint32_t part_bytes = rows * 32u;
-          const int ks = o.ks_smem + o.ks_tmem;
           for (int h = 0; h < n_halves; ++h) {
-            for (int j = 0; j < ks; ++j) {
-              const int wk = j < o.ks_smem ? o.ks_smem_w0 + j : o.ks_tmem_w0 + (j - o.ks_smem);
-              mbar_wait(&S.empty[stage], phase ^ 1);
-              mbar_expect_tx(&S.full[stage], 2 * part_bytes);
-              const unsigned char* src = a.w16 + (size_t)L.tc_w_off + (size_t)wk * ((size_t)o.np * 64) + (size_t)(o.n_row_off + h * 128) * 32;
-              unsigned char* dst = ring + stage * STAGE_BYTES;
-              bulk_g2s(dst, src, part_bytes, &S.full[stage]);                                   // hi rows
-              bulk_g2s(dst + part_bytes, src + (size_t)o.np * 32, part_bytes, &S.full[stage]);  // lo rows
-              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+            for (int seg = 0; seg < 2; ++seg) {
+              const int ks = seg == 0 ? o.ks_smem : o.ks_tmem;
+              const int w0 = seg == 0 ? o.ks_smem_w0 : o.ks_tmem_w0;
+              for (int j = 0; j < ks; j += STAGE_KSTEPS) {
+                const int cnt = min(STAGE_KSTEPS, ks - j);
+                mbar_wait(&S.empty[stage], phase ^ 1);
+                mbar_expect_tx(&S.full[stage], (uint32_t)cnt * 2u * part_bytes);
+                for (int u = 0; u < cnt; ++u) {
+                  const unsigned char* src = a.w16 + (size_t)L.tc_w_off + (size_t)(w0 + j + u) * ((size_t)o.np * 64) + (size_t)(o.n_row_off + h * 128) * 32;
+                  unsigned char* dst = ring + stage * STAGE_BYTES + u * 2 * part_bytes;
+                  bulk_g2s(dst, src, part_bytes, &S.full[stage]);                                   // hi rows
+                  bulk_g2s(dst + part_bytes, src + (size_t)o.np * 32, part_bytes, &S.full[stage]);  // lo rows
+                }
+                if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+              }
             }
           }
         }
       }
     }
   } else if (warp == 8) {
-    // ============================================================ MMA issuer (one thread)
-    if (lane == 0) {
+    // ============================================================ MMA issuer: the whole warp walks the (warp-uniform) program,
+    // one elected lane issues. Keeping the warp converged lets the compiler keep descriptors in uniform registers.
+    {
       int stage = 0; uint32_t phase = 0;
       uint32_t ph_a = 0, ph_epi = 0;   // per-barrier phase bits
       const uint32_t skip_addr = smem_u32(skip), ring_addr = smem_u32(ring);
+      const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);   // LBO, SBO, version
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = S.ops[oi];
           // A 256-wide layer is issued as two N=128 halves, each over the full K. The epilogue of half 0 (accumulator columns
           // 0..127 -> A chunks 0..3 of the next layer) then overlaps the MMAs of half 1, and the next layer's half 0 can start on
-          // chunks 0..3 the moment this layer's half 1 has been issued: the tensor pipe never waits for the epilogue.
+          // chunks 0..3 the moment this layer's half 1 has been issued: the tensor pipe does not wait for the epilogue.
           const int n_halves = o.n == 256 ? 2 : 1;
           const int rows = o.n / n_halves;
           const uint32_t idesc = make_idesc(rows);
@@ -374,28 +387,45 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
           for (int h = 0; h < n_halves; ++h) {
             const uint32_t d_addr = tmem + (uint32_t)(o.d_col + h * 128);
             uint32_t acc = o.accumulate ? 1u : 0u;
-            for (int j = 0; j < o.ks_smem; ++j) {
+            for (int j = 0; j < o.ks_smem; j += STAGE_KSTEPS) {
+              const int cnt = min(STAGE_KSTEPS, o.ks_smem - j);
               mbar_wait(&S.full[stage], phase); tc_fence_after();
-              const uint64_t b_hi = make_desc(ring_addr + stage * STAGE_BYTES), b_lo = make_desc(ring_addr + stage * STAGE_BYTES + part_bytes);
-              const uint64_t a_hi = make_desc(skip_addr + j * 8192), a_lo = make_desc(skip_addr + j * 8192 + 4096);
-              mma_ss(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-              mma_ss(d_addr, a_lo, b_hi, idesc, 1u);
-              mma_ss(d_addr, a_hi, b_lo, idesc, 1u);
-              tc_commit(&S.empty[stage]);
+              if (elect_one()) {
+                for (int u = 0; u < cnt; ++u) {
+                  const uint32_t b_addr = ring_addr + stage * STAGE_BYTES + u * 2 * part_bytes;
+                  const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
+                  const uint32_t a_addr = skip_addr + (j + u) * 8192;
+                  const uint64_t a_hi = desc_hi | (uint64_t)(a_addr >> 4), a_lo = desc_hi | (uint64_t)((a_addr + 4096) >> 4);
+                  mma_ss(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
+                  mma_ss(d_addr, a_lo, b_hi, idesc, 1u);
+                  mma_ss(d_addr, a_hi, b_lo, idesc, 1u);
+                }
+                tc_commit(&S.empty[stage]);
+              }
+              acc = 1u;
+              __syncwarp();
               if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
-            for (int j = 0; j < o.ks_tmem; ++j) {
-              if (o.wait_a && h == 0 && (j & 1) == 0) { const int c = j >> 1; mbar_wait(&S.a_ready[c], (ph_a >> c) & 1u); ph_a ^= (1u << c); tc_fence_after(); }
+            for (int c = 0; c < (o.ks_tmem >> 1); ++c) {      // one 32-column A chunk = 2 k-steps = one ring stage
+              if (o.wait_a && h == 0) { mbar_wait(&S.a_ready[c], (ph_a >> c) & 1u); ph_a ^= (1u << c); }
               mbar_wait(&S.full[stage], phase); tc_fence_after();
-              const uint64_t b_hi = make_desc(ring_addr + stage * STAGE_BYTES), b_lo = make_desc(ring_addr + stage * STAGE_BYTES + part_bytes);
-              const uint32_t a_hi = tmem + (uint32_t)o.a_col + (uint32_t)((j >> 1) * 32 + (j & 1) * 8), a_lo = a_hi + 16u;
-              mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-              mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
-              mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
-              tc_commit(&S.empty[stage]);
+              if (elect_one()) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const uint32_t b_addr = ring_addr + stage * STAGE_BYTES + u * 2 * part_bytes;
+                  const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
+                  const uint32_t a_hi = tmem + (uint32_t)o.a_col + (uint32_t)(c * 32 + u * 8), a_lo = a_hi + 16u;
+                  mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
+                  mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
+                  mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+                }
+                tc_commit(&S.empty[stage]);
+              }
+              acc = 1u;
+              __syncwarp();
               if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
-            if (o.commit_d) tc_commit(&S.d_ready[h]);
+            if (o.commit_d) { if (elect_one()) tc_commit(&S.d_ready[h]); __syncwarp(); }
           }
         }
       }
