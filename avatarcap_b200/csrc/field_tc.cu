@@ -51,6 +51,7 @@ struct TcOp {
   int act;
   int sb_off;         // float offset of {scale,bias} pairs in shared memory
   int signal_done;    // compute warps arrive on epi_done after this op's epilogue
+  unsigned int w_off; // byte offset of this op's weight stream in the f16 section
   int wait_a;         // the TMEM A chunks are produced by the preceding epilogue (0: already complete, e.g. the colour head re-reads s7)
 };
 
@@ -242,7 +243,8 @@ __device__ __forceinline__ void gather8(const float* __restrict__ hwc, int C, co
 __device__ void build_ops(TcShared& S, const AvcBlobHeader* hdr, int kind, int mode, bool texture, int* sb_total) {
   int n = 0, sb = 0;
   int sb_off[AVC_MAX_LAYERS];
-  for (int l = 0; l < (int)hdr->n_layers; ++l) { sb_off[l] = sb; sb += 2 * hdr->layers[l].np; }
+  unsigned int stream_pos[AVC_MAX_LAYERS];      // running offset inside each layer's weight stream (pieces in op order)
+  for (int l = 0; l < (int)hdr->n_layers; ++l) { sb_off[l] = sb; sb += 2 * hdr->layers[l].np; stream_pos[l] = (unsigned int)hdr->layers[l].tc_w_off; }
   *sb_total = sb;
   auto add = [&](int layer, int nn, int row_off, int ks_s, int ks_s_w0, int ks_t, int ks_t_w0, int a_col, int d_col, int accum, int wait_epi,
                  int commit, int epi, int signal) {
@@ -251,6 +253,7 @@ __device__ void build_ops(TcShared& S, const AvcBlobHeader* hdr, int kind, int m
     o.layer = layer; o.n = nn; o.n_row_off = row_off; o.np = L.np; o.ks_smem = ks_s; o.ks_smem_w0 = ks_s_w0; o.ks_tmem = ks_t; o.ks_tmem_w0 = ks_t_w0;
     o.a_col = a_col; o.d_col = d_col; o.accumulate = accum; o.wait_epi = wait_epi; o.commit_d = commit; o.epi = epi; o.act = L.act;
     o.sb_off = sb_off[layer] + 2 * row_off; o.signal_done = signal; o.wait_a = 1;
+    o.w_off = stream_pos[layer]; stream_pos[layer] += (unsigned int)(nn * 64 * (ks_s + ks_t));
   };
   const int X = 0, Y = 256;
   if (kind == AVC_KIND_AVATAR) {
@@ -334,30 +337,28 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
   const int64_t n_tiles = (a.n + TILE - 1) / TILE;
 
   if (warp == 9) {
-    // ============================================================ weight producer (one thread)
-    if (lane == 0) {
+    // ============================================================ weight producer: the layer's weights are stored as a stream in
+    // exactly the order and layout the ring consumes them (packer.py), so one bulk copy per stage is all it takes.
+    {
       int stage = 0; uint32_t phase = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = S.ops[oi];
-          const AvcLayerDesc& L = a.hdr->layers[o.layer];
-          const int n_halves = o.n == 256 ? 2 : 1;          // 256-wide layers run as two N=128 halves (see the MMA issuer)
-          const uint32_t rows = (uint32_t)(o.n / n_halves);
-          const uint32_t part_bytes = rows * 32u;
+          const int n_halves = o.n == 256 ? 2 : 1;
+          const uint32_t part_bytes = (uint32_t)(o.n / n_halves) * 32u;
+          const unsigned char* src = a.w16 + o.w_off;
           for (int h = 0; h < n_halves; ++h) {
             for (int seg = 0; seg < 2; ++seg) {
               const int ks = seg == 0 ? o.ks_smem : o.ks_tmem;
-              const int w0 = seg == 0 ? o.ks_smem_w0 : o.ks_tmem_w0;
               for (int j = 0; j < ks; j += STAGE_KSTEPS) {
-                const int cnt = min(STAGE_KSTEPS, ks - j);
+                const uint32_t bytes = (uint32_t)min(STAGE_KSTEPS, ks - j) * 2u * part_bytes;
                 mbar_wait(&S.empty[stage], phase ^ 1);
-                mbar_expect_tx(&S.full[stage], (uint32_t)cnt * 2u * part_bytes);
-                for (int u = 0; u < cnt; ++u) {
-                  const unsigned char* src = a.w16 + (size_t)L.tc_w_off + (size_t)(w0 + j + u) * ((size_t)o.np * 64) + (size_t)(o.n_row_off + h * 128) * 32;
-                  unsigned char* dst = ring + stage * STAGE_BYTES + u * 2 * part_bytes;
-                  bulk_g2s(dst, src, part_bytes, &S.full[stage]);                                   // hi rows
-                  bulk_g2s(dst + part_bytes, src + (size_t)o.np * 32, part_bytes, &S.full[stage]);  // lo rows
+                if (elect_one()) {
+                  mbar_expect_tx(&S.full[stage], bytes);
+                  bulk_g2s(ring + stage * STAGE_BYTES, src, bytes, &S.full[stage]);
                 }
+                __syncwarp();
+                src += bytes;
                 if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
               }
             }

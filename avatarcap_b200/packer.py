@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 MAGIC = 0x57435641
-VERSION = 2
+VERSION = 3
 MAX_LAYERS = 24
 KIND_AVATAR, KIND_RECON = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SOFTPLUS, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -128,6 +128,21 @@ def _slab(mat_nk16: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(mat_nk16.reshape(n // 8, 8, 2, 8).transpose(0, 2, 1, 3)).reshape(-1)
 
 
+STAGE_KSTEPS = 2      # k-steps per shared-memory ring stage (csrc/field_tc.cu)
+
+
+def tc_pieces(kind: int, layer: int, npad: int):
+    """[(row_off, n_rows, [(first weight k-step, k-steps), ...] in issue order)] for one layer -- the op program of
+    csrc/field_tc.cu build_ops(): skip-input (shared-memory) k-steps are issued before the TMEM-fed ones."""
+    if kind == KIND_AVATAR:
+        segs = {0: [(0, 5)], 4: [(0, 5), (5, 16)], 8: [(0, 4)], 12: [(16, 4), (0, 16)], 16: [(0, 8)], 19: [(0, 8)]}.get(layer, [(0, 16)])
+        return [(0, npad, segs)]
+    return {0: [(0, 256, [(0, 3)]), (256, 256, [(0, 3)])],
+            1: [(0, 256, [(0, 16)]), (0, 256, [(32, 3), (16, 16)])],
+            2: [(0, 128, [(16, 3), (0, 16)])],
+            3: [(0, 16, [(0, 8)])]}[layer]
+
+
 def pack(layers: List[_Layer], kind: int) -> bytes:
     f32: List[np.ndarray] = []
     f32_len = 0
@@ -159,11 +174,22 @@ def pack(layers: List[_Layer], kind: int) -> bytes:
             Wp[:n, k0p:k0p + L.k1] = L.W[:, L.k0:]
         Wp = Wp * np.float32(2.0 ** shift)
         hi, lo = split_hi_lo(Wp)
+        # The tensor-core kernel consumes a layer as a STREAM: for each piece (row block of an op), each N-half of 128 rows,
+        # each ring stage (<= 2 k-steps, in issue order: shared-memory segment first), the hi slab then the lo slab of those
+        # rows. One cp.async.bulk per stage moves it; tc_pieces() mirrors build_ops() in csrc/field_tc.cu.
         tc_w_off = f16_bytes
-        for s in range((k0p + k1p) // 16):
-            for part in (hi, lo):
-                sl = _slab(part[:, 16 * s:16 * s + 16])
-                f16.append(sl); f16_bytes += sl.size * 2
+        for row_off, n_piece, segs in tc_pieces(kind, len(descs), npad):
+            halves = 2 if n_piece == 256 else 1
+            rows = n_piece // halves
+            for h in range(halves):
+                r0 = row_off + h * rows
+                for w0, ks in segs:
+                    for j in range(0, ks, STAGE_KSTEPS):
+                        for u in range(min(STAGE_KSTEPS, ks - j)):
+                            kk = 16 * (w0 + j + u)
+                            for part in (hi, lo):
+                                sl = _slab(part[r0:r0 + rows, kk:kk + 16])
+                                f16.append(sl); f16_bytes += sl.size * 2
         tsc = np.zeros(npad, np.float32); tbi = np.zeros(npad, np.float32)
         tsc[:n] = L.scale * np.float32(2.0 ** -shift); tbi[:n] = L.bias
         tc_sb_off = add_f32(np.concatenate([tsc, tbi]))

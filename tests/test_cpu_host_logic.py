@@ -12,6 +12,10 @@ from avatarcap_b200 import packer, synth, shard, mc_tables
 from helpers import ROOT
 
 
+def h_layers(blob):
+    return packer.parse_header(blob)['layers']
+
+
 def test_packer_layout_and_folding():
     sd = synth.avatar_state_dict()
     blob = packer.pack_avatar(sd)
@@ -37,12 +41,19 @@ def test_packer_layout_and_folding():
     f16 = np.frombuffer(blob, np.float16, h['f16_bytes'] // 2, h['f16_off'])
     L = h['layers'][1]
     W = sd['warping_field.mlp.conv2.weight'][:, :, 0]
-    n, ks = 256, 3
-    off = L['tc_w_off'] // 2 + ks * 2 * n * 16
-    hi = f16[off:off + n * 16].reshape(n // 8, 2, 8, 8).transpose(0, 2, 1, 3).reshape(n, 16).astype(np.float64)
-    lo = f16[off + n * 16:off + 2 * n * 16].reshape(n // 8, 2, 8, 8).transpose(0, 2, 1, 3).reshape(n, 16).astype(np.float64)
-    ref = W[:, 16 * ks:16 * ks + 16].astype(np.float64) * 2.0 ** L['shift']
+    # stream order (packer.tc_pieces): half h (128 rows) -> k-step ks -> hi slab (128 x 16) then lo slab
+    rows, ks, h = 128, 3, 1
+    off = L['tc_w_off'] // 2 + h * (16 * rows * 32) + ks * (rows * 32)
+    hi = f16[off:off + rows * 16].reshape(rows // 8, 2, 8, 8).transpose(0, 2, 1, 3).reshape(rows, 16).astype(np.float64)
+    lo = f16[off + rows * 16:off + 2 * rows * 16].reshape(rows // 8, 2, 8, 8).transpose(0, 2, 1, 3).reshape(rows, 16).astype(np.float64)
+    ref = W[h * rows:(h + 1) * rows, 16 * ks:16 * ks + 16].astype(np.float64) * 2.0 ** L['shift']
     assert np.abs(hi + lo - ref).max() <= np.abs(ref).max() * 2.0 ** -20
+    # every layer's stream has exactly np * (k0p + k1p) * 4 bytes (hi + lo) and the streams tile the f16 section
+    pos = 0
+    for Ld in h_layers(blob):
+        assert Ld['tc_w_off'] == pos
+        pos += Ld['np'] * (Ld['k0p'] + Ld['k1p']) * 4
+    assert pos == packer.parse_header(blob)['f16_bytes']
     tsc = f32[L['tc_sb_off']:L['tc_sb_off'] + 256]
     assert np.allclose(tsc * 2.0 ** L['shift'], f32[L['sb_off']:L['sb_off'] + 256], rtol=1e-7)
 
