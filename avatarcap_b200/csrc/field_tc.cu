@@ -26,8 +26,8 @@ namespace {
 
 constexpr int TILE = 128;                 // points per tile == UMMA M
 constexpr int NT = 320;                   // 8 compute warps + MMA warp + producer warp
-constexpr int N_STAGES = 8;
-constexpr int STAGE_KSTEPS = 2;           // k-steps per ring stage (== one 32-column A chunk)
+constexpr int N_STAGES = 4;
+constexpr int STAGE_KSTEPS = 4;           // k-steps per ring stage (== two 32-column A chunks)
 constexpr int STAGE_BYTES = STAGE_KSTEPS * 8192;   // per k-step of one N-half: hi (128 rows * 32 B) + lo (128 rows * 32 B)
 constexpr int SKIP_KSTEPS = 5;            // up to K=80 of skip input
 constexpr int SKIP_BYTES = SKIP_KSTEPS * 8192;   // per k-step: hi slab 4 KB + lo slab 4 KB (128 rows x 16 k x 2 B)
@@ -407,15 +407,20 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
               __syncwarp();
               if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
-            for (int c = 0; c < (o.ks_tmem >> 1); ++c) {      // one 32-column A chunk = 2 k-steps = one ring stage
-              if (o.wait_a && h == 0) { mbar_wait(&S.a_ready[c], (ph_a >> c) & 1u); ph_a ^= (1u << c); }
+            for (int c2 = 0; c2 < (o.ks_tmem >> 2); ++c2) {   // one ring stage = 4 k-steps = two 32-column A chunks
+              if (o.wait_a && h == 0) {
+                mbar_wait(&S.a_ready[2 * c2], (ph_a >> (2 * c2)) & 1u); mbar_wait(&S.a_ready[2 * c2 + 1], (ph_a >> (2 * c2 + 1)) & 1u);
+                ph_a ^= (3u << (2 * c2));
+              }
               mbar_wait(&S.full[stage], phase); tc_fence_after();
               if (elect_one()) {
+                const uint32_t b0 = ring_addr + stage * STAGE_BYTES;
+                const uint32_t a0 = tmem + (uint32_t)o.a_col + (uint32_t)(c2 * 64);
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                  const uint32_t b_addr = ring_addr + stage * STAGE_BYTES + u * 2 * part_bytes;
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t b_addr = b0 + u * 2 * part_bytes;
                   const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
-                  const uint32_t a_hi = tmem + (uint32_t)o.a_col + (uint32_t)(c * 32 + u * 8), a_lo = a_hi + 16u;
+                  const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
                   mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
                   mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
                   mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
