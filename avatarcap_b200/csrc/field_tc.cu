@@ -62,6 +62,7 @@ struct TcArgs {
   float* out0; float* out_off; float* out_rgb; float* out_alpha;   // out0 = occ (avatar) or ov (recon)
   int if_type, mode, kind;
   const unsigned char* w16; const float* f32; const AvcBlobHeader* hdr;
+  long long* trace;   // optional timeline buffer (debug): [tile<4][op<24][8 events] clock64 stamps of CTA 0
 };
 
 struct __align__(16) TcShared {
@@ -238,6 +239,11 @@ __device__ __forceinline__ void gather8(const float* __restrict__ hwc, int C, co
   }
 }
 
+// debug timeline: event e of op `oi` in the CTA-local tile number `t` (only CTA 0, first 4 tiles)
+__device__ __forceinline__ void trace_ev(long long* trace, int t, int oi, int e) {
+  if (trace && blockIdx.x == 0 && t < 4) trace[(t * MAX_OPS + oi) * 8 + e] = clock64();
+}
+
 // ------------------------------------------------------------------------------------------------ op program
 // TMEM regions: X = columns [0,256), Y = [256,512). See the file header for the ping-pong scheme.
 __device__ void build_ops(TcShared& S, const AvcBlobHeader* hdr, int kind, int mode, bool texture, int* sb_total) {
@@ -374,6 +380,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
       uint32_t ph_a = 0, ph_epi = 0;   // per-barrier phase bits
       const uint32_t skip_addr = smem_u32(skip), ring_addr = smem_u32(ring);
       const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);   // LBO, SBO, version
+      int tl = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = S.ops[oi];
@@ -385,6 +392,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
           const uint32_t idesc = make_idesc(rows);
           const uint32_t part_bytes = (uint32_t)rows * 32u;
           if (o.wait_epi) { mbar_wait(&S.epi_done, ph_epi); ph_epi ^= 1; tc_fence_after(); }
+          if (lane == 0) trace_ev(a.trace, tl, oi, 0);
           for (int h = 0; h < n_halves; ++h) {
             const uint32_t d_addr = tmem + (uint32_t)(o.d_col + h * 128);
             uint32_t acc = o.accumulate ? 1u : 0u;
@@ -432,8 +440,10 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
               if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
             if (o.commit_d) { if (elect_one()) tc_commit(&S.d_ready[h]); __syncwarp(); }
+            if (lane == 0) trace_ev(a.trace, tl, oi, 1 + h);
           }
         }
+        ++tl;
       }
     }
   } else {
@@ -442,6 +452,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
     const int row = quad * 32 + lane;                  // point within the tile == TMEM lane
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t ph_d0 = 0, ph_d1 = 0;
+    int tl = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t g = tile * TILE + row;
       const bool valid = g < a.n;
@@ -509,11 +520,16 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
         const TcOp& o = S.ops[oi];
         if (!o.commit_d) continue;
         mbar_wait(&S.d_ready[0], ph_d0); ph_d0 ^= 1; tc_fence_after();
+        if (tid == 0) trace_ev(a.trace, tl, oi, 3);
         if (o.epi == EPI_HIDDEN) {
           const float* sb = s_sb + o.sb_off;
           const int n_chunks = o.n >> 5;
           for (int c = grp; c < n_chunks; c += 2) {
-            if (c == 4 + grp) { mbar_wait(&S.d_ready[1], ph_d1); ph_d1 ^= 1; tc_fence_after(); }   // second N-half (only 256-wide ops get here)
+            if (c == 4 + grp) {                                                                   // second N-half (only 256-wide ops get here)
+              if (tid == 0) trace_ev(a.trace, tl, oi, 4);
+              mbar_wait(&S.d_ready[1], ph_d1); ph_d1 ^= 1; tc_fence_after();
+              if (tid == 0) trace_ev(a.trace, tl, oi, 5);
+            }
             const uint32_t taddr = t_lane + (uint32_t)(o.d_col + c * 32);
             const float* sbc = sb + 64 * c;
             switch (o.act) {                                 // one branch per chunk, none per value
@@ -525,6 +541,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
             tc_fence_before(); __syncwarp();
             if (lane == 0) mbar_arrive(&S.a_ready[c]);
           }
+          if (tid == 0) trace_ev(a.trace, tl, oi, 6);
         } else {
           float v[4];
           tmem_ld4(t_lane + (uint32_t)o.d_col, v);
@@ -555,6 +572,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
           }
         }
       }
+      ++tl;
     }
   }
   tc_fence_before();
@@ -578,6 +596,7 @@ int launch_tc(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, co
   a.map = map ? map->d_hwc : nullptr; a.mC = map ? map->C : 0; a.mH = map ? map->H : 1; a.mW = map ? map->W : 1;
   a.out0 = out0; a.out_off = out_off; a.out_rgb = out_rgb; a.out_alpha = out_alpha; a.if_type = if_type; a.mode = mode; a.kind = kind;
   a.w16 = w.d_f16; a.f32 = w.d_f32; a.hdr = reinterpret_cast<const AvcBlobHeader*>(w.d_blob);
+  a.trace = reinterpret_cast<long long*>(ctx->d_trace);
   AVC_CUDA(ctx, cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int64_t tiles = (n + TILE - 1) / TILE;
   const int grid = (int)(tiles < (int64_t)ctx->sm_count ? tiles : ctx->sm_count);
