@@ -62,6 +62,7 @@ struct TcArgs {
   float* out0; float* out_off; float* out_rgb; float* out_alpha;   // out0 = occ (avatar) or ov (recon)
   int if_type, mode, kind;
   const unsigned char* w16; const float* f32; const AvcBlobHeader* hdr;
+  int n_ops; TcOp ops[MAX_OPS];   // the op program, built on the host: lives in the constant bank -> uniform registers
   long long* trace;   // optional timeline buffer (debug): [tile<4][op<24][8 events] clock64 stamps of CTA 0
 };
 
@@ -69,8 +70,7 @@ struct __align__(16) TcShared {
   unsigned long long full[N_STAGES], empty[N_STAGES];
   unsigned long long a_ready[8];
   unsigned long long d_ready[2], epi_done;   // d_ready[h]: N-half h of the current op is complete
-  unsigned int tmem_base; int n_ops; int pad[2];
-  TcOp ops[MAX_OPS];
+  unsigned int tmem_base; int pad[3];
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -246,12 +246,11 @@ __device__ __forceinline__ void trace_ev(long long* trace, int t, int oi, int e)
 
 // ------------------------------------------------------------------------------------------------ op program
 // TMEM regions: X = columns [0,256), Y = [256,512). See the file header for the ping-pong scheme.
-__device__ void build_ops(TcShared& S, const AvcBlobHeader* hdr, int kind, int mode, bool texture, int* sb_total) {
+void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool texture) {
   int n = 0, sb = 0;
   int sb_off[AVC_MAX_LAYERS];
   unsigned int stream_pos[AVC_MAX_LAYERS];      // running offset inside each layer's weight stream (pieces in op order)
   for (int l = 0; l < (int)hdr->n_layers; ++l) { sb_off[l] = sb; sb += 2 * hdr->layers[l].np; stream_pos[l] = (unsigned int)hdr->layers[l].tc_w_off; }
-  *sb_total = sb;
   auto add = [&](int layer, int nn, int row_off, int ks_s, int ks_s_w0, int ks_t, int ks_t_w0, int a_col, int d_col, int accum, int wait_epi,
                  int commit, int epi, int signal) {
     TcOp& o = S.ops[n++];
@@ -302,7 +301,7 @@ __device__ void build_ops(TcShared& S, const AvcBlobHeader* hdr, int kind, int m
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
+__global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) unsigned char dsm[];
   unsigned char* ring = dsm;                                       // N_STAGES * STAGE_BYTES
   unsigned char* skip = dsm + N_STAGES * STAGE_BYTES;              // SKIP_BYTES
@@ -311,13 +310,11 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool texture = (a.out_rgb != nullptr);
-  __shared__ int s_sb_total;
   if (tid == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
     for (int i = 0; i < 8; ++i) mbar_init(&S.a_ready[i], 4);
     mbar_init(&S.d_ready[0], 1); mbar_init(&S.d_ready[1], 1); mbar_init(&S.epi_done, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    int sbt; build_ops(S, a.hdr, a.kind, a.mode, texture, &sbt); s_sb_total = sbt;
   }
   if (warp == 8) {   // TMEM: all 512 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512) : "memory");
@@ -327,7 +324,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
-  const int n_ops = S.n_ops;
+  const int n_ops = a.n_ops;
   {  // stage {scale,bias} interleaved per channel: s_sb[2*c] = scale, s_sb[2*c+1] = bias (tensor-core variants: scale includes 2^-shift)
     int base = 0;
     for (int l = 0; l < (int)a.hdr->n_layers; ++l) {
@@ -349,7 +346,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < n_ops; ++oi) {
-          const TcOp& o = S.ops[oi];
+          const TcOp& o = a.ops[oi];
           const int n_halves = o.n == 256 ? 2 : 1;
           const uint32_t part_bytes = (uint32_t)(o.n / n_halves) * 32u;
           const unsigned char* src = a.w16 + o.w_off;
@@ -383,7 +380,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
       int tl = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < n_ops; ++oi) {
-          const TcOp& o = S.ops[oi];
+          const TcOp& o = a.ops[oi];
           // A 256-wide layer is issued as two N=128 halves, each over the full K. The epilogue of half 0 (accumulator columns
           // 0..127 -> A chunks 0..3 of the next layer) then overlaps the MMAs of half 1, and the next layer's half 0 can start on
           // chunks 0..3 the moment this layer's half 1 has been issued: the tensor pipe does not wait for the epilogue.
@@ -517,7 +514,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(TcArgs a) {
           if (lane == 0) mbar_arrive(&S.epi_done);      // input staged
         }
         if (oi == n_ops) break;
-        const TcOp& o = S.ops[oi];
+        const TcOp& o = a.ops[oi];
         if (!o.commit_d) continue;
         mbar_wait(&S.d_ready[0], ph_d0); ph_d0 ^= 1; tc_fence_after();
         if (tid == 0) trace_ev(a.trace, tl, oi, 3);
@@ -597,6 +594,7 @@ int launch_tc(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, co
   a.out0 = out0; a.out_off = out_off; a.out_rgb = out_rgb; a.out_alpha = out_alpha; a.if_type = if_type; a.mode = mode; a.kind = kind;
   a.w16 = w.d_f16; a.f32 = w.d_f32; a.hdr = reinterpret_cast<const AvcBlobHeader*>(w.d_blob);
   a.trace = reinterpret_cast<long long*>(ctx->d_trace);
+  build_ops(a, &w.hdr, kind, mode, out_rgb != nullptr);
   AVC_CUDA(ctx, cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int64_t tiles = (n + TILE - 1) / TILE;
   const int grid = (int)(tiles < (int64_t)ctx->sm_count ? tiles : ctx->sm_count);
