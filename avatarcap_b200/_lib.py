@@ -27,7 +27,7 @@ SIGNATURES = {
     'avc_has_tensor_core_path': (_i, [_vp]),
     'avc_launch_count': (_i64, [_vp]),
     'avc_reset_launch_count': (None, [_vp]),
-    'avc_debug_set_trace': (_i, [_vp, _vp]),
+    'avc_debug_set_trace': (_i, [_vp, _vp, _i]),
     'avc_load_avatar_weights': (_i, [_vp, _vp, C.c_size_t]),
     'avc_load_recon_weights': (_i, [_vp, _vp, C.c_size_t]),
     'avc_set_feature_map': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),

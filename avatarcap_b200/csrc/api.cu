@@ -80,7 +80,7 @@ extern "C" const char* avc_last_error(const avc_ctx* ctx) { return ctx ? ctx->er
 extern "C" int avc_has_tensor_core_path(const avc_ctx* ctx) { return ctx ? avc_tc_available(ctx) : 0; }
 extern "C" int64_t avc_launch_count(const avc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void avc_reset_launch_count(avc_ctx* ctx) { if (ctx) ctx->launches = 0; }
-extern "C" int avc_debug_set_trace(avc_ctx* ctx, void* dev_buf) { if (!ctx) return AVC_EINVAL; ctx->d_trace = dev_buf; return AVC_OK; }
+extern "C" int avc_debug_set_trace(avc_ctx* ctx, void* dev_buf, int flags) { if (!ctx) return AVC_EINVAL; ctx->d_trace = dev_buf; ctx->dbg_flags = flags; return AVC_OK; }
 
 // -----------------------------------------------------------------------------------------------------------------
 static int load_weights(avc_ctx* ctx, AvcWeights& w, const void* blob, size_t nbytes, uint32_t kind, uint32_t n_layers) {

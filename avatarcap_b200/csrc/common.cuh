@@ -65,6 +65,7 @@ struct avc_ctx {
   void* d_stage = nullptr;   size_t stage_cap = 0;
   cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
   int64_t* h_counts = nullptr;   // pinned, small
+  int dbg_flags = 0;             // avc_debug_set_trace(flags): timing experiments of the tensor-core kernel
   void* d_trace = nullptr;       // optional debug timeline buffer for the tensor-core kernel (avc_debug_set_trace)
 };
 

@@ -63,6 +63,7 @@ struct TcArgs {
   int if_type, mode, kind;
   const unsigned char* w16; const float* f32; const AvcBlobHeader* hdr;
   int n_ops; TcOp ops[MAX_OPS];   // the op program, built on the host: lives in the constant bank -> uniform registers
+  int dbg;            // debug experiments (timing only, results invalid): 1 = no weight streaming, 2 = one MMA pass instead of three
   long long* trace;   // optional timeline buffer (debug): [tile<4][op<24][8 events] clock64 stamps of CTA 0
 };
 
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
               const int ks = seg == 0 ? o.ks_smem : o.ks_tmem;
               for (int j = 0; j < ks; j += STAGE_KSTEPS) {
                 const uint32_t bytes = (uint32_t)min(STAGE_KSTEPS, ks - j) * 2u * part_bytes;
+                if (a.dbg & 1) continue;
                 mbar_wait(&S.empty[stage], phase ^ 1);
                 if (elect_one()) {
                   mbar_expect_tx(&S.full[stage], bytes);
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
             uint32_t acc = o.accumulate ? 1u : 0u;
             for (int j = 0; j < o.ks_smem; j += STAGE_KSTEPS) {
               const int cnt = min(STAGE_KSTEPS, o.ks_smem - j);
-              mbar_wait(&S.full[stage], phase); tc_fence_after();
+              if (!(a.dbg & 1)) { mbar_wait(&S.full[stage], phase); tc_fence_after(); }
               if (elect_one()) {
                 for (int u = 0; u < cnt; ++u) {
                   const uint32_t b_addr = ring_addr + stage * STAGE_BYTES + u * 2 * part_bytes;
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
                   mma_ss(d_addr, a_lo, b_hi, idesc, 1u);
                   mma_ss(d_addr, a_hi, b_lo, idesc, 1u);
                 }
-                tc_commit(&S.empty[stage]);
+                if (!(a.dbg & 1)) tc_commit(&S.empty[stage]);
               }
               acc = 1u;
               __syncwarp();
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
                 mbar_wait(&S.a_ready[2 * c2], (ph_a >> (2 * c2)) & 1u); mbar_wait(&S.a_ready[2 * c2 + 1], (ph_a >> (2 * c2 + 1)) & 1u);
                 ph_a ^= (3u << (2 * c2));
               }
-              mbar_wait(&S.full[stage], phase); tc_fence_after();
+              if (!(a.dbg & 1)) { mbar_wait(&S.full[stage], phase); tc_fence_after(); }
               if (elect_one()) {
                 const uint32_t b0 = ring_addr + stage * STAGE_BYTES;
                 const uint32_t a0 = tmem + (uint32_t)o.a_col + (uint32_t)(c2 * 64);
@@ -427,10 +429,12 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
                   const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
                   const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
                   mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-                  mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
-                  mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+                  if (!(a.dbg & 2)) {
+                    mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
+                    mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+                  }
                 }
-                tc_commit(&S.empty[stage]);
+                if (!(a.dbg & 1)) tc_commit(&S.empty[stage]);
               }
               acc = 1u;
               __syncwarp();
@@ -593,7 +597,7 @@ int launch_tc(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, co
   a.map = map ? map->d_hwc : nullptr; a.mC = map ? map->C : 0; a.mH = map ? map->H : 1; a.mW = map ? map->W : 1;
   a.out0 = out0; a.out_off = out_off; a.out_rgb = out_rgb; a.out_alpha = out_alpha; a.if_type = if_type; a.mode = mode; a.kind = kind;
   a.w16 = w.d_f16; a.f32 = w.d_f32; a.hdr = reinterpret_cast<const AvcBlobHeader*>(w.d_blob);
-  a.trace = reinterpret_cast<long long*>(ctx->d_trace);
+  a.trace = reinterpret_cast<long long*>(ctx->d_trace); a.dbg = ctx->dbg_flags;
   build_ops(a, &w.hdr, kind, mode, out_rgb != nullptr);
   AVC_CUDA(ctx, cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int64_t tiles = (n + TILE - 1) / TILE;

@@ -66,7 +66,7 @@ int64_t avc_launch_count(const avc_ctx* ctx);
 void    avc_reset_launch_count(avc_ctx* ctx);
 /* debugging aid: [dev] buffer of 4*24*8 int64 that the tensor-core kernel fills with clock64() stamps of CTA 0's
  * first tiles (op start / issue end / accumulator-ready / epilogue-done); NULL disables it (default). */
-int avc_debug_set_trace(avc_ctx* ctx, void* dev_buf /*[dev]|NULL*/);
+int avc_debug_set_trace(avc_ctx* ctx, void* dev_buf /*[dev]|NULL*/, int flags /*0; non-zero = timing experiments, results invalid*/);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* weights -- replaces torch.load(...)['network'] + nn.Module parameters (main.py:302-320)        */

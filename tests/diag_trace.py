@@ -16,6 +16,7 @@ from avatarcap_b200.engine import Engine  # noqa: E402
 
 def main():
     tex = bool(int(sys.argv[1])) if len(sys.argv) > 1 else True
+    flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     eng = Engine()
     s = tpose_scene(256)
     eng.load_avatar(s['avatar_sd']); eng.set_pose_feature_map(s['pose_map'])
@@ -23,12 +24,12 @@ def main():
     pts = eng.make_grid(fr['cano_bounds'], (128, 128, 128))
     buf = torch.zeros(4 * 24 * 8, dtype=torch.int64, device=eng.device)
     eng.eval_occupancy(pts, fr['cano_smpl_center'], want_texture=tex, impl='tc'); torch.cuda.synchronize()    # warm
-    eng.lib.avc_debug_set_trace(eng._h, C.c_void_p(buf.data_ptr()))
+    eng.lib.avc_debug_set_trace(eng._h, C.c_void_p(buf.data_ptr()), flags)
     eng.eval_occupancy(pts, fr['cano_smpl_center'], want_texture=tex, impl='tc'); torch.cuda.synchronize()
-    eng.lib.avc_debug_set_trace(eng._h, None)
+    eng.lib.avc_debug_set_trace(eng._h, None, 0)
     t = buf.cpu().numpy().reshape(4, 24, 8)
     n_ops = 20 if tex else 17
-    for tile in (1, 2):
+    for tile in (1,):
         base = t[tile, 0, 0]
         print('tile %d (cycles relative to the tile\'s first MMA op start; tile period %d)' % (tile, t[tile + 1, 0, 0] - base if tile < 3 else -1))
         print(' op |  mma_start  issued_h0  issued_h1 | d0_seen  h0_done  d1_seen  epi_done | op period')
