@@ -25,7 +25,7 @@
 namespace {
 
 constexpr int TILE = 128;                 // points per tile == UMMA M
-constexpr int NT = 320;                   // 8 compute warps + MMA warp + producer warp
+constexpr int NT = 352;                   // 8 compute warps + 2 alternating MMA-issuer warps + producer warp
 constexpr int N_STAGES = 4;
 constexpr int STAGE_KSTEPS = 4;           // k-steps per ring stage (== two 32-column A chunks)
 constexpr int STAGE_BYTES = STAGE_KSTEPS * 8192;   // per k-step of one N-half: hi (128 rows * 32 B) + lo (128 rows * 32 B)
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
   __syncthreads();
   const int64_t n_tiles = (a.n + TILE - 1) / TILE;
 
-  if (warp == 9) {
+  if (warp == 10) {
     // ============================================================ weight producer: the layer's weights are stored as a stream in
     // exactly the order and layout the ring consumes them (packer.py), so one bulk copy per stage is all it takes.
     {
@@ -371,15 +371,20 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
         }
       }
     }
-  } else if (warp == 8) {
-    // ============================================================ MMA issuer: the whole warp walks the (warp-uniform) program,
-    // one elected lane issues. Keeping the warp converged lets the compiler keep descriptors in uniform registers.
+  } else if (warp >= 8) {
+    // ============================================================ MMA issuers: warps 8 and 9 walk the same (warp-uniform) program and
+    // take the ring stages in turn (stage g belongs to warp 8 + (g & 1)). While one warp issues its 12 MMAs the other is already past
+    // its barrier waits and descriptor set-up, so the fixed per-stage latency of a single instruction stream (~600 cycles measured) no
+    // longer paces the tensor pipe. Issue ORDER is preserved by a named-barrier hand-off (bar 1: warp 8 may issue, bar 2: warp 9 may).
     {
+      const int me = warp - 8;
       int stage = 0; uint32_t phase = 0;
-      uint32_t ph_a = 0, ph_epi = 0;   // per-barrier phase bits
+      uint32_t ph_a = 0, ph_epi = 0;   // per-barrier phase bits (tracked by both warps, waited on by the stage owner)
+      uint32_t g = 0;                  // global stage counter
       const uint32_t skip_addr = smem_u32(skip), ring_addr = smem_u32(ring);
       const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);   // LBO, SBO, version
       int tl = 0;
+      if (me == 1) asm volatile("bar.arrive 1, 64;" ::: "memory");      // warp 8 owns stage 0
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = a.ops[oi];
@@ -390,58 +395,75 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
           const int rows = o.n / n_halves;
           const uint32_t idesc = make_idesc(rows);
           const uint32_t part_bytes = (uint32_t)rows * 32u;
-          if (o.wait_epi) { mbar_wait(&S.epi_done, ph_epi); ph_epi ^= 1; tc_fence_after(); }
-          if (lane == 0) trace_ev(a.trace, tl, oi, 0);
+          bool need_epi = o.wait_epi != 0;
+          if (lane == 0 && (int)(g & 1) == me) trace_ev(a.trace, tl, oi, 0);
           for (int h = 0; h < n_halves; ++h) {
             const uint32_t d_addr = tmem + (uint32_t)(o.d_col + h * 128);
             uint32_t acc = o.accumulate ? 1u : 0u;
-            for (int j = 0; j < o.ks_smem; j += STAGE_KSTEPS) {
+            for (int j = 0; j < o.ks_smem; j += STAGE_KSTEPS, ++g) {
               const int cnt = min(STAGE_KSTEPS, o.ks_smem - j);
-              if (!(a.dbg & 1)) { mbar_wait(&S.full[stage], phase); tc_fence_after(); }
-              if (elect_one()) {
-                for (int u = 0; u < cnt; ++u) {
-                  const uint32_t b_addr = ring_addr + stage * STAGE_BYTES + u * 2 * part_bytes;
-                  const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
-                  const uint32_t a_addr = skip_addr + (j + u) * 8192;
-                  const uint64_t a_hi = desc_hi | (uint64_t)(a_addr >> 4), a_lo = desc_hi | (uint64_t)((a_addr + 4096) >> 4);
-                  mma_ss(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-                  mma_ss(d_addr, a_lo, b_hi, idesc, 1u);
-                  mma_ss(d_addr, a_hi, b_lo, idesc, 1u);
-                }
-                if (!(a.dbg & 1)) tc_commit(&S.empty[stage]);
-              }
-              acc = 1u;
-              __syncwarp();
-              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
-            }
-            for (int c2 = 0; c2 < (o.ks_tmem >> 2); ++c2) {   // one ring stage = 4 k-steps = two 32-column A chunks
-              if (o.wait_a && h == 0) {
-                mbar_wait(&S.a_ready[2 * c2], (ph_a >> (2 * c2)) & 1u); mbar_wait(&S.a_ready[2 * c2 + 1], (ph_a >> (2 * c2 + 1)) & 1u);
-                ph_a ^= (3u << (2 * c2));
-              }
-              if (!(a.dbg & 1)) { mbar_wait(&S.full[stage], phase); tc_fence_after(); }
-              if (elect_one()) {
-                const uint32_t b0 = ring_addr + stage * STAGE_BYTES;
-                const uint32_t a0 = tmem + (uint32_t)o.a_col + (uint32_t)(c2 * 64);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const uint32_t b_addr = b0 + u * 2 * part_bytes;
-                  const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
-                  const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
-                  mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-                  if (!(a.dbg & 2)) {
-                    mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
-                    mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+              if ((int)(g & 1) == me) {
+                if (need_epi) { mbar_wait(&S.epi_done, ph_epi); }
+                if (!(a.dbg & 1)) mbar_wait(&S.full[stage], phase);
+                tc_fence_after();
+                if (me == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+                if (elect_one()) {
+                  for (int u = 0; u < cnt; ++u) {
+                    const uint32_t b_addr = ring_addr + stage * STAGE_BYTES + u * 2 * part_bytes;
+                    const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
+                    const uint32_t a_addr = skip_addr + (j + u) * 8192;
+                    const uint64_t a_hi = desc_hi | (uint64_t)(a_addr >> 4), a_lo = desc_hi | (uint64_t)((a_addr + 4096) >> 4);
+                    mma_ss(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
+                    mma_ss(d_addr, a_lo, b_hi, idesc, 1u);
+                    mma_ss(d_addr, a_hi, b_lo, idesc, 1u);
                   }
+                  if (!(a.dbg & 1)) tc_commit(&S.empty[stage]);
                 }
-                if (!(a.dbg & 1)) tc_commit(&S.empty[stage]);
+                __syncwarp();
+                if (me == 0) asm volatile("bar.arrive 2, 64;" ::: "memory"); else asm volatile("bar.arrive 1, 64;" ::: "memory");
               }
+              if (need_epi) { ph_epi ^= 1; need_epi = false; }
               acc = 1u;
-              __syncwarp();
               if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
             }
-            if (o.commit_d) { if (elect_one()) tc_commit(&S.d_ready[h]); __syncwarp(); }
-            if (lane == 0) trace_ev(a.trace, tl, oi, 1 + h);
+            for (int c2 = 0; c2 < (o.ks_tmem >> 2); ++c2, ++g) {   // one ring stage = 4 k-steps = two 32-column A chunks
+              const bool wa = o.wait_a && h == 0;
+              if ((int)(g & 1) == me) {
+                if (need_epi) { mbar_wait(&S.epi_done, ph_epi); }
+                if (wa) { mbar_wait(&S.a_ready[2 * c2], (ph_a >> (2 * c2)) & 1u); mbar_wait(&S.a_ready[2 * c2 + 1], (ph_a >> (2 * c2 + 1)) & 1u); }
+                if (!(a.dbg & 1)) mbar_wait(&S.full[stage], phase);
+                tc_fence_after();
+                if (me == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
+                if (elect_one()) {
+                  const uint32_t b0 = ring_addr + stage * STAGE_BYTES;
+                  const uint32_t a0 = tmem + (uint32_t)o.a_col + (uint32_t)(c2 * 64);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const uint32_t b_addr = b0 + u * 2 * part_bytes;
+                    const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
+                    const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
+                    mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
+                    if (!(a.dbg & 2)) {
+                      mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
+                      mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+                    }
+                  }
+                  if (!(a.dbg & 1)) tc_commit(&S.empty[stage]);
+                }
+                __syncwarp();
+                if (me == 0) asm volatile("bar.arrive 2, 64;" ::: "memory"); else asm volatile("bar.arrive 1, 64;" ::: "memory");
+              }
+              if (wa) ph_a ^= (3u << (2 * c2));
+              if (need_epi) { ph_epi ^= 1; need_epi = false; }
+              acc = 1u;
+              if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
+            }
+            // the owner of this half's LAST stage signals the epilogue: its commit fires when its own MMAs are done, and the pipe
+            // completes MMAs in issue order, so everything before them is done too
+            if ((int)((g - 1) & 1) == me) {
+              if (o.commit_d) { if (elect_one()) tc_commit(&S.d_ready[h]); __syncwarp(); }
+              if (lane == 0) trace_ev(a.trace, tl, oi, 1 + h);
+            }
           }
         }
         ++tl;
