@@ -196,14 +196,29 @@ template <int ACT>
 __device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __restrict__ sbc) {
   float v[32];
   tmem_ld32(taddr, v);
-  uint32_t hi[16], lo[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float4 s4 = *reinterpret_cast<const float4*>(sbc + 4 * i);   // {scale0, bias0, scale1, bias1}
-    const float v0 = act_tc<ACT>(fmaf(v[2 * i], s4.x, s4.y));
-    const float v1 = act_tc<ACT>(fmaf(v[2 * i + 1], s4.z, s4.w));
-    split2(v0, v1, hi[i], lo[i]);
+    v[2 * i] = fmaf(v[2 * i], s4.x, s4.y);
+    v[2 * i + 1] = fmaf(v[2 * i + 1], s4.z, s4.w);
   }
+  if (ACT == AVC_ACT_SOFTPLUS) {
+    // softplus(v) = max(v,0) + ln2 * log2(1 + 2^(-|v| log2e)), in PHASES over the 32 values so that the 64 MUFU ops of a chunk are
+    // independent and back to back (the XU pipe, 16 lanes/clk/SM, is what bounds the OffsetDecoder layers' epilogue).
+    float t[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] = exp2f(-fabsf(v[i]) * 1.4426950408889634f);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] = __log2f(1.f + t[i]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(t[i], 0.6931471805599453f, fmaxf(v[i], 0.f));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = act_tc<ACT>(v[i]);
+  }
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
   tmem_st16(taddr, hi);            // k-steps 2c, 2c+1: hi in columns [0,16) of the chunk
   tmem_st16(taddr + 16u, lo);      //                   lo in columns [16,32)
   tmem_st_wait();
