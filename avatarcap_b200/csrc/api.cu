@@ -215,6 +215,14 @@ static int ensure_staging(avc_ctx* ctx, size_t bytes) {
   return AVC_OK;
 }
 
+// true when `p` is page-locked host memory (cudaMallocHost / cudaHostRegister / torch pin_memory): the DMA engines can use it directly
+static bool is_pinned_host(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, const float center[3], float* out_a, float* out_off, float* out_rgb,
                      float* out_alpha, int if_type, int impl) {
   if (!ctx) return AVC_EINVAL;
@@ -225,6 +233,9 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
   const size_t slot_floats = (size_t)chunk * 11;
   int rc = ensure_staging(ctx, 2 * slot_floats * sizeof(float));
   if (rc) return rc;
+  // buffers that are already page-locked skip the staging copy (DMA straight from / into the caller's memory)
+  const bool pin_in = is_pinned_host(pts), pin_a = is_pinned_host(out_a), pin_off = is_pinned_host(out_off), pin_rgb = is_pinned_host(out_rgb),
+             pin_al = is_pinned_host(out_alpha);
   cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
   for (int s = 0; s < 2; ++s) { cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming); }
   const int64_t n_chunks = (n + chunk - 1) / chunk;
@@ -236,17 +247,17 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
       const int s = (int)(c & 1); const int64_t b = (c - 2) * chunk; const int64_t m = (n - b < chunk) ? n - b : chunk;
       if (cudaEventSynchronize(ev_out[s]) != cudaSuccess) { status = avc_check_cuda(ctx, cudaGetLastError(), "host eval: D2H"); break; }
       float* hp = (float*)ctx->h_pinned + (size_t)s * slot_floats;
-      memcpy(out_a + b, hp + (size_t)chunk * 3, (size_t)m * sizeof(float));
-      if (out_off) memcpy(out_off + b * 3, hp + (size_t)chunk * 4, (size_t)m * 3 * sizeof(float));
-      if (out_rgb) memcpy(out_rgb + b * 3, hp + (size_t)chunk * 7, (size_t)m * 3 * sizeof(float));
-      if (out_alpha) memcpy(out_alpha + b, hp + (size_t)chunk * 10, (size_t)m * sizeof(float));
+      if (!pin_a) memcpy(out_a + b, hp + (size_t)chunk * 3, (size_t)m * sizeof(float));
+      if (out_off && !pin_off) memcpy(out_off + b * 3, hp + (size_t)chunk * 4, (size_t)m * 3 * sizeof(float));
+      if (out_rgb && !pin_rgb) memcpy(out_rgb + b * 3, hp + (size_t)chunk * 7, (size_t)m * 3 * sizeof(float));
+      if (out_alpha && !pin_al) memcpy(out_alpha + b, hp + (size_t)chunk * 10, (size_t)m * sizeof(float));
     }
     if (c < n_chunks) {
       const int s = (int)(c & 1); const int64_t b = c * chunk; const int64_t m = (n - b < chunk) ? n - b : chunk;
       float* hp = (float*)ctx->h_pinned + (size_t)s * slot_floats;
       float* dp = (float*)ctx->d_stage + (size_t)s * slot_floats;
-      memcpy(hp, pts + b * 3, (size_t)m * 3 * sizeof(float));
-      cudaMemcpyAsync(dp, hp, (size_t)m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->s_copy_in);
+      if (!pin_in) memcpy(hp, pts + b * 3, (size_t)m * 3 * sizeof(float));
+      cudaMemcpyAsync(dp, pin_in ? pts + b * 3 : hp, (size_t)m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->s_copy_in);
       cudaEventRecord(ev_in[s], ctx->s_copy_in);
       cudaStreamWaitEvent(ctx->s_compute, ev_in[s], 0);
       float* d_occ = dp + (size_t)chunk * 3; float* d_off = dp + (size_t)chunk * 4;
@@ -257,10 +268,10 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
       if (status != AVC_OK) break;
       cudaEventRecord(ev_k[s], ctx->s_compute);
       cudaStreamWaitEvent(ctx->s_copy_out, ev_k[s], 0);
-      cudaMemcpyAsync(hp + (size_t)chunk * 3, d_occ, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
-      if (out_off) cudaMemcpyAsync(hp + (size_t)chunk * 4, d_off, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
-      if (out_rgb) cudaMemcpyAsync(hp + (size_t)chunk * 7, d_rgb, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
-      if (out_alpha) cudaMemcpyAsync(hp + (size_t)chunk * 10, d_alpha, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      cudaMemcpyAsync(pin_a ? out_a + b : hp + (size_t)chunk * 3, d_occ, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      if (out_off) cudaMemcpyAsync(pin_off ? out_off + b * 3 : hp + (size_t)chunk * 4, d_off, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      if (out_rgb) cudaMemcpyAsync(pin_rgb ? out_rgb + b * 3 : hp + (size_t)chunk * 7, d_rgb, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
+      if (out_alpha) cudaMemcpyAsync(pin_al ? out_alpha + b : hp + (size_t)chunk * 10, d_alpha, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       cudaEventRecord(ev_out[s], ctx->s_copy_out);
       // the next use of this slot's device buffer (chunk c+2) must wait for this D2H
       cudaStreamWaitEvent(ctx->s_copy_in, ev_out[s], 0);

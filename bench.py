@@ -27,6 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_PT = {'occ': 1_773_568, 'occ+tex': 1_970_944, 'recon': 387_072}     # SURVEY.md section 8 / BASELINE.md section 2
+# dram__bytes_read.sum + dram__bytes_write.sum of field_tc_kernel at 256^3, one launch (profiles/r1_ncu_tc_v6_256cube.md)
+NCU_TRAFFIC_BYTES = 712_916_736
 GRIDS = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512, 512, 512)}
 
 
@@ -249,12 +251,42 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(mt, op=dist.ReduceOp.MAX); dist.all_reduce(nv)
 
+    # ---- the reference's own per-frame geometry pipeline (main.py:357-389), MASKED like the reference: only grid points within
+    # 10 cm of the body are evaluated, the rest is +-1 fill; N=1 only. Reported as `frame` (ms per stage), not part of `value`.
+    frame_ms = None
+    if world == 1 and not args.no_frame:
+        from avatarcap_b200 import pipeline, synth
+        flag = pipeline.valid_points_flag(eng, pts, cv)
+        fill_np = 2.0 * synth.body_inside(pts[~flag].cpu().numpy(), synth.cano_pose()).astype(np.float32) - 1.0
+        fill = torch.from_numpy(fill_np).to(dev); vpts = pts[flag].contiguous()
+        fdev = {'cano_smpl_v': cv, 'smpl_skinning_weights': sw, 'cano2live_jnt_mats': jm, 'cano_bounds': frame['cano_bounds'],
+                'cano_smpl_center': center}
+
+        def timed(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                out = fn()
+            a1.record(); torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / reps, out
+        t_field, o = timed(lambda: eng.eval_occupancy(vpts, center, want_offsets=True, impl=impl))
+        t_scat, vol_m = timed(lambda: eng.scatter_fill(flag, o['occ'], fill))
+        vol_m = vol_m.reshape(res)
+        t_mesh, (mv, mf, mn) = timed(lambda: eng.extract_mesh(vol_m, frame['cano_bounds'], 0.0))
+        t_lbs, _ = timed(lambda: eng.skin_mesh(mv, mn, cv, sw, jm))
+        t_all, _ = timed(lambda: pipeline.avatar_frame(eng, fdev, scene['pose_map'], res, flag, vpts, fill, 0.0, impl), reps=2)
+        frame_ms = {'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
+                    'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
+
     # ---- end to end through the host-buffer C-ABI entry: H2D of the points and D2H of every output inside the timed region
     e2e = None
     if not args.no_e2e:
         pts_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
         pts_h.copy_(pts.cpu())
-        occ_h = np.empty(n, np.float32); off_h = np.empty((n, 3), np.float32); rgb_h = np.empty((n, 3), np.float32); al_h = np.empty(n, np.float32)
+        # host result buffers are page-locked like the input (torch pin_memory), so the library DMAs straight into them
+        occ_h = torch.empty(n, dtype=torch.float32).pin_memory().numpy(); off_h = torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy()
+        rgb_h = torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy(); al_h = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
         ph = pts_h.numpy()
         eng.eval_occupancy_host(ph, center, occ_h, off_h, rgb_h, al_h, impl=impl)       # warm-up
         barrier()
@@ -287,13 +319,15 @@ def run_ours(args):
                        'grid': list(res), 'points_per_gpu': n, 'kernel': impl, 'flop_per_point': flop,
                        'l2_policy': 'inputs (201 MB of points) + outputs (537 MB) exceed the 126 MB L2 every step'},
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                         'traffic': None, 'peak_source': peak_src + ', sustained bf16 (kernel timed inside a long step)',
+                         'traffic': NCU_TRAFFIC_BYTES if (args.gpus == 1 and args.res is None) else None, 'peak_source': peak_src + ', sustained bf16 (kernel timed inside a long step)',
                          'note': 'algorithmic FLOPs (1x); the tcgen05 kernel issues 3x that as fp16 hi/lo passes'},
             'mesh_extract_ms': float(mt[0]), 'lbs_skin_ms': float(mt[1]), 'mesh_vertices': int(nv[0]), 'mesh_faces': int(nv[1]),
             'clocks': clocks, 'gpu_launches': int(launches), 'wall_s': t_wall,
         }
         if e2e:
             line['e2e'] = e2e
+        if frame_ms:
+            line['frame'] = frame_ms
         if args.gpus == 1 and not args.no_cpu:
             threads = host_cores()
             sub = strided_sample(scene, res, 64 ** 3)
@@ -316,6 +350,7 @@ def main():
     ap.add_argument('--res', type=int, default=None, help='override the per-GPU grid edge (debug only; the metric is quoted at 256)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-frame', action='store_true')
     args = ap.parse_args()
     if args.gpus not in GRIDS:
         raise SystemExit('--gpus must be one of 1, 2, 4, 8')

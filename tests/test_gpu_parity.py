@@ -348,3 +348,28 @@ def test_config3_full_frame_masked(eng, res):
         lbs = fo.calculate_lbs(rv, fr['cano_smpl_v'], fr['smpl_skinning_weights'])
         live, _ = fo.skinning(rv, lbs, fr['cano2live_jnt_mats'])
         assert mo.chamfer(out['live_verts'].cpu().numpy(), live) < 1e-3
+
+
+@pytest.mark.parametrize('pinned', [False, True])
+def test_host_buffer_entry_points(eng, scene, pinned):
+    """avc_eval_occupancy_host / avc_eval_recon_host (the end-to-end entry bench.py times): host in, host out, chunked
+    3-stream pipeline; must equal the device-pointer entry bit for bit, for pageable and for page-locked buffers."""
+    g = load_golden('avatar_golden.npz')
+    n = (1 << 21) + 12345                                   # more than one pipeline chunk, ragged tail
+    reps = n // len(g['pts']) + 1
+    pts = np.tile(g['pts'], (reps, 1))[:n].copy()
+    pts += np.random.RandomState(1).normal(0, 0.01, pts.shape).astype(np.float32)
+    eng.set_pose_feature_map(scene['pose_map']); eng.set_image_feature_map(scene['image_map'])
+
+    def buf(shape):
+        t = torch.empty(shape, dtype=torch.float32)
+        return (t.pin_memory() if pinned else t).numpy()
+    p_h = buf((n, 3)); p_h[:] = pts
+    occ, off, rgb, al, ov = buf(n), buf((n, 3)), buf((n, 3)), buf(n), buf(n)
+    eng.eval_occupancy_host(p_h, g['center'], occ, off, rgb, al)
+    eng.eval_recon_host(p_h, g['center'], ov)
+    d = eng.eval_occupancy(pts, g['center'], want_texture=True)
+    assert np.array_equal(occ, d['occ'].cpu().numpy()) and np.array_equal(off, d['off'].cpu().numpy())
+    assert np.array_equal(rgb, d['rgb'].cpu().numpy()) and np.array_equal(al, d['alpha'].cpu().numpy())
+    assert np.array_equal(ov, eng.eval_recon(pts, g['center']).cpu().numpy())
+    assert maxabs(occ[:3000], g['cano_pts_ov'][:, 0]) < 0.2      # perturbed points, same field
