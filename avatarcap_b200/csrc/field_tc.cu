@@ -126,6 +126,15 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, u
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// same with an A-collector hint: 1 = fill (keep A in the collector buffer), 2 = lastuse (take A from the collector buffer)
+__device__ __forceinline__ void mma_ts_c(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc, int coll) {
+  if (coll == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 // K-major, no swizzle: core matrix = 8 rows x 16 B; LBO = 128 B between the two k-halves, SBO = 256 B between 8-row groups
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
@@ -171,6 +180,24 @@ __device__ __forceinline__ float act_tc(float v) {
     return fmaf(__log2f(1.f + t), 0.6931471805599453f, fmaxf(v, 0.f));
   }
   return v;
+}
+// sin/cos for |x| < ~1e4 (the PE arguments reach 2^9 * |q| ~ 600): Cody-Waite reduction by pi/2 with three fused steps, then the
+// fdlibm single-precision kernels on [-pi/4, pi/4]. Max abs error 9.2e-8 over the PE range (numpy float32 sin: 6.9e-8); ~25
+// instructions for the pair, a third of sincosf().
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+  const float k = rintf(x * 0.63661977236758138f);
+  float r = fmaf(k, -1.5707964e+00f, x);
+  r = fmaf(k, 4.371139e-08f, r);
+  r = fmaf(k, 1.7151245e-15f, r);
+  const float r2 = r * r;
+  float ps = fmaf(2.7557314297e-06f, r2, -1.9841270114e-04f); ps = fmaf(ps, r2, 8.3333337680e-03f); ps = fmaf(ps, r2, -1.6666667163e-01f);
+  const float sn = fmaf(r * r2, ps, r);
+  float pc = fmaf(-2.7557314297e-07f, r2, 2.4801587642e-05f); pc = fmaf(pc, r2, -1.3888889225e-03f); pc = fmaf(pc, r2, 4.1666667908e-02f);
+  const float cs = fmaf(r2 * r2, pc, fmaf(r2, -0.5f, 1.f));
+  const int q = (int)k;
+  const float a = (q & 1) ? cs : sn, b = (q & 1) ? sn : cs;
+  s = (q & 2) ? -a : a;
+  c = ((q + 1) & 2) ? -b : b;
 }
 // split (v0, v1) into packed fp16 hi and lo words (element with the lower k index in the low 16 bits)
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
@@ -457,10 +484,16 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
                     const uint32_t b_addr = b0 + u * 2 * part_bytes;
                     const uint64_t b_hi = desc_hi | (uint64_t)(b_addr >> 4), b_lo = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
                     const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
-                    mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
-                    if (!(a.dbg & 2)) {
+                    if (a.dbg & 4) {          // experiment: hi*hi and hi*lo back to back, A (hi) held in the collector buffer
+                      mma_ts_c(d_addr, a_hi, b_hi, idesc, acc, 1); acc = 1u;
+                      mma_ts_c(d_addr, a_hi, b_lo, idesc, 1u, 2);
                       mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
-                      mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+                    } else {
+                      mma_ts(d_addr, a_hi, b_hi, idesc, acc); acc = 1u;
+                      if (!(a.dbg & 2)) {
+                        mma_ts(d_addr, a_lo, b_hi, idesc, 1u);
+                        mma_ts(d_addr, a_hi, b_lo, idesc, 1u);
+                      }
                     }
                   }
                   if (!(a.dbg & 1)) tc_commit(&S.empty[stage]);
@@ -543,7 +576,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
             const float fr = (float)(1 << f);
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-              float s, c; sincosf(qq[d] * fr, &s, &c);
+              float s, c; fast_sincos(qq[d] * fr, s, c);
               put(3 + 6 * f + d, s); put(3 + 6 * f + 3 + d, c);
             }
           }
