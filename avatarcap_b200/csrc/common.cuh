@@ -9,7 +9,7 @@
 #include "../../include/avatarcap_b200.h"
 
 #define AVC_MAGIC 0x57435641u /* 'AVCW' */
-#define AVC_BLOB_VERSION 4u
+#define AVC_BLOB_VERSION 3u
 #define AVC_MAX_LAYERS 24
 
 // Fixed layer order inside a blob (packer.py writes them in this order).
@@ -26,7 +26,7 @@ struct AvcLayerDesc {
   int32_t wt_off;      // f32 section, float index: W^T[(k0+k1)][n] (row k holds n contiguous outputs); heads (n<=4): W[n][k0+k1]
   int32_t sb_off;      // f32 section, float index: scale[n] then bias[n]   (y = acc*scale + bias)
   int32_t tc_w_off;    // f16 section, byte offset of the layer's weight STREAM in tensor-core consumption order (packer.py tc_pieces)
-  int32_t tc_sb_off;   // f32 section, float index: np interleaved {scale,bias} pairs for the tensor-core path (scale includes 2^-wshift)
+  int32_t tc_sb_off;   // f32 section, float index: scale[np] then bias[np] for the tensor-core path (scale includes 2^-wshift)
   int32_t reserved;
 };
 

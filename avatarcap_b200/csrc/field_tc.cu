@@ -49,7 +49,7 @@ struct TcOp {
   int commit_d;       // signal the epilogue when this op's MMAs are complete
   int epi;            // epilogue kind (0 = none)
   int act;
-  int sb_off;         // float offset of this op's interleaved {scale,bias} pairs in the blob's f32 section
+  int sb_off;         // float offset of {scale,bias} pairs in shared memory
   int signal_done;    // compute warps arrive on epi_done after this op's epilogue
   unsigned int w_off; // byte offset of this op's weight stream in the f16 section
   int wait_a;         // the TMEM A chunks are produced by the preceding epilogue (0: already complete, e.g. the colour head re-reads s7)
@@ -63,7 +63,7 @@ struct TcArgs {
   int if_type, mode, kind;
   const unsigned char* w16; const float* f32; const AvcBlobHeader* hdr;
   int n_ops; TcOp ops[MAX_OPS];   // the op program, built on the host: lives in the constant bank -> uniform registers
-  int dbg;            // debug experiments (timing only, results invalid): 1 = no weight streaming, 2 = one MMA pass instead of three
+  int dbg;            // reserved (debug experiments are compiled out)
   long long* trace;   // optional timeline buffer (debug): [tile<4][op<24][8 events] clock64 stamps of CTA 0
 };
 
@@ -225,7 +225,7 @@ __device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __rest
   tmem_ld32(taddr, v);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float4 s4 = __ldg(reinterpret_cast<const float4*>(sbc) + i);   // {scale0, bias0, scale1, bias1}: warp-uniform address, L1-resident
+    const float4 s4 = *reinterpret_cast<const float4*>(sbc + 4 * i);   // {scale0, bias0, scale1, bias1}
     v[2 * i] = fmaf(v[2 * i], s4.x, s4.y);
     v[2 * i + 1] = fmaf(v[2 * i + 1], s4.z, s4.w);
   }
@@ -293,7 +293,7 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
   int n = 0, sb = 0;
   int sb_off[AVC_MAX_LAYERS];
   unsigned int stream_pos[AVC_MAX_LAYERS];      // running offset inside each layer's weight stream (pieces in op order)
-  for (int l = 0; l < (int)hdr->n_layers; ++l) { sb_off[l] = hdr->layers[l].tc_sb_off; sb += 2 * hdr->layers[l].np; stream_pos[l] = (unsigned int)hdr->layers[l].tc_w_off; }
+  for (int l = 0; l < (int)hdr->n_layers; ++l) { sb_off[l] = sb; sb += 2 * hdr->layers[l].np; stream_pos[l] = (unsigned int)hdr->layers[l].tc_w_off; }
   auto add = [&](int layer, int nn, int row_off, int ks_s, int ks_s_w0, int ks_t, int ks_t_w0, int a_col, int d_col, int accum, int wait_epi,
                  int commit, int epi, int signal) {
     TcOp& o = S.ops[n++];
@@ -347,9 +347,9 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
 __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) unsigned char dsm[];
   unsigned char* ring = dsm;                                       // N_STAGES * STAGE_BYTES
-  unsigned char* skip0 = dsm + N_STAGES * STAGE_BYTES;             // 2 x SKIP_BYTES: skip operand of tile t in buffer t&1, so that
-                                                                   // the next tile's feature gather can be staged while this tile computes
-  TcShared& S = *reinterpret_cast<TcShared*>(skip0 + 2 * SKIP_BYTES);
+  unsigned char* skip = dsm + N_STAGES * STAGE_BYTES;              // SKIP_BYTES
+  float* s_sb = reinterpret_cast<float*>(skip + SKIP_BYTES);       // {scale,bias} pairs of every layer
+  TcShared& S = *reinterpret_cast<TcShared*>(reinterpret_cast<unsigned char*>(s_sb) + SB_FLOATS_MAX * sizeof(float));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool texture = (a.out_rgb != nullptr);
@@ -368,6 +368,17 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
   const int n_ops = a.n_ops;
+  {  // stage {scale,bias} interleaved per channel: s_sb[2*c] = scale, s_sb[2*c+1] = bias (tensor-core variants: scale includes 2^-shift)
+    int base = 0;
+    for (int l = 0; l < (int)a.hdr->n_layers; ++l) {
+      const AvcLayerDesc& L = a.hdr->layers[l];
+      for (int c = tid; c < L.np; c += NT) {
+        s_sb[base + 2 * c] = a.f32[L.tc_sb_off + c];
+        s_sb[base + 2 * c + 1] = a.f32[L.tc_sb_off + L.np + c];
+      }
+      base += 2 * L.np;
+    }
+  }
   __syncthreads();
   const int64_t n_tiles = (a.n + TILE - 1) / TILE;
 
@@ -387,9 +398,6 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
               const int ks = seg == 0 ? o.ks_smem : o.ks_tmem;
               for (int j = 0; j < ks; j += STAGE_KSTEPS) {
                 const uint32_t bytes = (uint32_t)min(STAGE_KSTEPS, ks - j) * 2u * part_bytes;
-#ifdef AVC_TC_DEBUG
-                if (a.dbg & 1) continue;
-#endif
                 mbar_wait(&S.empty[stage], phase ^ 1);
                 if (elect_one()) {
                   mbar_expect_tx(&S.full[stage], bytes);
@@ -414,12 +422,11 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       uint32_t ph_a = 0, ph_epi = 0;   // per-barrier phase bits (tracked by both warps, waited on by the stage owner)
       uint32_t g = 0;                  // global stage counter
-      const uint32_t skip_base = smem_u32(skip0), ring_addr = smem_u32(ring);
+      const uint32_t skip_addr = smem_u32(skip), ring_addr = smem_u32(ring);
       const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);   // LBO, SBO, version
       int tl = 0;
       if (me == 1) asm volatile("bar.arrive 1, 64;" ::: "memory");      // warp 8 owns stage 0
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t skip_addr = skip_base + (uint32_t)(tl & 1) * SKIP_BYTES;
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = a.ops[oi];
           // A 256-wide layer is issued as two N=128 halves, each over the full K. The epilogue of half 0 (accumulator columns
@@ -474,9 +481,6 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
                 }
                 if (need_epi) { mbar_wait(&S.epi_done, ph_epi); }
                 if (wa) { mbar_wait(&S.a_ready[2 * c2], (ph_a >> (2 * c2)) & 1u); mbar_wait(&S.a_ready[2 * c2 + 1], (ph_a >> (2 * c2 + 1)) & 1u); }
-#ifdef AVC_TC_DEBUG
-                if (!(a.dbg & 1))
-#endif
                 mbar_wait(&S.full[stage], phase);
                 tc_fence_after();
                 if (me == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
@@ -489,9 +493,6 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
                     mma_ts_c(d_addr, a_hi, bl[u], idesc, 1u, 2);
                     mma_ts(d_addr, a_lo, bh[u], idesc, 1u);
                   }
-#ifdef AVC_TC_DEBUG
-                  if (!(a.dbg & 1))
-#endif
                   tc_commit(&S.empty[stage]);
                 }
                 __syncwarp();
@@ -520,50 +521,41 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t ph_d0 = 0, ph_d1 = 0;
     int tl = 0;
-    const bool has_h0 = (a.kind == AVC_KIND_RECON) || (a.mode != AVC_MODE_TEMPLATE_ONLY);   // first layer fed by a feature gather
-    // stage piece `piece` (0 or 1) of the first-layer skip operand of the tile whose point is (x,y,z) into buffer `dst`:
-    //   avatar: h0 in tensor-core order [f0..f63, x, y, z, 0...] (packer permutes the 67 columns)   arch_avatar.py:121-136
-    //   recon : h0 = [f0..f31, z - cz, 0...]                                                          arch_recon.py:62-70
-    auto stage_h0 = [&](unsigned char* dst, float x, float y, float z, int piece) {
-      const Taps t = make_taps(x - a.cx, -(y - a.cy), a.mH, a.mW);
-      float v[8];
-      if (a.kind == AVC_KIND_AVATAR) {
-#pragma unroll
-        for (int q = 2 * piece; q < 2 * piece + 2; ++q) { gather8(a.map, a.mC, t, grp * 32 + q * 8, v); skip_store8(dst, row, grp * 4 + q, v); }
-        if (grp == 1 && piece == 1) {
-          v[0] = x; v[1] = y; v[2] = z; v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
-          skip_store8(dst, row, 8, v);
-          v[0] = v[1] = v[2] = 0.f;
-          skip_store8(dst, row, 9, v);
-        }
-      } else {
-        gather8(a.map, a.mC, t, grp * 16 + piece * 8, v); skip_store8(dst, row, grp * 2 + piece, v);
-        if (grp == 1 && piece == 1) {
-          v[0] = z - a.cz; v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
-          skip_store8(dst, row, 4, v);
-          v[0] = 0.f;
-          skip_store8(dst, row, 5, v);
-        }
-      }
-    };
-    float nx = 0.f, ny = 0.f, nz = 0.f;            // point of the NEXT tile (prefetched)
-    {
-      const int64_t g0 = (int64_t)blockIdx.x * TILE + row;
-      if (g0 < a.n) { nx = a.pts[g0 * 3]; ny = a.pts[g0 * 3 + 1]; nz = a.pts[g0 * 3 + 2]; }
-      if (has_h0 && (int64_t)blockIdx.x < n_tiles) { stage_h0(skip0, nx, ny, nz, 0); stage_h0(skip0, nx, ny, nz, 1); }
-    }
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t g = tile * TILE + row;
       const bool valid = g < a.n;
-      if (!has_h0 && tl > 0) { nx = ny = nz = 0.f; if (valid) { nx = a.pts[g * 3]; ny = a.pts[g * 3 + 1]; nz = a.pts[g * 3 + 2]; } }
-      const float px = nx, py = ny, pz = nz;
-      int n_hid = 0;                                                // hidden-layer epilogues finished in this tile
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (valid) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; }
       float qx = px, qy = py, qz = pz;
-      unsigned char* skip = skip0 + (tl & 1) * SKIP_BYTES;          // this tile's skip operand (h0, later the PE)
-      unsigned char* skip_next = skip0 + ((tl + 1) & 1) * SKIP_BYTES;
-      const int64_t gn = (tile + gridDim.x) * TILE + row;           // same lane of this CTA's next tile
-      const bool have_next = tile + gridDim.x < n_tiles;
-      bool need_pe = !has_h0;                                       // template only: PE of the input points
+      // ---------------- input stage: skip operand of the first layer ------------------------------------------------
+      bool need_pe = false;
+      if (a.kind == AVC_KIND_AVATAR && a.mode != AVC_MODE_TEMPLATE_ONLY) {
+        // h0 in tensor-core order [f0..f63, x, y, z, 0...] (packer permutes the 67 columns accordingly)   arch_avatar.py:121-136
+        const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { gather8(a.map, a.mC, t, grp * 32 + q * 8, v); skip_store8(skip, row, grp * 4 + q, v); }
+        if (grp == 1) {
+          v[0] = px; v[1] = py; v[2] = pz; v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
+          skip_store8(skip, row, 8, v);
+          v[0] = v[1] = v[2] = 0.f;
+          skip_store8(skip, row, 9, v);
+        }
+      } else if (a.kind == AVC_KIND_RECON) {
+        // h0 = [f0..f31, z - cz, 0...]   arch_recon.py:62-70
+        const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { gather8(a.map, a.mC, t, grp * 16 + q * 8, v); skip_store8(skip, row, grp * 2 + q, v); }
+        if (grp == 1) {
+          v[0] = pz - a.cz; v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
+          skip_store8(skip, row, 4, v);
+          v[0] = 0.f;
+          skip_store8(skip, row, 5, v);
+        }
+      } else {
+        need_pe = true;   // template only: PE of the input points
+      }
       for (int oi = 0; oi <= n_ops; ++oi) {
         if (need_pe) {
           // positional encoding of q into the skip buffer: k = [q(3), {sin(2^f q)(3), cos(2^f q)(3)}_f=0..9, 0]   net_util.py:28-37
@@ -598,7 +590,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
         mbar_wait(&S.d_ready[0], ph_d0); ph_d0 ^= 1; tc_fence_after();
         if (tid == 0) trace_ev(a.trace, tl, oi, 3);
         if (o.epi == EPI_HIDDEN) {
-          const float* sb = a.f32 + o.sb_off;
+          const float* sb = s_sb + o.sb_off;
           const int n_chunks = o.n >> 5;
           for (int c = grp; c < n_chunks; c += 2) {
             if (c == 4 + grp) {                                                                   // second N-half (only 256-wide ops get here)
@@ -618,20 +610,13 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
             if (lane == 0) mbar_arrive(&S.a_ready[c]);
           }
           if (tid == 0) trace_ev(a.trace, tl, oi, 6);
-          // the compute warps now idle until the next accumulator half is ready: use the gap to stage the NEXT tile's first-layer
-          // operand (feature gather) into the other skip buffer -- every MMA that read that buffer (previous tile) has completed
-          if (has_h0 && have_next && n_hid < 2) {
-            if (n_hid == 0) { nx = ny = nz = 0.f; if (gn < a.n) { nx = a.pts[gn * 3]; ny = a.pts[gn * 3 + 1]; nz = a.pts[gn * 3 + 2]; } }
-            stage_h0(skip_next, nx, ny, nz, n_hid);
-          }
-          ++n_hid;
         } else {
           float v[4];
           tmem_ld4(t_lane + (uint32_t)o.d_col, v);
-          const float* sb = a.f32 + o.sb_off;
+          const float* sb = s_sb + o.sb_off;
           float r[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) r[i] = fmaf(v[i], __ldg(sb + 2 * i), __ldg(sb + 2 * i + 1));
+          for (int i = 0; i < 4; ++i) r[i] = fmaf(v[i], sb[2 * i], sb[2 * i + 1]);
           if (o.epi == EPI_WARP_OUT) {
             qx = px + r[0]; qy = py + r[1]; qz = pz + r[2];                       // cano_pts_chunk + offset_chunk  arch_avatar.py:372
             if (grp == 0 && valid && a.out_off) { a.out_off[g * 3] = r[0]; a.out_off[g * 3 + 1] = r[1]; a.out_off[g * 3 + 2] = r[2]; }
@@ -666,14 +651,14 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const __grid_constant__
   }
 }
 
-constexpr size_t TC_SMEM = (size_t)N_STAGES * STAGE_BYTES + 2 * SKIP_BYTES + sizeof(TcShared) + 64;
+constexpr size_t TC_SMEM = (size_t)N_STAGES * STAGE_BYTES + SKIP_BYTES + SB_FLOATS_MAX * sizeof(float) + sizeof(TcShared) + 64;
 
 int launch_tc(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, const float* pts, int64_t n, const float center[3], float* out0,
               float* out_off, float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st) {
   if (n == 0) return AVC_OK;
   int sb = 0;
   for (uint32_t l = 0; l < w.hdr.n_layers; ++l) sb += 2 * w.hdr.layers[l].np;
-  (void)sb;
+  if (sb > SB_FLOATS_MAX) return avc_fail(ctx, AVC_EFORMAT, "tensor-core path: scale/bias table too large (%d floats)", sb);
   TcArgs a;
   a.pts = pts; a.n = n; a.cx = center[0]; a.cy = center[1]; a.cz = center[2];
   a.map = map ? map->d_hwc : nullptr; a.mC = map ? map->C : 0; a.mH = map ? map->H : 1; a.mW = map ? map->W : 1;

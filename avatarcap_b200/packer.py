@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 MAGIC = 0x57435641
-VERSION = 4
+VERSION = 3
 MAX_LAYERS = 24
 KIND_AVATAR, KIND_RECON = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SOFTPLUS, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -192,7 +192,7 @@ def pack(layers: List[_Layer], kind: int) -> bytes:
                                 f16.append(sl); f16_bytes += sl.size * 2
         tsc = np.zeros(npad, np.float32); tbi = np.zeros(npad, np.float32)
         tsc[:n] = L.scale * np.float32(2.0 ** -shift); tbi[:n] = L.bias
-        tc_sb_off = add_f32(np.stack([tsc, tbi], 1).reshape(-1))     # interleaved {scale, bias} pairs (float4 = two channels)
+        tc_sb_off = add_f32(np.concatenate([tsc, tbi]))
         descs.append((L.k0, L.k1, k0p, k1p, n, npad, L.act, wt_off, sb_off, tc_w_off, tc_sb_off, shift))
     f32_blob = np.concatenate(f32).astype(np.float32).tobytes() if f32 else b''
     f16_blob = np.concatenate(f16).astype(np.float16).tobytes() if f16 else b''

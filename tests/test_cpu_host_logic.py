@@ -54,7 +54,7 @@ def test_packer_layout_and_folding():
         assert Ld['tc_w_off'] == pos
         pos += Ld['np'] * (Ld['k0p'] + Ld['k1p']) * 4
     assert pos == packer.parse_header(blob)['f16_bytes']
-    tsc = f32[L['tc_sb_off']:L['tc_sb_off'] + 512:2]              # interleaved {scale, bias} pairs
+    tsc = f32[L['tc_sb_off']:L['tc_sb_off'] + 256]
     assert np.allclose(tsc * 2.0 ** L['shift'], f32[L['sb_off']:L['sb_off'] + 256], rtol=1e-7)
 
 
