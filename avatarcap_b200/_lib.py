@@ -46,6 +46,9 @@ SIGNATURES = {
     'avc_skin_points': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'avc_skin_normals': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'avc_skin_mesh': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    'avc_ray_samples': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    'avc_nerf_raw': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_f), _i64, _vp, _vp]),
+    'avc_composite': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     'avc_posed_to_cano': (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, C.POINTER(_f), _vp, C.POINTER(_i), _vp, _vp, _vp]),
 }
 

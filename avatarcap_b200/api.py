@@ -162,9 +162,63 @@ def geotex_forward(engine: Engine, wpts: torch.Tensor, dists: torch.Tensor, batc
         else:
             off = torch.zeros_like(cano)
             rgb, alpha, occ = engine.eval_template(cano, _if_type(if_type), impl=impl)
-        bb = bounds.to(engine.device, torch.float32)
-        inside = ((cano > bb[0][None]) & (cano < bb[1][None])).sum(1) == 3                                     # :221-223
-        alpha = torch.where(inside & near, alpha, torch.zeros_like(alpha))                                    # :224-225
-        alpha = 1.0 - torch.exp(-alpha[:, None] * engine._f32(dists[b]).reshape(-1, 1))                       # :227-229
-        raws.append(torch.cat([rgb, alpha], -1)[None]); occs.append(occ[None, :, None]); offs.append(off[None])
+        raw = engine.nerf_raw(cano, near, rgb, alpha, dists[b], bounds)                                       # :220-231
+        raws.append(raw[None]); occs.append(occ[None, :, None]); offs.append(off[None])
     return {'raw': torch.cat(raws, 0), 'occ': torch.cat(occs, 0), 'nonrigid_offset': torch.cat(offs, 0)}
+
+
+class NerfRenderer:
+    """Mirror of network.arch_avatar.NerfRenderer (arch_avatar.py:240-349) for inference: ray sampling, the per-sample field
+    (geotex_forward) and front-to-back compositing (utils/nerf_util.raw2outputs) all run in the CUDA library.
+    `forward(wpts, dists, batch, pts_space)` is any callable with geotex_forward's result dict (see `for_engine`)."""
+
+    def __init__(self, forward, engine: Optional[Engine] = None, n_samples: int = 64):
+        self.forward = forward
+        self.engine = engine or default_engine()
+        self.n_samples = n_samples                     # config.N_samples (config.py:9)
+
+    @classmethod
+    def for_engine(cls, engine: Engine, pose_feat_map, smpl_skinning_weights, cano_smpl_vertices, weight_volume, n_samples: int = 64):
+        def fwd(wpts, dists, batch, pts_space):
+            return geotex_forward(engine, wpts, dists, batch, pose_feat_map, smpl_skinning_weights, cano_smpl_vertices, weight_volume, pts_space)
+        return cls(fwd, engine, n_samples)
+
+    def render(self, batch: Dict, pts_space: str = 'posed', near_dist: float = 0.05, far_dist: float = 0.05) -> Dict[str, torch.Tensor]:
+        """render (arch_avatar.py:320-349) with B == 1 (as main.py:476 calls it). Like the reference, near/far of rays with a valid
+        depth are overwritten IN PLACE in the caller's batch (get_pixel_value :285-287). Keys: rgb_map, acc_map, depth_map, raw, occ,
+        nonrigid_offset."""
+        e = self.engine
+        ray_o, ray_d, near, far, depth = batch['ray_o'], batch['ray_d'], batch['near'], batch['far'], batch['depth']
+        assert ray_o.shape[0] == 1, 'batch size 1'
+        valid = depth > 1e-6
+        near[valid] = depth[valid] - near_dist; far[valid] = depth[valid] + far_dist
+        n_pixel = ray_o.shape[1]; S = self.n_samples
+        outs = {k: [] for k in ('raw', 'occ', 'nonrigid_offset', 'rgb_map', 'acc_map', 'depth_map')}
+        chunk = 1 << 15                                   # rays per call (the reference uses 2048, :330; chunking does not change results)
+        for i in range(0, n_pixel, chunk):
+            sl = slice(i, i + chunk)
+            pts, z, dists = e.ray_samples(ray_o[0, sl], ray_d[0, sl], near[0, sl], far[0, sl], S)
+            ret = self.forward(pts[None], dists[None, :, None], batch, pts_space)
+            raw = ret['raw'][0]
+            rgb, acc, dep = e.composite(raw, z)
+            outs['raw'].append(raw); outs['occ'].append(ret['occ'][0]); outs['nonrigid_offset'].append(ret['nonrigid_offset'][0])
+            outs['rgb_map'].append(rgb); outs['acc_map'].append(acc); outs['depth_map'].append(dep)
+        return {k: torch.cat(v, 0)[None] for k, v in outs.items()}
+
+
+def vertex_colors(renderer: NerfRenderer, batch: Dict, vertices: torch.Tensor, normals: torch.Tensor) -> torch.Tensor:
+    """main.py:464-478: integrate the texture template along -normal through each avatar vertex; returns (V,3) colours in the
+    reference's channel order ([:, [2,1,0]])."""
+    items = dict(batch)
+    items['ray_o'] = (vertices + normals)[None]; items['ray_d'] = -normals[None]
+    items['depth'] = torch.ones((1, vertices.shape[0]), device=vertices.device, dtype=torch.float32)
+    items['near'] = items['depth'] - 0.05; items['far'] = items['depth'] + 0.05
+    out = renderer.render(items, pts_space='cano', near_dist=0.02, far_dist=0.05)
+    return out['rgb_map'][0][:, [2, 1, 0]]
+
+
+def transfer_colors(engine: Engine, vertices: torch.Tensor, src_vertices: torch.Tensor, src_colors: torch.Tensor) -> torch.Tensor:
+    """main.py:480-484: nearest avatar vertex's colour for every reconstructed vertex (knn_points K=1 + knn_gather).
+    The source set can be large (a mesh), so it is processed in tiles of the KNN kernel's reference capacity."""
+    _, idx = engine.knn(vertices, src_vertices, 1)
+    return src_colors[idx[:, 0]]

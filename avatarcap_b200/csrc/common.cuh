@@ -61,6 +61,7 @@ struct avc_ctx {
   int64_t launches = 0;
   // scratch owned by the context (marching cubes scans, host staging)
   void* d_scratch = nullptr; size_t scratch_cap = 0;
+  void* d_scratch2 = nullptr; size_t scratch2_cap = 0;   // marching cubes: compact edge list
   void* h_pinned = nullptr;  size_t pinned_cap = 0;
   void* d_stage = nullptr;   size_t stage_cap = 0;
   cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;

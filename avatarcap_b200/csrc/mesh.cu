@@ -120,15 +120,22 @@ __global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(int* __restrict__ 
 }
 
 // pass C: vbase[v] = exclusive vertex prefix of voxel v (canonical order: voxel linear index, then axis)
+// Also compacts the sign-changing edges: edges[vid] = voxel*4 + axis, so that the vertex kernel runs one thread per vertex.
 __global__ void __launch_bounds__(MC_NT) mc_vbase_kernel(const float* __restrict__ vol, McDims d, const int* __restrict__ blk,
-                                                         int* __restrict__ vbase) {
+                                                         int* __restrict__ vbase, long long* __restrict__ edges) {
   const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  int c[MC_VPT]; int nv = 0;
+  int c[MC_VPT], cut[MC_VPT]; int nv = 0;
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) { const VoxInfo r = classify(vol, d, v0 + q); c[q] = r.in_scan ? __popc(r.cut) : 0; nv += c[q]; }
+  for (int q = 0; q < MC_VPT; ++q) { const VoxInfo r = classify(vol, d, v0 + q); cut[q] = r.in_scan ? r.cut : 0; c[q] = __popc(cut[q]); nv += c[q]; }
   int tot; int p = blk[3 * blockIdx.x] + block_excl_scan(nv, &tot);
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = p; p += c[q]; }
+  for (int q = 0; q < MC_VPT; ++q) {
+    if (v0 + q < d.nvox) vbase[v0 + q] = p;
+    int e = p;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) if ((cut[q] >> ax) & 1) edges[e++] = (long long)(v0 + q) * 4 + ax;
+    p += c[q];
+  }
 }
 
 struct McEmit {
@@ -147,110 +154,107 @@ __device__ __forceinline__ float vol_at(const float* __restrict__ vol, const McD
   return ldv(vol, ((int64_t)i * d.ry + j) * d.rz + k);
 }
 
-// pass D: emit vertices (+normals) and faces
-__global__ void __launch_bounds__(MC_NT) mc_emit_kernel(const float* __restrict__ vol, McDims d, McEmit e, const int* __restrict__ blk,
-                                                        const int* __restrict__ vbase) {
-  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  VoxInfo info[MC_VPT]; int nt = 0;
+// pass D1: one thread per owned vertex (dense warps): position by linear interpolation + Sobel/trilinear normal
+__global__ void __launch_bounds__(128) mc_verts_kernel(const float* __restrict__ vol, McDims d, McEmit e, const long long* __restrict__ edges,
+                                                       int64_t n_owned) {
+  const int64_t vid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vid >= n_owned) return;
+  const long long key = edges[vid];
+  const int64_t v = key >> 2; const int ax = (int)(key & 3);
+  const int k = (int)(v % d.rz); const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
+  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
+  const float va = ldv(vol, v);
+  const float vb = ldv(vol, v + (ax == 0 ? sx : (ax == 1 ? sy : 1)));
+  const float tt = __fdiv_rn(__fsub_rn(d.iso, va), __fsub_rn(vb, va));      // linear interpolation (skimage: edge-weighted)
+  float idx[3] = {(float)(i + e.x_origin), (float)j, (float)k};
+  idx[ax] = __fadd_rn(idx[ax], tt);
+  float p[3], g[3];
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) { info[q] = classify(vol, d, v0 + q); if (info[q].owned && info[q].ccase >= 0) nt += c_mc_ntri[info[q].ccase]; }
+  for (int c = 0; c < 3; ++c) {
+    // vertices = mc*voxel (spacing) ; + bounds[0] + 0.5*voxel   recon_util.py:64-65
+    p[c] = __fadd_rn(__fadd_rn(__fmul_rn(idx[c], e.vox[c]), e.bmin[c]), __fmul_rn(0.5f, e.vox[c]));
+    // vertices_grid = 2*(v - bmin)/len - 1   :66 ; grid_sample unnormalise ((g+1)/2)*(R-1), border clip
+    const float gg = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(p[c], e.bmin[c])), e.len[c]), 1.f);
+    float s = __fmul_rn(__fdiv_rn(__fadd_rn(gg, 1.f), 2.f), (float)(e.gres[c] - 1));
+    g[c] = fminf((float)(e.gres[c] - 1), fmaxf(s, 0.f));
+  }
+  e.verts[vid * 3 + 0] = p[0]; e.verts[vid * 3 + 1] = p[1]; e.verts[vid * 3 + 2] = p[2];
+  if (!e.normals) return;
+  // trilinear sample of the Sobel gradient volume: 8 corners, each a 3x3x3 stencil -> a 4x4x4 block of voxels
+  const int x0 = (int)floorf(g[0]), y0 = (int)floorf(g[1]), z0 = (int)floorf(g[2]);
+  const float fx = g[0] - (float)x0, fy = g[1] - (float)y0, fz = g[2] - (float)z0;
+  float blk4[4][4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) blk4[a][b][c] = vol_at(vol, d, e, x0 - 1 + a - e.x_origin, y0 - 1 + b, z0 - 1 + c);
+  float n[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz) {
+        // corner (x0+dx, y0+dy, z0+dz); taps beyond the last plane have weight 0 (border clip)
+        const bool ok = (x0 + dx <= e.gres[0] - 1) && (y0 + dy <= e.gres[1] - 1) && (z0 + dz <= e.gres[2] - 1);
+        const float w = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * (dz ? fz : 1.f - fz);
+        if (!ok) continue;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            const float sw = (float)((a == 1 ? 2 : 1) * (b == 1 ? 2 : 1));
+            gx += sw * (blk4[dx + 2][dy + a][dz + b] - blk4[dx][dy + a][dz + b]);
+            gy += sw * (blk4[dx + a][dy + 2][dz + b] - blk4[dx + a][dy][dz + b]);
+            gz += sw * (blk4[dx + a][dy + b][dz + 2] - blk4[dx + a][dy + b][dz]);
+          }
+        n[0] += w * (gx / (32.f * e.vox[0])); n[1] += w * (gy / (32.f * e.vox[1])); n[2] += w * (gz / (32.f * e.vox[2]));
+      }
+  const float nn = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);   // no epsilon (recon_util.py:46-47)
+  e.normals[vid * 3 + 0] = -(n[0] / nn);                              // negated (:68)
+  e.normals[vid * 3 + 1] = -(n[1] / nn);
+  e.normals[vid * 3 + 2] = -(n[2] / nn);
+}
+
+// pass D2: faces of the cell whose lowest corner is each owned voxel
+__global__ void __launch_bounds__(MC_NT) mc_faces_kernel(const float* __restrict__ vol, McDims d, McEmit e, const int* __restrict__ blk,
+                                                         const int* __restrict__ vbase) {
+  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  int ccase[MC_VPT]; int nt = 0;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) { const VoxInfo r = classify(vol, d, v0 + q); ccase[q] = (r.owned ? r.ccase : -1); if (ccase[q] >= 0) nt += c_mc_ntri[ccase[q]]; }
   int tot; int tbase = blk[3 * blockIdx.x + 2] + block_excl_scan(nt, &tot);
   const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
+    if (ccase[q] < 0) continue;
     const int64_t v = v0 + q;
-    const VoxInfo r = info[q];
-    if (!r.owned) continue;
-    const int k = (int)(v % d.rz); const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
-    // ---- vertices owned by this voxel -------------------------------------------------------------------------
-    if (r.cut) {
-      int vid = vbase[v];
-      const float va = ldv(vol, v);
+    const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
+    const int ntri = c_mc_ntri[ccase[q]];
+    for (int tix = 0; tix < ntri; ++tix) {
+      int ids[3];
 #pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        if (!((r.cut >> ax) & 1)) continue;
-        const float vb = ldv(vol, v + (ax == 0 ? sx : (ax == 1 ? sy : 1)));
-        const float tt = __fdiv_rn(__fsub_rn(d.iso, va), __fsub_rn(vb, va));      // linear interpolation (skimage: edge-weighted)
-        float idx[3] = {(float)(i + e.x_origin), (float)j, (float)k};
-        idx[ax] = __fadd_rn(idx[ax], tt);
-        float p[3], g[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          // vertices = mc*voxel (spacing) ; + bounds[0] + 0.5*voxel   recon_util.py:64-65
-          p[c] = __fadd_rn(__fadd_rn(__fmul_rn(idx[c], e.vox[c]), e.bmin[c]), __fmul_rn(0.5f, e.vox[c]));
-          // vertices_grid = 2*(v - bmin)/len - 1   :66 ; grid_sample unnormalise ((g+1)/2)*(R-1), border clip
-          const float gg = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, __fsub_rn(p[c], e.bmin[c])), e.len[c]), 1.f);
-          float s = __fmul_rn(__fdiv_rn(__fadd_rn(gg, 1.f), 2.f), (float)(e.gres[c] - 1));
-          g[c] = fminf((float)(e.gres[c] - 1), fmaxf(s, 0.f));
+      for (int c = 0; c < 3; ++c) {
+        const int ed = c_mc_tri[ccase[q]][3 * tix + c];
+        const int corner = c_mc_edge_corner[ed], ax = c_mc_edge_axis[ed];
+        const int64_t ov = v + (corner & 1) * sx + ((corner >> 1) & 1) * sy + ((corner >> 2) & 1);
+        // rank of `ax` among the owner's cut edges: recompute the owner's lower-axis cut flags
+        int rank = 0;
+        if (ax > 0) {
+          const bool o0 = ldv(vol, ov) > d.iso;
+          const int oi = i + (corner & 1), oj = j + ((corner >> 1) & 1);
+          if (oi + 1 < d.rx && ((ldv(vol, ov + sx) > d.iso) != o0)) ++rank;
+          if (ax > 1 && oj + 1 < d.ry && ((ldv(vol, ov + sy) > d.iso) != o0)) ++rank;
         }
-        e.verts[(int64_t)vid * 3 + 0] = p[0]; e.verts[(int64_t)vid * 3 + 1] = p[1]; e.verts[(int64_t)vid * 3 + 2] = p[2];
-        if (e.normals) {
-          // trilinear sample of the Sobel gradient volume: 8 corners, each a 3x3x3 stencil -> a 4x4x4 block of voxels
-          const int x0 = (int)floorf(g[0]), y0 = (int)floorf(g[1]), z0 = (int)floorf(g[2]);
-          const float fx = g[0] - (float)x0, fy = g[1] - (float)y0, fz = g[2] - (float)z0;
-          float blk4[4][4][4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) blk4[a][b][c] = vol_at(vol, d, e, x0 - 1 + a - e.x_origin, y0 - 1 + b, z0 - 1 + c);
-          float n[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-          for (int dx = 0; dx < 2; ++dx)
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-              for (int dz = 0; dz < 2; ++dz) {
-                // corner (x0+dx, y0+dy, z0+dz); taps beyond the last plane have weight 0 (border clip)
-                const bool ok = (x0 + dx <= e.gres[0] - 1) && (y0 + dy <= e.gres[1] - 1) && (z0 + dz <= e.gres[2] - 1);
-                const float w = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * (dz ? fz : 1.f - fz);
-                if (!ok) continue;
-                float gx = 0.f, gy = 0.f, gz = 0.f;
-#pragma unroll
-                for (int a = 0; a < 3; ++a)
-#pragma unroll
-                  for (int b = 0; b < 3; ++b) {
-                    const float sw = (float)((a == 1 ? 2 : 1) * (b == 1 ? 2 : 1));
-                    gx += sw * (blk4[dx + 2][dy + a][dz + b] - blk4[dx][dy + a][dz + b]);
-                    gy += sw * (blk4[dx + a][dy + 2][dz + b] - blk4[dx + a][dy][dz + b]);
-                    gz += sw * (blk4[dx + a][dy + b][dz + 2] - blk4[dx + a][dy + b][dz]);
-                  }
-                n[0] += w * (gx / (32.f * e.vox[0])); n[1] += w * (gy / (32.f * e.vox[1])); n[2] += w * (gz / (32.f * e.vox[2]));
-              }
-          const float nn = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);   // no epsilon (recon_util.py:46-47)
-          e.normals[(int64_t)vid * 3 + 0] = -(n[0] / nn);                      // negated (:68)
-          e.normals[(int64_t)vid * 3 + 1] = -(n[1] / nn);
-          e.normals[(int64_t)vid * 3 + 2] = -(n[2] / nn);
-        }
-        ++vid;
+        ids[c] = vbase[ov] + rank;
       }
+      const int64_t f = (int64_t)tbase + tix;
+      e.faces[f * 3 + 0] = ids[2]; e.faces[f * 3 + 1] = ids[1]; e.faces[f * 3 + 2] = ids[0];   // faces[:, [2,1,0]]  :69
     }
-    // ---- faces of the cell whose lowest corner is this voxel -------------------------------------------------
-    if (r.ccase >= 0) {
-      const int ntri = c_mc_ntri[r.ccase];
-      for (int tix = 0; tix < ntri; ++tix) {
-        int ids[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int ed = c_mc_tri[r.ccase][3 * tix + c];
-          const int corner = c_mc_edge_corner[ed], ax = c_mc_edge_axis[ed];
-          const int64_t ov = v + (corner & 1) * sx + ((corner >> 1) & 1) * sy + ((corner >> 2) & 1);
-          // rank of `ax` among the owner's cut edges: recompute the owner's lower-axis cut flags
-          int rank = 0;
-          if (ax > 0) {
-            const bool o0 = ldv(vol, ov) > d.iso;
-            const int oi = i + (corner & 1), oj = j + ((corner >> 1) & 1);
-            if (oi + 1 < d.rx && ((ldv(vol, ov + sx) > d.iso) != o0)) ++rank;
-            if (ax > 1 && oj + 1 < d.ry && ((ldv(vol, ov + sy) > d.iso) != o0)) ++rank;
-          }
-          ids[c] = vbase[ov] + rank;
-        }
-        const int64_t f = (int64_t)tbase + tix;
-        e.faces[f * 3 + 0] = ids[2]; e.faces[f * 3 + 1] = ids[1]; e.faces[f * 3 + 2] = ids[0];   // faces[:, [2,1,0]]  :69
-      }
-      tbase += ntri;
-    }
+    tbase += ntri;
   }
 }
 
@@ -388,7 +392,16 @@ extern "C" int avc_mc_emit(avc_ctx* ctx, const float* vol, const int res[3], con
                     (long long)cap_v, (long long)cap_f);
   if (ctx->h_counts[0] > 0x7fffffffLL || nf > 0x7fffffffLL) return avc_fail(ctx, AVC_EINVAL, "mesh too large for int32 indices");
   if (nv == 0 && nf == 0) return AVC_OK;
-  mc_vbase_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk, d_vbase);
+  // compact edge list (8 B per vertex in the scan range), separate buffer so the scan scratch above stays valid
+  const size_t need_edges = (size_t)(ctx->h_counts[0] + 1) * sizeof(long long);
+  if (need_edges > ctx->scratch2_cap) {
+    if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
+    ctx->d_scratch2 = nullptr; ctx->scratch2_cap = 0;
+    AVC_CUDA(ctx, cudaMalloc(&ctx->d_scratch2, need_edges + (need_edges >> 3)));
+    ctx->scratch2_cap = need_edges + (need_edges >> 3);
+  }
+  long long* d_edges = reinterpret_cast<long long*>(ctx->d_scratch2);
+  mc_vbase_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk, d_vbase, d_edges);
   AVC_LAUNCH_CHECK(ctx, "mc_vbase_kernel");
   McEmit e;
   const int gres[3] = {gres_x, res[1], res[2]};
@@ -397,7 +410,11 @@ extern "C" int avc_mc_emit(avc_ctx* ctx, const float* vol, const int res[3], con
     e.vox[c] = e.len[c] / (float)gres[c];                                   // recon_util.py:60-61
   }
   e.x_origin = x_origin; e.verts = verts; e.normals = normals; e.faces = faces;
-  mc_emit_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, e, d_blk, d_vbase);
-  AVC_LAUNCH_CHECK(ctx, "mc_emit_kernel");
+  if (nv > 0) {
+    mc_verts_kernel<<<(unsigned)((nv + 127) / 128), 128, 0, st>>>(vol, d, e, d_edges, nv);
+    AVC_LAUNCH_CHECK(ctx, "mc_verts_kernel");
+  }
+  mc_faces_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, e, d_blk, d_vbase);
+  AVC_LAUNCH_CHECK(ctx, "mc_faces_kernel");
   return AVC_OK;
 }

@@ -263,6 +263,34 @@ class Engine:
         return cano, near.bool()
 
 
+    # ------------------------------------------------------------------ vertex-colour driver (NerfRenderer / raw2outputs)
+    def ray_samples(self, ray_o, ray_d, near, far, n_samples: int):
+        o = self._f32(ray_o, 3); d = self._f32(ray_d, 3); nr = self._f32(near).reshape(-1); fr = self._f32(far).reshape(-1)
+        n = o.shape[0]
+        pts = torch.empty((n * n_samples, 3), device=self.device, dtype=torch.float32)
+        z = torch.empty((n, n_samples), device=self.device, dtype=torch.float32)
+        dists = torch.empty((n * n_samples,), device=self.device, dtype=torch.float32)
+        self._check(self.lib.avc_ray_samples(self._h, _ptr(o), _ptr(d), _ptr(nr), _ptr(fr), n, n_samples, _ptr(pts), _ptr(z), _ptr(dists), self._stream()))
+        return pts, z, dists
+
+    def nerf_raw(self, cano_q, near_flag, rgb, alpha_raw, dists, bounds) -> torch.Tensor:
+        q = self._f32(cano_q, 3); nf = near_flag.to(self.device).contiguous()
+        nf8 = nf.view(torch.uint8) if nf.dtype == torch.bool else nf.to(torch.uint8)
+        c = self._f32(rgb, 3); al = self._f32(alpha_raw).reshape(-1); dd = self._f32(dists).reshape(-1)
+        raw = torch.empty((q.shape[0], 4), device=self.device, dtype=torch.float32)
+        b = np.asarray(bounds.detach().cpu().numpy() if isinstance(bounds, torch.Tensor) else bounds, dtype=np.float32).reshape(6)
+        self._check(self.lib.avc_nerf_raw(self._h, _ptr(q), _ptr(nf8), _ptr(c), _ptr(al), _ptr(dd), _lib.f6(b), q.shape[0], _ptr(raw), self._stream()))
+        return raw
+
+    def composite(self, raw, z_vals, white_bkgd: bool = False):
+        r = self._f32(raw, 4); z = self._f32(z_vals)
+        n, S = z.shape
+        rgb = torch.empty((n, 3), device=self.device, dtype=torch.float32)
+        acc = torch.empty(n, device=self.device, dtype=torch.float32); dep = torch.empty(n, device=self.device, dtype=torch.float32)
+        self._check(self.lib.avc_composite(self._h, _ptr(r), _ptr(z), n, S, int(white_bkgd), _ptr(rgb), _ptr(acc), _ptr(dep), self._stream()))
+        return rgb, acc, dep
+
+
 _default: Dict[int, Engine] = {}
 
 

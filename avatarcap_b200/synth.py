@@ -219,7 +219,7 @@ def _conv(rs: np.random.RandomState, cout: int, cin: int, sd: Dict[str, np.ndarr
     sd[prefix + '.bias'] = rs.uniform(-bound, bound, (cout,)).astype(np.float32)
 
 
-def avatar_state_dict(seed: int = SEED, occ_scale: float = 1.0, off_scale: float = 0.02) -> Dict[str, np.ndarray]:
+def avatar_state_dict(seed: int = SEED, occ_scale: float = 1.0, off_scale: float = 0.02, density_scale: float = 300.0) -> Dict[str, np.ndarray]:
     """Per-point keys of GeoTexAvatar.state_dict() (the UNet keys are out of scope and omitted).
 
     occ_scale / off_scale set the magnitude of the two heads the reference initialises to ~0
@@ -256,6 +256,8 @@ def avatar_state_dict(seed: int = SEED, occ_scale: float = 1.0, off_scale: float
     k = 'cano_template.geo_mlp.fc_list.1'
     sd[k + '.weight'] = (rs.uniform(-1, 1, (2, 128, 1)) * occ_scale * 6.0).astype(np.float32)
     sd[k + '.bias'] = (rs.uniform(-0.1, 0.1, 2) * occ_scale).astype(np.float32)
+    # row 1 is the NeRF density: a trained field reaches sigma*delta ~ 1 over a ~1 mm sample spacing (arch_avatar.py:227-229)
+    sd[k + '.weight'][1] *= density_scale; sd[k + '.bias'][1] *= density_scale
     k = 'warping_field.out_layer_coord_affine'
     sd[k + '.weight'] = (rs.uniform(-1, 1, (3, 256, 1)) * off_scale * 0.12).astype(np.float32)
     sd[k + '.bias'] = (rs.uniform(-0.2, 0.2, 3) * off_scale).astype(np.float32)

@@ -177,6 +177,22 @@ int avc_posed_to_cano(avc_ctx* ctx, const float* wpts /*[dev]*/, int64_t n, cons
                       const float bounds[6] /*[host]*/, const float* weight_volume /*[dev] (X,Y,Z,24)*/, const int vdims[3],
                       float* out_cano /*[dev]*/, uint8_t* out_near /*[dev]*/, void* stream);
 
+/* ---------------------------------------------------------------------------------------------- */
+/* vertex-colour evaluation driver ("next" row: NerfRenderer.render + raw2outputs, main.py:464-485) */
+/* ---------------------------------------------------------------------------------------------- */
+/* NerfRenderer.get_wsampling_points / get_density_color (network/arch_avatar.py:244-281), eval mode: out_pts (n_rays*S,3),
+ * out_z (n_rays*S) = near*(1-t)+far*t with t = linspace(0,1,S), out_dists (n_rays*S) = z[i+1]-z[i] (last repeated).       */
+int avc_ray_samples(avc_ctx* ctx, const float* ray_o /*[dev] (n_rays,3)*/, const float* ray_d /*[dev]*/, const float* near /*[dev]*/,
+                    const float* far /*[dev]*/, int64_t n_rays, int n_samples, float* out_pts, float* out_z, float* out_dists, void* stream);
+/* GeoTexAvatar.forward post-processing (arch_avatar.py:220-231): alpha = 0 outside cano_bounds or far from SMPL, then
+ * 1-exp(-alpha*dist); out_raw (n,4) = [rgb, alpha]. cano_q = warped canonical points (p + offset).                       */
+int avc_nerf_raw(avc_ctx* ctx, const float* cano_q /*[dev] (n,3)*/, const uint8_t* near_flag /*[dev] (n)*/, const float* rgb /*[dev] (n,3)*/,
+                 const float* alpha_raw /*[dev] (n)*/, const float* dists /*[dev] (n)*/, const float bounds[6] /*[host]*/, int64_t n,
+                 float* out_raw /*[dev] (n,4)*/, void* stream);
+/* raw2outputs (utils/nerf_util.py:185-212): rgb_map (n_rays,3), acc_map (n_rays), depth_map (n_rays)                     */
+int avc_composite(avc_ctx* ctx, const float* raw /*[dev] (n_rays,S,4)*/, const float* z_vals /*[dev] (n_rays,S)*/, int64_t n_rays, int n_samples,
+                  int white_bkgd, float* out_rgb, float* out_acc, float* out_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -339,3 +339,37 @@ def scatter_fill(flag: np.ndarray, vals: np.ndarray, fill: np.ndarray, res) -> n
     vol[flag] = vals
     vol[~flag] = fill
     return vol.reshape(res)
+
+
+# ------------------------------------------------------------------------------------------------
+# NerfRenderer + raw2outputs (vertex-colour driver, main.py:464-478)
+# ------------------------------------------------------------------------------------------------
+def raw2outputs(raw: Tensor, z_vals: Tensor, white_bkgd: bool = False):
+    """utils/nerf_util.py:185-212 -> rgb_map, acc_map, depth_map."""
+    rgb = raw[..., :-1]; alpha = raw[..., -1]
+    weights = alpha * torch.cumprod(torch.cat([torch.ones((alpha.shape[0], 1), dtype=alpha.dtype), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+    rgb_map = torch.sum(weights[..., None] * rgb, -2)
+    depth_map = torch.sum(weights * z_vals, -1)
+    acc_map = torch.sum(weights, -1)
+    if white_bkgd:
+        rgb_map = rgb_map + (1. - acc_map[..., None])
+    return rgb_map, acc_map, depth_map
+
+
+def nerf_render(sd: SD, ray_o: np.ndarray, ray_d: np.ndarray, near: np.ndarray, far: np.ndarray, depth: np.ndarray,
+                frame: Dict[str, np.ndarray], feat_map: np.ndarray, weight_volume: np.ndarray, pts_space: str = 'cano',
+                near_dist: float = 0.05, far_dist: float = 0.05, n_samples: int = 64, dtype=torch.float32):
+    """NerfRenderer.render / get_pixel_value / get_wsampling_points / get_density_color (arch_avatar.py:244-349), eval mode, B=1."""
+    o = _t(ray_o, dtype); d = _t(ray_d, dtype); nr = _t(near, dtype).clone(); fr = _t(far, dtype).clone(); dp = _t(depth, dtype)
+    valid = dp > 1e-6                                                                   # :285-287
+    nr[valid] = dp[valid] - near_dist; fr[valid] = dp[valid] + far_dist
+    t_vals = torch.linspace(0., 1., steps=n_samples).to(nr)                             # :249
+    z_vals = nr[..., None] * (1. - t_vals) + fr[..., None] * t_vals                     # :250
+    pts = o[:, None] + d[:, None] * z_vals[..., None]                                   # :262
+    dists = z_vals[..., 1:] - z_vals[..., :-1]                                          # :276-277
+    dists = torch.cat([dists, dists[..., -1:]], dim=1)
+    ret = geotex_forward(sd, pts.reshape(-1, 3).numpy(), dists.reshape(-1, 1).numpy(), frame, feat_map, weight_volume, pts_space, dtype)
+    raw = _t(ret['raw'], dtype).reshape(-1, n_samples, 4)
+    rgb_map, acc_map, depth_map = raw2outputs(raw, z_vals)
+    return {'rgb_map': rgb_map.numpy(), 'acc_map': acc_map.numpy(), 'depth_map': depth_map.numpy(), 'raw': raw.reshape(-1, 4).numpy(),
+            'near': nr.numpy(), 'far': fr.numpy()}

@@ -140,6 +140,20 @@ def main() -> None:
         g_avatar['fwd_%s_occ' % space] = o['occ'][0].numpy()
         g_avatar['fwd_%s_off' % space] = o['nonrigid_offset'][0].numpy()
         g_avatar['fwd_%s_wpts_after' % space] = wt[0].numpy()     # 'cano' mutates its input (arch_avatar.py:207,213)
+    # NerfRenderer.render as main.py:464-478 drives it (vertex colours): rays through surface-like points along -normal
+    from network.arch_avatar import NerfRenderer
+    R = 700
+    rv = (frame['cano_smpl_v'][rs.randint(0, synth.N_VERTS, R)] + rs.normal(0, 0.01, (R, 3))).astype(np.float32)
+    rn = rs.normal(0, 1, (R, 3)).astype(np.float32); rn /= np.linalg.norm(rn, axis=1, keepdims=True)
+    items = dict(batch)
+    items['ray_o'] = torch.from_numpy(rv + rn)[None]; items['ray_d'] = torch.from_numpy(-rn)[None]
+    items['depth'] = torch.ones((1, R)); items['near'] = items['depth'] - 0.05; items['far'] = items['depth'] + 0.05
+    items['occupancy'] = items['depth'].clone()
+    with torch.no_grad():
+        no = NerfRenderer(net).render(items, pts_space='cano', near_dist=0.02, far_dist=0.05)
+    np.savez_compressed(os.path.join(HERE, 'nerf_golden.npz'), verts=rv, normals=rn, rgb_map=no['rgb_map'][0].numpy(),
+                        acc_map=no['acc_map'][0].numpy(), depth_map=no['depth_map'][0].numpy(), raw=no['raw'][0].numpy(),
+                        near_after=items['near'][0].numpy(), far_after=items['far'][0].numpy(), pose_seed=np.array(7))
     g_avatar['fwd_wpts_live'] = wl; g_avatar['fwd_wpts_cano'] = wc; g_avatar['fwd_dists'] = dists
     g_avatar['pose_seed'] = np.array(7)
     np.savez_compressed(os.path.join(HERE, 'avatar_golden.npz'), **g_avatar)

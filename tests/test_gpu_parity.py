@@ -46,7 +46,7 @@ def test_avatar_vs_golden(eng, scene, impl):
     assert maxabs(o['occ'].cpu().numpy(), g['cano_pts_ov'][:, 0]) < tol_occ
     assert maxabs(o['off'].cpu().numpy(), g['nonrigid_offset']) < 2e-6
     assert maxabs(o['rgb'].cpu().numpy(), g['rgb']) < 1e-5
-    assert maxabs(o['alpha'].cpu().numpy(), g['alpha'][:, 0]) < 1e-4
+    assert maxabs(o['alpha'].cpu().numpy(), g['alpha'][:, 0]) < 1e-4 * max(1.0, float(np.abs(g['alpha']).max()))   # density is O(100)
     off = eng.eval_warp(g['pts'], g['center'], impl=impl)
     assert maxabs(off.cpu().numpy(), g['warp_query']) < 2e-6
     q = g['pts'] + g['nonrigid_offset']
@@ -306,7 +306,7 @@ def test_config2_dense_256_properties(eng, impl):
     ref = fo.occupancy_query(s['avatar_sd'], pts[sel_t].cpu().numpy(), s['pose_map'], fr['cano_smpl_center'], with_texture=True)
     assert maxabs(o['occ'][sel_t].cpu().numpy(), ref['cano_pts_ov'][:, 0]) < 1e-4
     assert maxabs(o['rgb'][sel_t].cpu().numpy(), ref['rgb']) < 1e-5
-    assert maxabs(o['alpha'][sel_t].cpu().numpy(), ref['alpha'][:, 0]) < 1e-4
+    assert maxabs(o['alpha'][sel_t].cpu().numpy(), ref['alpha'][:, 0]) < 1e-4 * max(1.0, float(np.abs(ref['alpha']).max()))
 
 
 @pytest.mark.parametrize('res', [(96, 96, 48)])
@@ -372,3 +372,35 @@ def test_host_buffer_entry_points(eng, scene, pinned):
     assert np.array_equal(occ, d['occ'].cpu().numpy()) and np.array_equal(off, d['off'].cpu().numpy())
     assert np.array_equal(rgb, d['rgb'].cpu().numpy()) and np.array_equal(al, d['alpha'].cpu().numpy())
     assert np.array_equal(ov, eng.eval_recon(pts, g['center']).cpu().numpy())
+
+
+def test_nerf_vertex_colours_vs_golden(eng, scene):
+    """'next' row 2: NerfRenderer.render + raw2outputs through the library, driven like main.py:464-478."""
+    from avatarcap_b200 import api
+    g = load_golden('nerf_golden.npz'); fr = scene['frame']; dev = eng.device
+    wvol = torch.from_numpy(synth.blend_weight_volume(fr)).to(dev)
+    batch = {k: torch.from_numpy(fr[k])[None].to(dev) for k in ('cano_smpl_center', 'cano_bounds', 'cano2live_jnt_mats', 'live_smpl_v')}
+    R = len(g['verts'])
+    rend = api.NerfRenderer.for_engine(eng, torch.from_numpy(scene['pose_map'])[None].to(dev), torch.from_numpy(fr['smpl_skinning_weights']).to(dev),
+                                       torch.from_numpy(fr['cano_smpl_v']).to(dev), wvol)
+    items = dict(batch)
+    v = torch.from_numpy(g['verts']).to(dev); n = torch.from_numpy(g['normals']).to(dev)
+    items['ray_o'] = (v + n)[None]; items['ray_d'] = -n[None]
+    items['depth'] = torch.ones((1, R), device=dev); items['near'] = items['depth'] - 0.05; items['far'] = items['depth'] + 0.05
+    out = rend.render(items, pts_space='cano', near_dist=0.02, far_dist=0.05)
+    assert set(out) == {'rgb_map', 'acc_map', 'depth_map', 'raw', 'occ', 'nonrigid_offset'}
+    assert np.array_equal(items['near'][0].cpu().numpy(), g['near_after']) and np.array_equal(items['far'][0].cpu().numpy(), g['far_after'])
+    assert maxabs(out['raw'][0].cpu().numpy(), g['raw']) < 1e-4
+    assert maxabs(out['rgb_map'][0].cpu().numpy(), g['rgb_map']) < 1e-4
+    assert maxabs(out['acc_map'][0].cpu().numpy(), g['acc_map']) < 1e-4 and maxabs(out['depth_map'][0].cpu().numpy(), g['depth_map']) < 1e-4
+    col = api.vertex_colors(rend, batch, v, n)
+    assert maxabs(col.cpu().numpy(), g['rgb_map'][:, [2, 1, 0]]) < 1e-4
+    # colour transfer to another vertex set (main.py:480-484)
+    tgt = v[:100] + 0.001
+    assert torch.equal(api.transfer_colors(eng, tgt, v, col), col[eng.knn(tgt, v, 1)[1][:, 0]])
+    # compositing alone, bit-level vs the oracle's raw2outputs on the same raw
+    from oracle import field_oracle as fo
+    pts, z, dists = eng.ray_samples(items['ray_o'][0], items['ray_d'][0], items['near'][0], items['far'][0], 64)
+    rgb_o, acc_o, dep_o = fo.raw2outputs(out['raw'][0].cpu().reshape(R, 64, 4), z.cpu())
+    rgb_k, acc_k, dep_k = eng.composite(out['raw'][0], z)
+    assert maxabs(rgb_k.cpu().numpy(), rgb_o.numpy()) < 2e-6 and maxabs(acc_k.cpu().numpy(), acc_o.numpy()) < 2e-6
