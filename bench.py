@@ -62,18 +62,25 @@ class ClockSampler(threading.Thread):
         self.index = index; self.samples = []; self._halt = threading.Event()
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        # one streaming nvidia-smi process (-lms) instead of one process per sample: ~100 ms resolution inside the timed region
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        for line in self.proc.stdout:
+            if self._halt.is_set():
+                break
+            line = line.strip()
+            if line:
+                self.samples.append([x.strip() for x in line.split(',')])
 
     def stop(self):
-        self._halt.set(); self.join(timeout=6)
+        self._halt.set()
+        if getattr(self, 'proc', None):
+            self.proc.kill()
+        self.join(timeout=6)
         sm = [float(s[0]) for s in self.samples if s and s[0].replace('.', '').isdigit()]
         mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace('.', '').isdigit()]
         reasons = set()
