@@ -68,6 +68,7 @@ extern "C" void avc_ctx_destroy(avc_ctx* ctx) {
   for (int i = 0; i < 2; ++i) if (ctx->maps[i].d_hwc) cudaFree(ctx->maps[i].d_hwc);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
+  if (ctx->d_grid) cudaFree(ctx->d_grid);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);

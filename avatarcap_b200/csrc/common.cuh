@@ -62,6 +62,7 @@ struct avc_ctx {
   // scratch owned by the context (marching cubes scans, host staging)
   void* d_scratch = nullptr; size_t scratch_cap = 0;
   void* d_scratch2 = nullptr; size_t scratch2_cap = 0;   // marching cubes: compact edge list
+  void* d_grid = nullptr; size_t grid_cap = 0;           // KNN: uniform grid over the reference vertices
   void* h_pinned = nullptr;  size_t pinned_cap = 0;
   void* d_stage = nullptr;   size_t stage_cap = 0;
   cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;

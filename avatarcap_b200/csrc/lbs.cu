@@ -20,15 +20,18 @@ struct Top4 { float d[4]; int i[4]; };
 
 __device__ __forceinline__ void top_init(Top4& t) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { t.d[k] = 3.4e38f; t.i[k] = 0; }
+  for (int k = 0; k < 4; ++k) { t.d[k] = 3.4e38f; t.i[k] = 0x7fffffff; }
 }
 template <int K>
 __device__ __forceinline__ void top_insert(Top4& t, float d, int idx) {
-  if (d < t.d[K - 1]) {           // strict: the earlier index wins ties
+  // ordered by (distance, index): the lower index wins ties whatever the visiting order (brute force and grid agree bit for bit)
+  if (d < t.d[K - 1] || (d == t.d[K - 1] && idx < t.i[K - 1])) {
     t.d[K - 1] = d; t.i[K - 1] = idx;
 #pragma unroll
     for (int k = K - 1; k > 0; --k)
-      if (t.d[k] < t.d[k - 1]) { const float td = t.d[k]; t.d[k] = t.d[k - 1]; t.d[k - 1] = td; const int ti = t.i[k]; t.i[k] = t.i[k - 1]; t.i[k - 1] = ti; }
+      if (t.d[k] < t.d[k - 1] || (t.d[k] == t.d[k - 1] && t.i[k] < t.i[k - 1])) {
+        const float td = t.d[k]; t.d[k] = t.d[k - 1]; t.d[k - 1] = td; const int ti = t.i[k]; t.i[k] = t.i[k - 1]; t.i[k - 1] = ti;
+      }
   }
 }
 
@@ -53,15 +56,153 @@ __device__ __forceinline__ void knn_scan(const float* __restrict__ ref, int m, f
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Uniform grid over the reference vertices: exact KNN in a few cells instead of a 6 890-vertex scan per query.
+// After the shells of Chebyshev radius 0..r around the query's (clamped) cell have been visited, every unvisited vertex is
+// at least r*h away (projection onto the grid box is non-expansive), so the search stops as soon as the K-th best squared
+// distance is <= (r*h)^2; queries that are far from every vertex fall back to a scan of the whole set.
+constexpr int GRID_MAX_CELLS = 1 << 18;
+constexpr int GRID_RMAX = 3;
+struct GridDesc { float ox, oy, oz, h, inv_h; int dx, dy, dz, m, cells; };
+
+__device__ __forceinline__ int grid_cell(const GridDesc& G, float x, float y, float z, int& cx, int& cy, int& cz) {
+  cx = min(max((int)floorf((x - G.ox) * G.inv_h), 0), G.dx - 1);
+  cy = min(max((int)floorf((y - G.oy) * G.inv_h), 0), G.dy - 1);
+  cz = min(max((int)floorf((z - G.oz) * G.inv_h), 0), G.dz - 1);
+  return (cx * G.dy + cy) * G.dz + cz;
+}
+
+__global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restrict__ ref, int m, GridDesc* __restrict__ G, int* __restrict__ cnt) {
+  __shared__ float s_mn[3][32], s_mx[3][32];
+  float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int i = threadIdx.x; i < m; i += blockDim.x)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const float v = ref[3 * i + c]; mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v); }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s_mn[c][threadIdx.x >> 5] = mn[c]; s_mx[c][threadIdx.x >> 5] = mx[c]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < 3; ++c) for (int w = 0; w < 32; ++w) { mn[c] = fminf(mn[c], s_mn[c][w]); mx[c] = fmaxf(mx[c], s_mx[c][w]); }
+    const float ext = fmaxf(fmaxf(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
+    GridDesc g;
+    g.h = fmaxf(0.04f, ext / 60.f); g.inv_h = 1.f / g.h;
+    g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+    g.dx = (int)floorf((mx[0] - mn[0]) * g.inv_h) + 1; g.dy = (int)floorf((mx[1] - mn[1]) * g.inv_h) + 1; g.dz = (int)floorf((mx[2] - mn[2]) * g.inv_h) + 1;
+    g.m = m; g.cells = g.dx * g.dy * g.dz;          // <= 61^3 < GRID_MAX_CELLS
+    *G = g;
+  }
+  for (int i = threadIdx.x; i < GRID_MAX_CELLS; i += blockDim.x) cnt[i] = 0;
+}
+__global__ void grid_count_kernel(const float* __restrict__ ref, int m, const GridDesc* __restrict__ Gp, int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const GridDesc G = *Gp; int cx, cy, cz;
+  atomicAdd(&cnt[grid_cell(G, ref[3 * i], ref[3 * i + 1], ref[3 * i + 2], cx, cy, cz)], 1);
+}
+__global__ void __launch_bounds__(1024) grid_scan_kernel(const GridDesc* __restrict__ Gp, int* __restrict__ cnt, int* __restrict__ start) {
+  __shared__ int wsum[32]; __shared__ int carry;
+  const int cells = Gp->cells;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < cells; base += 1024) {
+    const int c = base + threadIdx.x;
+    const int x = c < cells ? cnt[c] : 0;
+    int inc = x;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) { const int sw = wsum[w]; if (w < wid) pre += sw; tot += sw; }
+    if (c < cells) { start[c] = carry + pre + inc - x; cnt[c] = 0; }      // cnt becomes the fill cursor
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[cells] = carry;
+}
+__global__ void grid_fill_kernel(const float* __restrict__ ref, int m, const GridDesc* __restrict__ Gp, const int* __restrict__ start,
+                                 int* __restrict__ cursor, float4* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const GridDesc G = *Gp; int cx, cy, cz;
+  const float x = ref[3 * i], y = ref[3 * i + 1], z = ref[3 * i + 2];
+  const int c = grid_cell(G, x, y, z, cx, cy, cz);
+  sorted[start[c] + atomicAdd(&cursor[c], 1)] = make_float4(x, y, z, __int_as_float(i));
+}
+
+struct GridView { const GridDesc* G; const int* start; const float4* sorted; };
+
+__device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, const float4& r) {
+  const float dx = __fsub_rn(qx, r.x), dy = __fsub_rn(qy, r.y), dz = __fsub_rn(qz, r.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+template <int K>
+__device__ __forceinline__ void knn_grid(const GridView& V, float qx, float qy, float qz, Top4& best) {
+  const GridDesc G = *V.G;
+  top_init(best);
+  int cx, cy, cz; grid_cell(G, qx, qy, qz, cx, cy, cz);
+  bool done = false;
+  for (int r = 0; r <= GRID_RMAX && !done; ++r) {
+    for (int i = max(cx - r, 0); i <= min(cx + r, G.dx - 1); ++i)
+      for (int j = max(cy - r, 0); j <= min(cy + r, G.dy - 1); ++j) {
+        const bool shell_ij = (abs(i - cx) == r) || (abs(j - cy) == r);
+        for (int k = max(cz - r, 0); k <= min(cz + r, G.dz - 1); ++k) {
+          if (!shell_ij && abs(k - cz) != r) continue;             // only the shell of radius r
+          const int c = (i * G.dy + j) * G.dz + k;
+          const int e = __ldg(V.start + c + 1);
+          for (int p = __ldg(V.start + c); p < e; ++p) { const float4 v = __ldg(V.sorted + p); top_insert<K>(best, dist2_rn(qx, qy, qz, v), __float_as_int(v.w)); }
+        }
+      }
+    const float rh = (float)r * G.h * 0.999f;      // 0.1 % slack for the float rounding of the cell assignment
+    done = best.d[K - 1] <= rh * rh;
+  }
+  if (!done) {          // far from every vertex: scan the whole set (all lanes that get here walk the same addresses)
+    top_init(best);
+    for (int p = 0; p < G.m; ++p) { const float4 v = __ldg(V.sorted + p); top_insert<K>(best, dist2_rn(qx, qy, qz, v), __float_as_int(v.w)); }
+  }
+}
+
+// min squared distance < r2 ?  (dataset/avatarcap_dataset.py:114-116 valid flag) -- bounded search, exact
+__global__ void __launch_bounds__(KNN_NT) near_flag_kernel(const float* __restrict__ q, int64_t n, GridView V, float r2, uint8_t* __restrict__ out) {
+  const int64_t g = (int64_t)blockIdx.x * KNN_NT + threadIdx.x;
+  if (g >= n) return;
+  const GridDesc G = *V.G;
+  const float qx = q[g * 3], qy = q[g * 3 + 1], qz = q[g * 3 + 2];
+  // vertices within sqrt(r2) of q lie in cells within ceil(sqrt(r2)/h) of the cell of q's projection onto the grid box;
+  // a query farther than that from the box itself cannot have any
+  const float px = fminf(fmaxf(qx, G.ox), G.ox + G.dx * G.h), py = fminf(fmaxf(qy, G.oy), G.oy + G.dy * G.h), pz = fminf(fmaxf(qz, G.oz), G.oz + G.dz * G.h);
+  const float ob = (qx - px) * (qx - px) + (qy - py) * (qy - py) + (qz - pz) * (qz - pz);
+  bool hit = false;
+  if (ob < r2 * 1.0001f) {
+    const int R = (int)floorf(sqrtf(r2) * G.inv_h) + 1;   // >= ceil, with a full cell of slack when radius is a multiple of h
+    int cx, cy, cz; grid_cell(G, qx, qy, qz, cx, cy, cz);
+    for (int i = max(cx - R, 0); i <= min(cx + R, G.dx - 1) && !hit; ++i)
+      for (int j = max(cy - R, 0); j <= min(cy + R, G.dy - 1) && !hit; ++j)
+        for (int k = max(cz - R, 0); k <= min(cz + R, G.dz - 1) && !hit; ++k) {
+          const int c = (i * G.dy + j) * G.dz + k;
+          const int e = __ldg(V.start + c + 1);
+          for (int p = __ldg(V.start + c); p < e; ++p) if (dist2_rn(qx, qy, qz, __ldg(V.sorted + p)) < r2) { hit = true; break; }
+        }
+  }
+  out[g] = hit ? 1 : 0;
+}
+
 template <int K>
 __global__ void __launch_bounds__(KNN_NT) knn_kernel(const float* __restrict__ q, int64_t n, const float* __restrict__ ref, int m,
-                                                     float* __restrict__ out_d2, int64_t* __restrict__ out_idx) {
+                                                     float* __restrict__ out_d2, int64_t* __restrict__ out_idx, GridView V) {
   __shared__ float s_ref[KNN_TILE * 3];
   const int64_t g = (int64_t)blockIdx.x * KNN_NT + threadIdx.x;
   const bool active = g < n;
   float qx = 0, qy = 0, qz = 0;
   if (active) { qx = q[g * 3]; qy = q[g * 3 + 1]; qz = q[g * 3 + 2]; }
-  Top4 best; knn_scan<K>(ref, m, qx, qy, qz, active, best, s_ref);
+  Top4 best;
+  if (V.G) { if (active) knn_grid<K>(V, qx, qy, qz, best); else top_init(best); } else knn_scan<K>(ref, m, qx, qy, qz, active, best, s_ref);
   if (active) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -105,13 +246,14 @@ __device__ __forceinline__ void blend_mats(const float lbs[24], const float* s_m
 }
 
 __global__ void __launch_bounds__(KNN_NT) lbs_weights_kernel(const float* __restrict__ pts, int64_t n, const float* __restrict__ cano_v, int m,
-                                                             const float* __restrict__ skin_w, float* __restrict__ out_lbs) {
+                                                             const float* __restrict__ skin_w, float* __restrict__ out_lbs, GridView V) {
   __shared__ float s_ref[KNN_TILE * 3];
   const int64_t g = (int64_t)blockIdx.x * KNN_NT + threadIdx.x;
   const bool active = g < n;
   float qx = 0, qy = 0, qz = 0;
   if (active) { qx = pts[g * 3]; qy = pts[g * 3 + 1]; qz = pts[g * 3 + 2]; }
-  Top4 best; knn_scan<4>(cano_v, m, qx, qy, qz, active, best, s_ref);
+  Top4 best;
+  if (V.G) { if (active) knn_grid<4>(V, qx, qy, qz, best); else top_init(best); } else knn_scan<4>(cano_v, m, qx, qy, qz, active, best, s_ref);
   if (!active) return;
   float lbs[24]; lbs_from_knn(best, skin_w, lbs);
 #pragma unroll
@@ -141,7 +283,7 @@ __global__ void __launch_bounds__(KNN_NT) skin_kernel(const float* __restrict__ 
 
 __global__ void __launch_bounds__(KNN_NT) skin_mesh_kernel(const float* __restrict__ verts, const float* __restrict__ normals, int64_t n,
                                                            const float* __restrict__ cano_v, int m, const float* __restrict__ skin_w,
-                                                           const float* __restrict__ jm, float* __restrict__ out_v, float* __restrict__ out_n) {
+                                                           const float* __restrict__ jm, float* __restrict__ out_v, float* __restrict__ out_n, GridView V) {
   __shared__ float s_ref[KNN_TILE * 3];
   __shared__ float s_m[24 * 16];
   for (int t = threadIdx.x; t < 24 * 16; t += blockDim.x) s_m[t] = jm[t];
@@ -149,7 +291,8 @@ __global__ void __launch_bounds__(KNN_NT) skin_mesh_kernel(const float* __restri
   const bool active = g < n;
   float x = 0, y = 0, z = 0;
   if (active) { x = verts[g * 3]; y = verts[g * 3 + 1]; z = verts[g * 3 + 2]; }
-  Top4 best; knn_scan<4>(cano_v, m, x, y, z, active, best, s_ref);
+  Top4 best;
+  if (V.G) { __syncthreads(); if (active) knn_grid<4>(V, x, y, z, best); else top_init(best); } else knn_scan<4>(cano_v, m, x, y, z, active, best, s_ref);
   if (!active) return;
   float lbs[24]; lbs_from_knn(best, skin_w, lbs);
   float M[12]; blend_mats<3>(lbs, s_m, M);
@@ -172,7 +315,7 @@ struct P2C {
 __global__ void __launch_bounds__(KNN_NT) posed_to_cano_kernel(const float* __restrict__ wpts, int64_t n, const float* __restrict__ live_v, int m,
                                                                const float* __restrict__ skin_w, const float* __restrict__ l2c, P2C p,
                                                                const float* __restrict__ wvol, float* __restrict__ out_cano,
-                                                               uint8_t* __restrict__ out_near) {
+                                                               uint8_t* __restrict__ out_near, GridView V) {
   __shared__ float s_ref[KNN_TILE * 3];
   __shared__ float s_m[24 * 16];
   for (int t = threadIdx.x; t < 24 * 16; t += blockDim.x) s_m[t] = l2c[t];
@@ -180,7 +323,8 @@ __global__ void __launch_bounds__(KNN_NT) posed_to_cano_kernel(const float* __re
   const bool active = g < n;
   float x = 0, y = 0, z = 0;
   if (active) { x = wpts[g * 3]; y = wpts[g * 3 + 1]; z = wpts[g * 3 + 2]; }
-  Top4 best; knn_scan<1>(live_v, m, x, y, z, active, best, s_ref);     // arch_avatar.py:190
+  Top4 best;                                                           // arch_avatar.py:190
+  if (V.G) { __syncthreads(); if (active) knn_grid<1>(V, x, y, z, best); else top_init(best); } else knn_scan<1>(live_v, m, x, y, z, active, best, s_ref);
   if (!active) return;
   if (out_near) out_near[g] = best.d[0] < 0.08f * 0.08f ? 1 : 0;         // :191
   float lbs[24];
@@ -225,6 +369,32 @@ __global__ void __launch_bounds__(KNN_NT) posed_to_cano_kernel(const float* __re
 
 inline int nblocks(int64_t n) { return (int)((n + KNN_NT - 1) / KNN_NT); }
 
+// (re)build the uniform grid over `ref` on the stream (4 tiny kernels); small sets keep the shared-memory brute force
+int build_grid(avc_ctx* ctx, const float* ref, int m, cudaStream_t st, GridView* gv) {
+  gv->G = nullptr; gv->start = nullptr; gv->sorted = nullptr;
+  if (m < 512) return AVC_OK;
+  const size_t need = 256 + (size_t)GRID_MAX_CELLS * 4 + ((size_t)GRID_MAX_CELLS + 4) * 4 + (size_t)m * sizeof(float4) + 64;
+  if (need > ctx->grid_cap) {
+    if (ctx->d_grid) cudaFree(ctx->d_grid);
+    ctx->d_grid = nullptr; ctx->grid_cap = 0;
+    AVC_CUDA(ctx, cudaMalloc(&ctx->d_grid, need));
+    ctx->grid_cap = need;
+  }
+  char* base = (char*)ctx->d_grid;
+  GridDesc* G = (GridDesc*)base; int* cnt = (int*)(base + 256); int* start = cnt + GRID_MAX_CELLS;
+  float4* sorted = (float4*)(base + 256 + (size_t)GRID_MAX_CELLS * 4 + ((size_t)GRID_MAX_CELLS + 4) * 4);
+  grid_bounds_kernel<<<1, 1024, 0, st>>>(ref, m, G, cnt);
+  AVC_LAUNCH_CHECK(ctx, "grid_bounds_kernel");
+  grid_count_kernel<<<(m + 255) / 256, 256, 0, st>>>(ref, m, G, cnt);
+  AVC_LAUNCH_CHECK(ctx, "grid_count_kernel");
+  grid_scan_kernel<<<1, 1024, 0, st>>>(G, cnt, start);
+  AVC_LAUNCH_CHECK(ctx, "grid_scan_kernel");
+  grid_fill_kernel<<<(m + 255) / 256, 256, 0, st>>>(ref, m, G, start, cnt, sorted);
+  AVC_LAUNCH_CHECK(ctx, "grid_fill_kernel");
+  gv->G = G; gv->start = start; gv->sorted = sorted;
+  return AVC_OK;
+}
+
 }  // namespace
 
 extern "C" int avc_knn(avc_ctx* ctx, const float* query, int64_t n, const float* ref, int m, int K, float* out_d2, int64_t* out_idx, void* stream) {
@@ -232,11 +402,13 @@ extern "C" int avc_knn(avc_ctx* ctx, const float* query, int64_t n, const float*
   if (K < 1 || K > 4 || m < K) return avc_fail(ctx, AVC_EINVAL, "avc_knn: K must be 1..4 and m >= K");
   if (n == 0) return AVC_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  GridView gv; int rc = build_grid(ctx, ref, m, st, &gv);
+  if (rc) return rc;
   switch (K) {
-    case 1: knn_kernel<1><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx); break;
-    case 2: knn_kernel<2><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx); break;
-    case 3: knn_kernel<3><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx); break;
-    default: knn_kernel<4><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx); break;
+    case 1: knn_kernel<1><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx, gv); break;
+    case 2: knn_kernel<2><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx, gv); break;
+    case 3: knn_kernel<3><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx, gv); break;
+    default: knn_kernel<4><<<nblocks(n), KNN_NT, 0, st>>>(query, n, ref, m, out_d2, out_idx, gv); break;
   }
   AVC_LAUNCH_CHECK(ctx, "knn_kernel");
   return AVC_OK;
@@ -247,7 +419,9 @@ extern "C" int avc_lbs_weights(avc_ctx* ctx, const float* pts, int64_t n, const 
   if (!ctx || !pts || !cano_verts || !skin_weights || !out_lbs) return avc_fail(ctx, AVC_EINVAL, "avc_lbs_weights: NULL argument");
   if (m < 4) return avc_fail(ctx, AVC_EINVAL, "avc_lbs_weights: need at least 4 reference vertices");
   if (n == 0) return AVC_OK;
-  lbs_weights_kernel<<<nblocks(n), KNN_NT, 0, (cudaStream_t)stream>>>(pts, n, cano_verts, m, skin_weights, out_lbs);
+  GridView gv; int rc = build_grid(ctx, cano_verts, m, (cudaStream_t)stream, &gv);
+  if (rc) return rc;
+  lbs_weights_kernel<<<nblocks(n), KNN_NT, 0, (cudaStream_t)stream>>>(pts, n, cano_verts, m, skin_weights, out_lbs, gv);
   AVC_LAUNCH_CHECK(ctx, "lbs_weights_kernel");
   return AVC_OK;
 }
@@ -275,7 +449,9 @@ extern "C" int avc_skin_mesh(avc_ctx* ctx, const float* verts, const float* norm
   if (!ctx || !verts || !cano_verts || !skin_weights || !jnt_mats || !out_verts) return avc_fail(ctx, AVC_EINVAL, "avc_skin_mesh: NULL argument");
   if (m < 4) return avc_fail(ctx, AVC_EINVAL, "avc_skin_mesh: need at least 4 reference vertices");
   if (n == 0) return AVC_OK;
-  skin_mesh_kernel<<<nblocks(n), KNN_NT, 0, (cudaStream_t)stream>>>(verts, normals, n, cano_verts, m, skin_weights, jnt_mats, out_verts, out_normals);
+  GridView gv; int rc = build_grid(ctx, cano_verts, m, (cudaStream_t)stream, &gv);
+  if (rc) return rc;
+  skin_mesh_kernel<<<nblocks(n), KNN_NT, 0, (cudaStream_t)stream>>>(verts, normals, n, cano_verts, m, skin_weights, jnt_mats, out_verts, out_normals, gv);
   AVC_LAUNCH_CHECK(ctx, "skin_mesh_kernel");
   return AVC_OK;
 }
@@ -289,8 +465,23 @@ extern "C" int avc_posed_to_cano(avc_ctx* ctx, const float* wpts, int64_t n, con
   if (n == 0) return AVC_OK;
   P2C p;
   for (int a = 0; a < 3; ++a) { p.bmin[a] = bounds[a]; p.len[a] = bounds[3 + a] - bounds[a]; p.vd[a] = vdims[a]; p.inv_unused[a] = 0.f; }
+  GridView gv; int rc = build_grid(ctx, live_verts, m, (cudaStream_t)stream, &gv);
+  if (rc) return rc;
   posed_to_cano_kernel<<<nblocks(n), KNN_NT, 0, (cudaStream_t)stream>>>(wpts, n, live_verts, m, skin_weights, live2cano_mats, p, weight_volume,
-                                                                       out_cano, out_near);
+                                                                       out_cano, out_near, gv);
   AVC_LAUNCH_CHECK(ctx, "posed_to_cano_kernel");
+  return AVC_OK;
+}
+
+extern "C" int avc_near_flag(avc_ctx* ctx, const float* query, int64_t n, const float* ref, int m, float radius, uint8_t* out_flag, void* stream) {
+  if (!ctx || !query || !ref || !out_flag) return avc_fail(ctx, AVC_EINVAL, "avc_near_flag: NULL argument");
+  if (m < 1 || !(radius > 0.f)) return avc_fail(ctx, AVC_EINVAL, "avc_near_flag: bad sizes");
+  if (n == 0) return AVC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  GridView gv; int rc = build_grid(ctx, ref, m, st, &gv);
+  if (rc) return rc;
+  if (!gv.G) return avc_fail(ctx, AVC_EINVAL, "avc_near_flag: needs at least 512 reference vertices (use avc_knn for small sets)");
+  near_flag_kernel<<<nblocks(n), KNN_NT, 0, st>>>(query, n, gv, radius * radius, out_flag);
+  AVC_LAUNCH_CHECK(ctx, "near_flag_kernel");
   return AVC_OK;
 }

@@ -226,6 +226,12 @@ class Engine:
         self._check(self.lib.avc_knn(self._h, _ptr(q), n, _ptr(r), r.shape[0], K, _ptr(d2), _ptr(idx), self._stream()))
         return d2, idx
 
+    def near_flag(self, query, ref, radius: float) -> torch.Tensor:
+        q = self._f32(query, 3); r = self._f32(ref, 3)
+        out = torch.empty(q.shape[0], device=self.device, dtype=torch.uint8)
+        self._check(self.lib.avc_near_flag(self._h, _ptr(q), q.shape[0], _ptr(r), r.shape[0], float(radius), _ptr(out), self._stream()))
+        return out.bool()
+
     def lbs_weights(self, pts, cano_verts, skin_weights) -> torch.Tensor:
         p = self._f32(pts, 3); v = self._f32(cano_verts, 3); w = self._f32(skin_weights, 24)
         out = torch.empty((p.shape[0], 24), device=self.device, dtype=torch.float32)

@@ -20,8 +20,7 @@ from .engine import Engine
 
 def valid_points_flag(engine: Engine, vol_pts: torch.Tensor, cano_smpl_v, thres: float = 0.1) -> torch.Tensor:
     """infer_pts_flag = knn_points(vol_pts, cano_smpl_v, K=1).dists < 0.1**2   (avatarcap_dataset.py:114-116)."""
-    d2, _ = engine.knn(vol_pts, cano_smpl_v, 1)
-    return d2[:, 0] < thres ** 2
+    return engine.near_flag(vol_pts, cano_smpl_v, thres)
 
 
 def _mesh_to_live(engine: Engine, verts, normals, frame: Dict):

@@ -155,6 +155,10 @@ int avc_mc_emit(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], cons
  * out_d2 (n,K) float, out_idx (n,K) int64 (either may be NULL).                                        */
 int avc_knn(avc_ctx* ctx, const float* query /*[dev] (n,3)*/, int64_t n, const float* ref /*[dev] (m,3)*/, int m, int K,
             float* out_d2 /*[dev]*/, int64_t* out_idx /*[dev]*/, void* stream);
+/* validity flag of the dense grid (dataset/avatarcap_dataset.py:114-116): out_flag[i] = (min_j |q_i - ref_j|^2 < radius^2), exact,
+ * bounded search in a uniform grid over the reference vertices (m >= 512). radius = 0.1 in the reference. */
+int avc_near_flag(avc_ctx* ctx, const float* query /*[dev] (n,3)*/, int64_t n, const float* ref /*[dev] (m,3)*/, int m, float radius,
+                  uint8_t* out_flag /*[dev] (n)*/, void* stream);
 /* SmplUtil.calculate_lbs (smpl_util.py:24-39): out (n,24) */
 int avc_lbs_weights(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, const float* cano_verts /*[dev] (m,3)*/, int m,
                     const float* skin_weights /*[dev] (m,24)*/, float* out_lbs /*[dev] (n,24)*/, void* stream);

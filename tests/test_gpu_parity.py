@@ -404,3 +404,18 @@ def test_nerf_vertex_colours_vs_golden(eng, scene):
     rgb_o, acc_o, dep_o = fo.raw2outputs(out['raw'][0].cpu().reshape(R, 64, 4), z.cpu())
     rgb_k, acc_k, dep_k = eng.composite(out['raw'][0], z)
     assert maxabs(rgb_k.cpu().numpy(), rgb_o.numpy()) < 2e-6 and maxabs(acc_k.cpu().numpy(), acc_o.numpy()) < 2e-6
+
+
+def test_near_flag_and_grid_knn_far_queries(eng, scene):
+    """uniform-grid KNN: exact also for queries far from every vertex (fallback scan) and for the bounded near-flag search"""
+    from oracle import field_oracle as fo
+    fr = scene['frame']
+    rs = np.random.RandomState(12)
+    bmin, bmax = fr['cano_bounds']
+    q = (rs.uniform(0, 1, (20000, 3)) * (bmax - bmin) * 1.6 + bmin - 0.3 * (bmax - bmin)).astype(np.float32)     # many far outside the body
+    rd, ri = fo.knn_points(torch.from_numpy(q), torch.from_numpy(fr['cano_smpl_v']), 4)
+    d2, idx = eng.knn(q, fr['cano_smpl_v'], 4)
+    assert np.array_equal(idx.cpu().numpy(), ri.numpy()) and np.array_equal(d2.cpu().numpy(), rd.numpy())
+    for radius in (0.1, 0.08, 0.03):
+        flag = eng.near_flag(q, fr['cano_smpl_v'], radius).cpu().numpy()
+        assert np.array_equal(flag, rd[:, 0].numpy() < np.float32(radius) ** 2 if False else rd[:, 0].numpy() < radius * radius)
