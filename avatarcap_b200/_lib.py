@@ -42,11 +42,12 @@ SIGNATURES = {
     'avc_mc_count': (_i, [_vp, _vp, C.POINTER(_i), _f, _i, _i, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     'avc_mc_emit': (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_f), _f, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i64, _vp]),
     'avc_knn': (_i, [_vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
-    'avc_near_flag': (_i, [_vp, _vp, _i64, _vp, _i, _f, _vp, _vp]),
+    'avc_near_flag': (_i, [_vp, _vp, _i64, _vp, _i, C.c_double, _vp, _vp]),
     'avc_lbs_weights': (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),
     'avc_skin_points': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'avc_skin_normals': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'avc_skin_mesh': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    'avc_inside_volume': (_i, [_vp, _vp, _i, _vp, _i, C.POINTER(_f), C.POINTER(_i), _vp, _vp]),
     'avc_ray_samples': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     'avc_nerf_raw': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_f), _i64, _vp, _vp]),
     'avc_composite': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp]),

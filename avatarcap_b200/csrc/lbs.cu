@@ -143,7 +143,7 @@ __device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, const fl
 }
 
 template <int K>
-__device__ __forceinline__ void knn_grid(const GridView& V, float qx, float qy, float qz, Top4& best) {
+__device__ __forceinline__ bool knn_grid(const GridView& V, float qx, float qy, float qz, Top4& best) {
   const GridDesc G = *V.G;
   top_init(best);
   int cx, cy, cz; grid_cell(G, qx, qy, qz, cx, cy, cz);
@@ -162,10 +162,7 @@ __device__ __forceinline__ void knn_grid(const GridView& V, float qx, float qy, 
     const float rh = (float)r * G.h * 0.999f;      // 0.1 % slack for the float rounding of the cell assignment
     done = best.d[K - 1] <= rh * rh;
   }
-  if (!done) {          // far from every vertex: scan the whole set (all lanes that get here walk the same addresses)
-    top_init(best);
-    for (int p = 0; p < G.m; ++p) { const float4 v = __ldg(V.sorted + p); top_insert<K>(best, dist2_rn(qx, qy, qz, v), __float_as_int(v.w)); }
-  }
+  return done;          // false: far from every vertex -> the caller falls back to the block-cooperative brute-force scan
 }
 
 // min squared distance < r2 ?  (dataset/avatarcap_dataset.py:114-116 valid flag) -- bounded search, exact
@@ -202,7 +199,9 @@ __global__ void __launch_bounds__(KNN_NT) knn_kernel(const float* __restrict__ q
   float qx = 0, qy = 0, qz = 0;
   if (active) { qx = q[g * 3]; qy = q[g * 3 + 1]; qz = q[g * 3 + 2]; }
   Top4 best;
-  if (V.G) { if (active) knn_grid<K>(V, qx, qy, qz, best); else top_init(best); } else knn_scan<K>(ref, m, qx, qy, qz, active, best, s_ref);
+  bool need = active;
+  if (V.G) { top_init(best); need = active && !knn_grid<K>(V, qx, qy, qz, best); }
+  if (__syncthreads_or(need)) { Top4 b2; knn_scan<K>(ref, m, qx, qy, qz, need, b2, s_ref); if (need) best = b2; }
   if (active) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -253,7 +252,9 @@ __global__ void __launch_bounds__(KNN_NT) lbs_weights_kernel(const float* __rest
   float qx = 0, qy = 0, qz = 0;
   if (active) { qx = pts[g * 3]; qy = pts[g * 3 + 1]; qz = pts[g * 3 + 2]; }
   Top4 best;
-  if (V.G) { if (active) knn_grid<4>(V, qx, qy, qz, best); else top_init(best); } else knn_scan<4>(cano_v, m, qx, qy, qz, active, best, s_ref);
+  bool need = active;
+  if (V.G) { top_init(best); need = active && !knn_grid<4>(V, qx, qy, qz, best); }
+  if (__syncthreads_or(need)) { Top4 b2; knn_scan<4>(cano_v, m, qx, qy, qz, need, b2, s_ref); if (need) best = b2; }
   if (!active) return;
   float lbs[24]; lbs_from_knn(best, skin_w, lbs);
 #pragma unroll
@@ -292,7 +293,9 @@ __global__ void __launch_bounds__(KNN_NT) skin_mesh_kernel(const float* __restri
   float x = 0, y = 0, z = 0;
   if (active) { x = verts[g * 3]; y = verts[g * 3 + 1]; z = verts[g * 3 + 2]; }
   Top4 best;
-  if (V.G) { __syncthreads(); if (active) knn_grid<4>(V, x, y, z, best); else top_init(best); } else knn_scan<4>(cano_v, m, x, y, z, active, best, s_ref);
+  bool need = active;
+  if (V.G) { top_init(best); need = active && !knn_grid<4>(V, x, y, z, best); }
+  if (__syncthreads_or(need)) { Top4 b2; knn_scan<4>(cano_v, m, x, y, z, need, b2, s_ref); if (need) best = b2; }
   if (!active) return;
   float lbs[24]; lbs_from_knn(best, skin_w, lbs);
   float M[12]; blend_mats<3>(lbs, s_m, M);
@@ -324,7 +327,9 @@ __global__ void __launch_bounds__(KNN_NT) posed_to_cano_kernel(const float* __re
   float x = 0, y = 0, z = 0;
   if (active) { x = wpts[g * 3]; y = wpts[g * 3 + 1]; z = wpts[g * 3 + 2]; }
   Top4 best;                                                           // arch_avatar.py:190
-  if (V.G) { __syncthreads(); if (active) knn_grid<1>(V, x, y, z, best); else top_init(best); } else knn_scan<1>(live_v, m, x, y, z, active, best, s_ref);
+  bool need = active;
+  if (V.G) { top_init(best); need = active && !knn_grid<1>(V, x, y, z, best); }
+  if (__syncthreads_or(need)) { Top4 b2; knn_scan<1>(live_v, m, x, y, z, need, b2, s_ref); if (need) best = b2; }
   if (!active) return;
   if (out_near) out_near[g] = best.d[0] < 0.08f * 0.08f ? 1 : 0;         // :191
   float lbs[24];
@@ -473,15 +478,15 @@ extern "C" int avc_posed_to_cano(avc_ctx* ctx, const float* wpts, int64_t n, con
   return AVC_OK;
 }
 
-extern "C" int avc_near_flag(avc_ctx* ctx, const float* query, int64_t n, const float* ref, int m, float radius, uint8_t* out_flag, void* stream) {
+extern "C" int avc_near_flag(avc_ctx* ctx, const float* query, int64_t n, const float* ref, int m, double radius, uint8_t* out_flag, void* stream) {
   if (!ctx || !query || !ref || !out_flag) return avc_fail(ctx, AVC_EINVAL, "avc_near_flag: NULL argument");
-  if (m < 1 || !(radius > 0.f)) return avc_fail(ctx, AVC_EINVAL, "avc_near_flag: bad sizes");
+  if (m < 1 || !(radius > 0.0)) return avc_fail(ctx, AVC_EINVAL, "avc_near_flag: bad sizes");
   if (n == 0) return AVC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   GridView gv; int rc = build_grid(ctx, ref, m, st, &gv);
   if (rc) return rc;
   if (!gv.G) return avc_fail(ctx, AVC_EINVAL, "avc_near_flag: needs at least 512 reference vertices (use avc_knn for small sets)");
-  near_flag_kernel<<<nblocks(n), KNN_NT, 0, st>>>(query, n, gv, radius * radius, out_flag);
+  near_flag_kernel<<<nblocks(n), KNN_NT, 0, st>>>(query, n, gv, (float)(radius * radius), out_flag);   // float32(0.1 ** 2) like torch (dist < 0.1 ** 2)
   AVC_LAUNCH_CHECK(ctx, "near_flag_kernel");
   return AVC_OK;
 }

@@ -232,6 +232,14 @@ class Engine:
         self._check(self.lib.avc_near_flag(self._h, _ptr(q), q.shape[0], _ptr(r), r.shape[0], float(radius), _ptr(out), self._stream()))
         return out.bool()
 
+    def inside_volume(self, verts, faces, bounds, res) -> torch.Tensor:
+        """(Rx,Ry,Rz) bool: grid point inside the closed mesh (trimesh.contains on the dense grid, avatarcap_dataset.py:120-124)."""
+        v = self._f32(verts, 3); f = torch.as_tensor(np.asarray(faces) if not isinstance(faces, torch.Tensor) else faces).to(self.device, torch.int32).contiguous()
+        out = torch.empty(tuple(int(r) for r in res), device=self.device, dtype=torch.uint8)
+        b = np.asarray(bounds, dtype=np.float32).reshape(6)
+        self._check(self.lib.avc_inside_volume(self._h, _ptr(v), v.shape[0], _ptr(f), f.shape[0], _lib.f6(b), _lib.i3(res), _ptr(out), self._stream()))
+        return out.bool()
+
     def lbs_weights(self, pts, cano_verts, skin_weights) -> torch.Tensor:
         p = self._f32(pts, 3); v = self._f32(cano_verts, 3); w = self._f32(skin_weights, 24)
         out = torch.empty((p.shape[0], 24), device=self.device, dtype=torch.float32)

@@ -23,6 +23,13 @@ def valid_points_flag(engine: Engine, vol_pts: torch.Tensor, cano_smpl_v, thres:
     return engine.near_flag(vol_pts, cano_smpl_v, thres)
 
 
+def invalid_points_fill(engine: Engine, smpl_verts, smpl_faces, bounds, vol_res, flag: torch.Tensor) -> torch.Tensor:
+    """invalid_pts_ov = 2 * trimesh.contains(invalid_pts) - 1 for the grid points with flag == False, in grid order
+    (avatarcap_dataset.py:120-124)."""
+    inside = engine.inside_volume(smpl_verts, smpl_faces, bounds, vol_res).reshape(-1)
+    return 2.0 * inside[~flag].to(torch.float32) - 1.0
+
+
 def _mesh_to_live(engine: Engine, verts, normals, frame: Dict):
     return engine.skin_mesh(verts, normals, frame['cano_smpl_v'], frame['smpl_skinning_weights'], frame['cano2live_jnt_mats'])
 

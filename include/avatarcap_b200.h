@@ -157,7 +157,7 @@ int avc_knn(avc_ctx* ctx, const float* query /*[dev] (n,3)*/, int64_t n, const f
             float* out_d2 /*[dev]*/, int64_t* out_idx /*[dev]*/, void* stream);
 /* validity flag of the dense grid (dataset/avatarcap_dataset.py:114-116): out_flag[i] = (min_j |q_i - ref_j|^2 < radius^2), exact,
  * bounded search in a uniform grid over the reference vertices (m >= 512). radius = 0.1 in the reference. */
-int avc_near_flag(avc_ctx* ctx, const float* query /*[dev] (n,3)*/, int64_t n, const float* ref /*[dev] (m,3)*/, int m, float radius,
+int avc_near_flag(avc_ctx* ctx, const float* query /*[dev] (n,3)*/, int64_t n, const float* ref /*[dev] (m,3)*/, int m, double radius,
                   uint8_t* out_flag /*[dev] (n)*/, void* stream);
 /* SmplUtil.calculate_lbs (smpl_util.py:24-39): out (n,24) */
 int avc_lbs_weights(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, const float* cano_verts /*[dev] (m,3)*/, int m,
@@ -180,6 +180,14 @@ int avc_posed_to_cano(avc_ctx* ctx, const float* wpts /*[dev]*/, int64_t n, cons
                       const float* skin_weights /*[dev] (m,24)*/, const float* live2cano_mats /*[dev] (24,4,4)*/,
                       const float bounds[6] /*[host]*/, const float* weight_volume /*[dev] (X,Y,Z,24)*/, const int vdims[3],
                       float* out_cano /*[dev]*/, uint8_t* out_near /*[dev]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* dataset-side precompute ("next" row: dataset/avatarcap_dataset.py:110-125)                       */
+/* ---------------------------------------------------------------------------------------------- */
+/* trimesh.contains on the dense grid (avatarcap_dataset.py:120-124): out_inside (Rx,Ry,Rz) uint8 = 1 where the grid point of
+ * generate_volume_points lies inside the closed triangle mesh (verts (nv,3) f32, faces (nf,3) int32), by crossing parity along +z. */
+int avc_inside_volume(avc_ctx* ctx, const float* verts /*[dev]*/, int nv, const int32_t* faces /*[dev]*/, int nf, const float bounds[6] /*[host]*/,
+                      const int res[3], uint8_t* out_inside /*[dev]*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* vertex-colour evaluation driver ("next" row: NerfRenderer.render + raw2outputs, main.py:464-485) */

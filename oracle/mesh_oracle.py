@@ -147,3 +147,30 @@ def chamfer(a: np.ndarray, b: np.ndarray) -> float:
     from scipy.spatial import cKDTree
     da, _ = cKDTree(b).query(a); db, _ = cKDTree(a).query(b)
     return float(0.5 * (da.mean() + db.mean()))
+
+
+def contains_points(verts: np.ndarray, faces: np.ndarray, pts: np.ndarray, chunk: int = 2048) -> np.ndarray:
+    """Restates trimesh.Trimesh.contains (ray-casting parity; dataset/avatarcap_dataset.py:120-123; trimesh is a third-party
+    dependency that is not installed here -> PARITY UNPINNED, pinned by analytic shapes in the tests): a point is inside a closed
+    mesh iff a ray along +z crosses the surface an odd number of times. float64, top-left rule on the projected triangles."""
+    v = np.asarray(verts, np.float64); f = np.asarray(faces, np.int64); p = np.asarray(pts, np.float64)
+    a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    area = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])
+    ok = area != 0
+    a, b, c, area = a[ok], b[ok], c[ok], area[ok]
+    sgn = np.sign(area)
+    out = np.zeros(len(p), bool)
+
+    def edge(pa, pb, px, py):
+        e = sgn[None] * ((pb[None, :, 0] - pa[None, :, 0]) * (py[:, None] - pa[None, :, 1]) - (pb[None, :, 1] - pa[None, :, 1]) * (px[:, None] - pa[None, :, 0]))
+        dx = (sgn * (pb[:, 0] - pa[:, 0]))[None]; dy = (sgn * (pb[:, 1] - pa[:, 1]))[None]
+        return (e > 0) | ((e == 0) & (((dy == 0) & (dx < 0)) | (dy < 0)))
+
+    for s in range(0, len(p), chunk):
+        q = p[s:s + chunk]; px, py, pz = q[:, 0], q[:, 1], q[:, 2]
+        ins = edge(a, b, px, py) & edge(b, c, px, py) & edge(c, a, px, py)
+        w0 = ((b[None, :, 0] - px[:, None]) * (c[None, :, 1] - py[:, None]) - (b[None, :, 1] - py[:, None]) * (c[None, :, 0] - px[:, None])) / area[None]
+        w1 = ((c[None, :, 0] - px[:, None]) * (a[None, :, 1] - py[:, None]) - (c[None, :, 1] - py[:, None]) * (a[None, :, 0] - px[:, None])) / area[None]
+        zc = w0 * a[None, :, 2] + w1 * b[None, :, 2] + (1 - w0 - w1) * c[None, :, 2]
+        out[s:s + chunk] = ((ins & (zc > pz[:, None])).sum(1) % 2) == 1
+    return out

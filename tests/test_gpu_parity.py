@@ -418,4 +418,42 @@ def test_near_flag_and_grid_knn_far_queries(eng, scene):
     assert np.array_equal(idx.cpu().numpy(), ri.numpy()) and np.array_equal(d2.cpu().numpy(), rd.numpy())
     for radius in (0.1, 0.08, 0.03):
         flag = eng.near_flag(q, fr['cano_smpl_v'], radius).cpu().numpy()
-        assert np.array_equal(flag, rd[:, 0].numpy() < np.float32(radius) ** 2 if False else rd[:, 0].numpy() < radius * radius)
+        assert np.array_equal(flag, (rd[:, 0] < radius ** 2).numpy())            # torch semantics: float32(radius ** 2)
+
+
+def _uv_sphere(center, radius, n_lat=24, n_lon=32):
+    th = np.linspace(0, np.pi, n_lat + 1)[1:-1]; ph = np.linspace(0, 2 * np.pi, n_lon, endpoint=False)
+    v = [[0, 0, 1]] + [[np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(t)] for t in th for p in ph] + [[0, 0, -1]]
+    v = np.asarray(v) * radius + np.asarray(center)
+    f = []
+    for j in range(n_lon):
+        f.append([0, 1 + j, 1 + (j + 1) % n_lon])
+    for i in range(n_lat - 2):
+        for j in range(n_lon):
+            a = 1 + i * n_lon + j; b = 1 + i * n_lon + (j + 1) % n_lon; c = a + n_lon; d = b + n_lon
+            f += [[a, c, b], [b, c, d]]
+    last = len(v) - 1; base = 1 + (n_lat - 2) * n_lon
+    for j in range(n_lon):
+        f.append([last, base + (j + 1) % n_lon, base + j])
+    return v.astype(np.float32), np.asarray(f, np.int32)
+
+
+def test_inside_volume_fill(eng):
+    """'next' row 3: trimesh.contains on the dense grid, by crossing parity; vs the CPU ray-parity oracle and the analytic shape"""
+    from oracle import mesh_oracle as mo
+    from oracle import field_oracle as fo
+    from avatarcap_b200 import pipeline
+    bounds = np.array([[-0.9, -1.0, -0.35], [0.95, 0.9, 0.3]], np.float32)
+    v1, f1 = _uv_sphere([0.1, -0.2, 0.0], 0.27); v2, f2 = _uv_sphere([-0.45, 0.5, 0.05], 0.2, 16, 20)
+    verts = np.concatenate([v1, v2], 0); faces = np.concatenate([f1, f2 + len(v1)], 0)
+    res = (48, 56, 24)
+    inside = eng.inside_volume(verts, faces, bounds, res).cpu().numpy()
+    pts = fo.generate_volume_points(bounds, res)
+    ref = mo.contains_points(verts, faces, pts).reshape(res)
+    assert np.array_equal(inside, ref)
+    d1 = np.linalg.norm(pts - np.array([0.1, -0.2, 0.0]), axis=1).reshape(res); d2 = np.linalg.norm(pts - np.array([-0.45, 0.5, 0.05]), axis=1).reshape(res)
+    sure_in = (d1 < 0.25) | (d2 < 0.18); sure_out = (d1 > 0.28) & (d2 > 0.21)
+    assert inside[sure_in].all() and not inside[sure_out].any() and inside.sum() > 100
+    flag = torch.from_numpy((d1 < 0.31).reshape(-1)).to(eng.device)
+    fill = pipeline.invalid_points_fill(eng, verts, faces, bounds, res, flag).cpu().numpy()
+    assert np.array_equal(fill, 2.0 * ref.reshape(-1)[~flag.cpu().numpy()].astype(np.float32) - 1.0)
