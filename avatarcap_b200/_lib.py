@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libavatarcap_b200.so')
 
 OK, EINVAL, ECUDA, ESTATE, ECAPACITY, EFORMAT, EVALUE = 0, -1, -2, -3, -4, -5, -6
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC2 = 0, 1, 2, 3
 IF_SDF, IF_OCCUPANCY = 0, 1
 MAP_POSE, MAP_IMAGE = 0, 1
 

@@ -154,6 +154,7 @@ extern "C" int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw, in
 // -----------------------------------------------------------------------------------------------------------------
 static int pick_impl(avc_ctx* ctx, int impl, bool* use_tc) {
   if (impl == AVC_IMPL_SIMT) { *use_tc = false; return AVC_OK; }
+  if (impl == AVC_IMPL_TC2) impl = AVC_IMPL_TC;
   if (impl == AVC_IMPL_TC) {
     if (!avc_tc_available(ctx)) return avc_fail(ctx, AVC_ESTATE, "tensor-core path requested but not available (needs sm_100 and a library built with tcgen05)");
     *use_tc = true; return AVC_OK;
@@ -174,6 +175,7 @@ static int eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float ce
   if (rc) return rc;
   const float zero[3] = {0, 0, 0};
   const float* c = center ? center : zero;
+  if (use_tc && impl == AVC_IMPL_TC2) return avc_tc2_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st);
   return use_tc ? avc_tc_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st)
                 : avc_simt_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st);
 }
@@ -201,6 +203,7 @@ extern "C" int avc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const f
   if (!ctx->maps[AVC_MAP_IMAGE].d_hwc) return avc_fail(ctx, AVC_ESTATE, "image feature map not set");
   bool use_tc; int rc = pick_impl(ctx, impl, &use_tc);
   if (rc) return rc;
+  if (use_tc && impl == AVC_IMPL_TC2) return avc_tc2_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream);
   return use_tc ? avc_tc_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream)
                 : avc_simt_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream);
 }

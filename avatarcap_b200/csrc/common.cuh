@@ -96,6 +96,10 @@ int avc_tc_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float ce
                        float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
 int avc_tc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
 int avc_tc_available(const avc_ctx* ctx);
+// experimental cta_group::2 variant (field_tc2.cu)
+int avc_tc2_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
+                        float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
+int avc_tc2_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
 
 // mode for the avatar evaluation
 enum { AVC_MODE_QUERY = 0 /* warp + template */, AVC_MODE_WARP_ONLY = 1, AVC_MODE_TEMPLATE_ONLY = 2 };

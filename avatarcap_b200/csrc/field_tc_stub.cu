@@ -8,4 +8,10 @@ int avc_tc_eval_avatar(avc_ctx* ctx, const float*, int64_t, const float*, float*
 int avc_tc_eval_recon(avc_ctx* ctx, const float*, int64_t, const float*, float*, cudaStream_t) {
   return avc_fail(ctx, AVC_ESTATE, "library built without the tcgen05 kernel");
 }
+int avc_tc2_eval_avatar(avc_ctx* ctx, const float*, int64_t, const float*, float*, float*, float*, float*, int, int, cudaStream_t) {
+  return avc_fail(ctx, AVC_ESTATE, "library built without the tcgen05 kernel");
+}
+int avc_tc2_eval_recon(avc_ctx* ctx, const float*, int64_t, const float*, float*, cudaStream_t) {
+  return avc_fail(ctx, AVC_ESTATE, "library built without the tcgen05 kernel");
+}
 #endif

@@ -15,7 +15,7 @@ import torch
 from . import _lib, packer
 from ._lib import AvcError, IMPL_AUTO, IMPL_SIMT, IMPL_TC, IF_SDF, IF_OCCUPANCY, MAP_POSE, MAP_IMAGE
 
-_IMPL = {'auto': IMPL_AUTO, 'simt': IMPL_SIMT, 'tc': IMPL_TC}
+_IMPL = {'auto': IMPL_AUTO, 'simt': IMPL_SIMT, 'tc': IMPL_TC, 'tc2': _lib.IMPL_TC2}
 
 
 def _ptr(t: Optional[torch.Tensor]):

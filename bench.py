@@ -353,7 +353,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--kernel', default='auto', choices=['auto', 'simt', 'tc'])
+    ap.add_argument('--kernel', default='auto', choices=['auto', 'simt', 'tc', 'tc2'])
     ap.add_argument('--res', type=int, default=None, help='override the per-GPU grid edge (debug only; the metric is quoted at 256)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')

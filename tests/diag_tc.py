@@ -25,6 +25,7 @@ def stats(name, a, b):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+    impl = sys.argv[2] if len(sys.argv) > 2 else 'tc'
     eng = Engine()
     print('device', torch.cuda.get_device_name(0), 'tc path:', eng.has_tensor_core_path)
     s = golden_scene(); g = load_golden('avatar_golden.npz')
@@ -41,7 +42,7 @@ def main():
     ):
         try:
             ref = fn('simt'); torch.cuda.synchronize()
-            out = fn('tc'); torch.cuda.synchronize()
+            out = fn(impl); torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             print('%-28s FAILED: %r' % (name, e))
             break
@@ -51,7 +52,7 @@ def main():
             print('   first occ tc  :', out[2][:6].cpu().numpy())
             print('   first occ simt:', ref[2][:6].cpu().numpy())
     # determinism / tile independence
-    a = eng.eval_occupancy(pts, c, impl='tc')['occ']; b = eng.eval_occupancy(pts[:n // 2 + 7], c, impl='tc')['occ']
+    a = eng.eval_occupancy(pts, c, impl=impl)['occ']; b = eng.eval_occupancy(pts[:n // 2 + 7], c, impl=impl)['occ']
     print('tile independence: max|d| =', float((a[:n // 2 + 7] - b).abs().max()))
     eng.close()
 
