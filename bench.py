@@ -283,7 +283,14 @@ def run_ours(args):
         t_mesh, (mv, mf, mn) = timed(lambda: eng.extract_mesh(vol_m, frame['cano_bounds'], 0.0))
         t_lbs, _ = timed(lambda: eng.skin_mesh(mv, mn, cv, sw, jm))
         t_all, _ = timed(lambda: pipeline.avatar_frame(eng, fdev, scene['pose_map'], res, flag, vpts, fill, 0.0, impl), reps=2)
-        frame_ms = {'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
+        # vertex colours ("next" row 2, main.py:464-478): 64 field samples per vertex along -normal, composited front to back
+        from avatarcap_b200 import api
+        nvc = min(262144, int(mv.shape[0]))
+        wvol = torch.from_numpy(synth.blend_weight_volume(frame)).to(dev)
+        rend = api.NerfRenderer.for_engine(eng, torch.from_numpy(scene['pose_map'])[None].to(dev), sw, cv, wvol)
+        cb = {'cano_smpl_center': torch.from_numpy(center)[None].to(dev), 'cano_bounds': torch.from_numpy(frame['cano_bounds'])[None].to(dev)}
+        t_col, _ = timed(lambda: api.vertex_colors(rend, cb, mv[:nvc], mn[:nvc]), reps=2)
+        frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
 
     # ---- end to end through the host-buffer C-ABI entry: H2D of the points and D2H of every output inside the timed region

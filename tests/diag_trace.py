@@ -17,15 +17,16 @@ from avatarcap_b200.engine import Engine  # noqa: E402
 def main():
     tex = bool(int(sys.argv[1])) if len(sys.argv) > 1 else True
     flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    impl = sys.argv[3] if len(sys.argv) > 3 else 'tc'
     eng = Engine()
     s = tpose_scene(256)
     eng.load_avatar(s['avatar_sd']); eng.set_pose_feature_map(s['pose_map'])
     fr = s['frame']
     pts = eng.make_grid(fr['cano_bounds'], (128, 128, 128))
     buf = torch.zeros(4 * 24 * 8, dtype=torch.int64, device=eng.device)
-    eng.eval_occupancy(pts, fr['cano_smpl_center'], want_texture=tex, impl='tc'); torch.cuda.synchronize()    # warm
+    eng.eval_occupancy(pts, fr['cano_smpl_center'], want_texture=tex, impl=impl); torch.cuda.synchronize()    # warm
     eng.lib.avc_debug_set_trace(eng._h, C.c_void_p(buf.data_ptr()), flags)
-    eng.eval_occupancy(pts, fr['cano_smpl_center'], want_texture=tex, impl='tc'); torch.cuda.synchronize()
+    eng.eval_occupancy(pts, fr['cano_smpl_center'], want_texture=tex, impl=impl); torch.cuda.synchronize()
     eng.lib.avc_debug_set_trace(eng._h, None, 0)
     t = buf.cpu().numpy().reshape(4, 24, 8)
     n_ops = 20 if tex else 17
