@@ -152,14 +152,20 @@ extern "C" int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw, in
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-static int pick_impl(avc_ctx* ctx, int impl, bool* use_tc) {
+// AUTO resolves to the paired-CTA tcgen05 kernel (TC2) when the tensor-core path exists, else to the fp32 SIMT kernels; *impl is
+// rewritten to the concrete choice.
+static int pick_impl(avc_ctx* ctx, int* impl_io, bool* use_tc) {
+  int impl = *impl_io;
   if (impl == AVC_IMPL_SIMT) { *use_tc = false; return AVC_OK; }
-  if (impl == AVC_IMPL_TC2) impl = AVC_IMPL_TC;
-  if (impl == AVC_IMPL_TC) {
+  if (impl == AVC_IMPL_AUTO) {
+    *use_tc = avc_tc_available(ctx) != 0;
+    *impl_io = *use_tc ? (ctx->sm_count >= 2 ? AVC_IMPL_TC2 : AVC_IMPL_TC) : AVC_IMPL_SIMT;
+    return AVC_OK;
+  }
+  if (impl == AVC_IMPL_TC || impl == AVC_IMPL_TC2) {
     if (!avc_tc_available(ctx)) return avc_fail(ctx, AVC_ESTATE, "tensor-core path requested but not available (needs sm_100 and a library built with tcgen05)");
     *use_tc = true; return AVC_OK;
   }
-  if (impl == AVC_IMPL_AUTO) { *use_tc = avc_tc_available(ctx) != 0; return AVC_OK; }
   return avc_fail(ctx, AVC_EINVAL, "bad impl %d", impl);
 }
 
@@ -171,7 +177,7 @@ static int eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float ce
   if (!ctx->avatar.loaded) return avc_fail(ctx, AVC_ESTATE, "avatar weights not loaded");
   if (mode != AVC_MODE_TEMPLATE_ONLY && (!ctx->maps[AVC_MAP_POSE].d_hwc || !center))
     return avc_fail(ctx, AVC_ESTATE, "pose feature map not set (call avc_set_feature_map after WarpingField.precompute_conv)");
-  bool use_tc; int rc = pick_impl(ctx, impl, &use_tc);
+  bool use_tc; int rc = pick_impl(ctx, &impl, &use_tc);
   if (rc) return rc;
   const float zero[3] = {0, 0, 0};
   const float* c = center ? center : zero;
@@ -201,7 +207,7 @@ extern "C" int avc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const f
   if (n < 0 || (n > 0 && (!pts || !out_ov)) || !center) return avc_fail(ctx, AVC_EINVAL, "avc_eval_recon: bad argument");
   if (!ctx->recon.loaded) return avc_fail(ctx, AVC_ESTATE, "recon weights not loaded");
   if (!ctx->maps[AVC_MAP_IMAGE].d_hwc) return avc_fail(ctx, AVC_ESTATE, "image feature map not set");
-  bool use_tc; int rc = pick_impl(ctx, impl, &use_tc);
+  bool use_tc; int rc = pick_impl(ctx, &impl, &use_tc);
   if (rc) return rc;
   if (use_tc && impl == AVC_IMPL_TC2) return avc_tc2_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream);
   return use_tc ? avc_tc_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream)

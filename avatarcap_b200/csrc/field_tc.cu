@@ -217,6 +217,8 @@ __device__ __forceinline__ void skip_store8(unsigned char* skip, int r, int g, c
   *reinterpret_cast<uint4*>(base + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // One 32-column accumulator chunk: TMEM -> scale/bias/activation -> fp16 hi/lo -> TMEM, in place (A operand of the next layer).
 // sbc points at {scale,bias} pairs of the chunk's 32 channels.
 template <int ACT>
@@ -230,15 +232,19 @@ __device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __rest
     v[2 * i + 1] = fmaf(v[2 * i + 1], s4.z, s4.w);
   }
   if (ACT == AVC_ACT_SOFTPLUS) {
-    // softplus(v) = max(v,0) + ln2 * log2(1 + 2^(-|v| log2e)), in PHASES over the 32 values so that the 64 MUFU ops of a chunk are
-    // independent and back to back (the XU pipe, 16 lanes/clk/SM, is what bounds the OffsetDecoder layers' epilogue).
+    // softplus(v) = max(v,0) + log1p(t), t = 2^(-|v| log2e) in (0,1]. One MUFU per value (ex2.approx.ftz); log1p(t) is a degree-7
+    // near-minimax polynomial t*q(t) on the FMA pipe (max abs error 3.0e-7 in f32 Horner, the same order as lg2.approx): with
+    // ex2 + lg2 both on the XU pipe (16 lanes/clk/SM) the OffsetDecoder epilogues were XU-bound and slower than their MMAs.
     float t[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[i] = exp2f(-fabsf(v[i]) * 1.4426950408889634f);
+    for (int i = 0; i < 32; ++i) t[i] = ex2_ftz(-fabsf(v[i]) * 1.4426950408889634f);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[i] = __log2f(1.f + t[i]);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(t[i], 0.6931471805599453f, fmaxf(v[i], 0.f));
+    for (int i = 0; i < 32; ++i) {
+      float q = 1.076442841e-02f;
+      q = fmaf(q, t[i], -5.514492467e-02f); q = fmaf(q, t[i], 1.346741915e-01f); q = fmaf(q, t[i], -2.258978188e-01f);
+      q = fmaf(q, t[i], 3.282421529e-01f); q = fmaf(q, t[i], -4.994717836e-01f); q = fmaf(q, t[i], 9.999811649e-01f);
+      v[i] = fmaf(q, t[i], fmaxf(v[i], 0.f));
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = act_tc<ACT>(v[i]);

@@ -95,7 +95,7 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
   uint32_t done;
   long long t0 = 0;
   for (;;) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
     if (done) break;
     // watchdog: a protocol bug must abort the launch (sticky error reported through the C ABI) instead of hanging the GPU
@@ -104,6 +104,30 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
       printf("avatarcap_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, a, parity);
       __trap();
     }
+  }
+}
+// cluster-scope acquire wait: only where the PEER CTA's generic-proxy writes (its skip operand in shared memory) must be observed
+__device__ __forceinline__ void mbar_wait_cluster(void* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) break;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 6000000000LL) { printf("avatarcap_b200: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+// relaxed arrive on the leader's barrier: for hand-offs whose payload lives in TMEM / was moved by the async proxy (the tcgen05 fences and
+// the async-proxy completion order it); a release at cluster scope on every chunk costs an L1 invalidation each time
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(void* bar, uint32_t rank) {
+  if (rank == 0) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  } else {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0u));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
   }
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -236,6 +260,8 @@ __device__ __forceinline__ void skip_store8(unsigned char* skip, int r, int g, c
   *reinterpret_cast<uint4*>(base + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // One 32-column accumulator chunk: TMEM -> scale/bias/activation -> fp16 hi/lo -> TMEM, in place (A operand of the next layer).
 // sbc points at {scale,bias} pairs of the chunk's 32 channels.
 template <int ACT>
@@ -249,15 +275,19 @@ __device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __rest
     v[2 * i + 1] = fmaf(v[2 * i + 1], s4.z, s4.w);
   }
   if (ACT == AVC_ACT_SOFTPLUS) {
-    // softplus(v) = max(v,0) + ln2 * log2(1 + 2^(-|v| log2e)), in PHASES over the 32 values so that the 64 MUFU ops of a chunk are
-    // independent and back to back (the XU pipe, 16 lanes/clk/SM, is what bounds the OffsetDecoder layers' epilogue).
+    // softplus(v) = max(v,0) + log1p(t), t = 2^(-|v| log2e) in (0,1]. One MUFU per value (ex2.approx.ftz); log1p(t) is a degree-7
+    // near-minimax polynomial t*q(t) on the FMA pipe (max abs error 3.0e-7 in f32 Horner, the same order as lg2.approx): with
+    // ex2 + lg2 both on the XU pipe (16 lanes/clk/SM) the OffsetDecoder epilogues were XU-bound and slower than their MMAs.
     float t[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[i] = exp2f(-fabsf(v[i]) * 1.4426950408889634f);
+    for (int i = 0; i < 32; ++i) t[i] = ex2_ftz(-fabsf(v[i]) * 1.4426950408889634f);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[i] = __log2f(1.f + t[i]);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaf(t[i], 0.6931471805599453f, fmaxf(v[i], 0.f));
+    for (int i = 0; i < 32; ++i) {
+      float q = 1.076442841e-02f;
+      q = fmaf(q, t[i], -5.514492467e-02f); q = fmaf(q, t[i], 1.346741915e-01f); q = fmaf(q, t[i], -2.258978188e-01f);
+      q = fmaf(q, t[i], 3.282421529e-01f); q = fmaf(q, t[i], -4.994717836e-01f); q = fmaf(q, t[i], 9.999811649e-01f);
+      v[i] = fmaf(q, t[i], fmaxf(v[i], 0.f));
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = act_tc<ACT>(v[i]);
@@ -457,7 +487,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
               const int ks = seg == 0 ? o.ks_smem : o.ks_tmem;
               for (int j = 0; j < ks; j += STAGE_KSTEPS) {
                 mbar_wait(&S.full[stage], phase);
-                if (lane == 0) mbar_arrive_leader(&S.peer_full[stage], rank);
+                if (lane == 0) mbar_arrive_leader_relaxed(&S.peer_full[stage], rank);
                 __syncwarp();
                 if (++stage == N_STAGES) { stage = 0; phase ^= 1; }
               }
@@ -497,7 +527,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
             for (int j = 0; j < o.ks_smem; j += STAGE_KSTEPS, ++g) {
               const int cnt = min(STAGE_KSTEPS, o.ks_smem - j);
               if ((int)(g & 1) == me) {
-                if (need_epi) { mbar_wait(&S.epi_done, ph_epi); }
+                if (need_epi) { mbar_wait_cluster(&S.epi_done, ph_epi); }
                 mbar_wait(&S.full[stage], phase); mbar_wait(&S.peer_full[stage], phase);
                 tc_fence_after();
                 if (me == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
@@ -532,7 +562,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
                   const uint32_t b_addr = b0 + u * 2 * part_bytes;
                   bh[u] = desc_hi | (uint64_t)(b_addr >> 4); bl[u] = desc_hi | (uint64_t)((b_addr + part_bytes) >> 4);
                 }
-                if (need_epi) { mbar_wait(&S.epi_done, ph_epi); }
+                if (need_epi) { mbar_wait_cluster(&S.epi_done, ph_epi); }
                 if (wa) { mbar_wait(&S.a_ready[2 * c2], (ph_a >> (2 * c2)) & 1u); mbar_wait(&S.a_ready[2 * c2 + 1], (ph_a >> (2 * c2 + 1)) & 1u); }
                 mbar_wait(&S.full[stage], phase); mbar_wait(&S.peer_full[stage], phase);
                 tc_fence_after();
@@ -661,7 +691,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
               default: hidden_chunk<AVC_ACT_NONE>(taddr, sbc); break;
             }
             tc_fence_before(); __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&S.a_ready[c], rank);
+            if (lane == 0) mbar_arrive_leader_relaxed(&S.a_ready[c], rank);
           }
           if (tid == 0) trace_ev(a.trace, tl, oi, 6);
         } else {

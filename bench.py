@@ -187,7 +187,7 @@ def run_ours(args):
     eng = Engine(dev)
     impl = args.kernel
     if impl == 'auto':
-        impl = 'tc' if eng.has_tensor_core_path else 'simt'
+        impl = 'tc2' if eng.has_tensor_core_path else 'simt'   # what AVC_IMPL_AUTO resolves to (api.cu pick_impl)
     scene = build_scene()
     frame = scene['frame']
     eng.load_avatar(scene['avatar_sd']); eng.set_pose_feature_map(scene['pose_map'])
@@ -239,20 +239,23 @@ def run_ours(args):
         vol = shard.exchange_halo(occ, rank, world, res[0]) if world > 1 else occ
         return eng.extract_mesh(vol, frame['cano_bounds'], 0.0, True, lo, hi, x0 - lo, res[0])
 
-    mesh_step(); barrier()
-    m0 = torch.cuda.Event(enable_timing=True); m1 = torch.cuda.Event(enable_timing=True)
-    m0.record()
-    reps = 3
-    for _ in range(reps):
-        v, f, nrm = mesh_step()
-    m1.record(); barrier()
-    mesh_ms = m0.elapsed_time(m1) / reps
-    s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+    def median_ms(fn, reps):
+        """Per-repetition CUDA-event times, median (one allocator / driver hiccup must not masquerade as kernel time); returns (ms, last result)."""
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+            a0.record(); out = fn(); a1.record(); torch.cuda.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        return float(np.median(ts)), out
+
+    barrier()
+    mesh_ms, (v, f, nrm) = median_ms(mesh_step, 5)
+    barrier()
     cv = torch.from_numpy(frame['cano_smpl_v']).to(dev); sw = torch.from_numpy(frame['smpl_skinning_weights']).to(dev)
     jm = torch.from_numpy(frame['cano2live_jnt_mats']).to(dev)
     eng.skin_mesh(v, nrm, cv, sw, jm); torch.cuda.synchronize()
-    s0.record(); eng.skin_mesh(v, nrm, cv, sw, jm); s1.record(); torch.cuda.synchronize()
-    lbs_ms = s0.elapsed_time(s1)
+    lbs_ms, _ = median_ms(lambda: eng.skin_mesh(v, nrm, cv, sw, jm), 3)
     mt = torch.tensor([mesh_ms, lbs_ms], device=dev, dtype=torch.float64)
     nv = torch.tensor([v.shape[0], f.shape[0]], device=dev, dtype=torch.int64)
     if world > 1:
@@ -269,27 +272,21 @@ def run_ours(args):
         fdev = {'cano_smpl_v': cv, 'smpl_skinning_weights': sw, 'cano2live_jnt_mats': jm, 'cano_bounds': frame['cano_bounds'],
                 'cano_smpl_center': center}
 
-        def timed(fn, reps=3):
-            fn(); torch.cuda.synchronize()
-            a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for _ in range(reps):
-                out = fn()
-            a1.record(); torch.cuda.synchronize()
-            return a0.elapsed_time(a1) / reps, out
+        def timed(fn, reps=5):
+            return median_ms(fn, reps)
         t_field, o = timed(lambda: eng.eval_occupancy(vpts, center, want_offsets=True, impl=impl))
         t_scat, vol_m = timed(lambda: eng.scatter_fill(flag, o['occ'], fill))
         vol_m = vol_m.reshape(res)
         t_mesh, (mv, mf, mn) = timed(lambda: eng.extract_mesh(vol_m, frame['cano_bounds'], 0.0))
         t_lbs, _ = timed(lambda: eng.skin_mesh(mv, mn, cv, sw, jm))
-        t_all, _ = timed(lambda: pipeline.avatar_frame(eng, fdev, scene['pose_map'], res, flag, vpts, fill, 0.0, impl), reps=2)
+        t_all, _ = timed(lambda: pipeline.avatar_frame(eng, fdev, scene['pose_map'], res, flag, vpts, fill, 0.0, impl), reps=3)
         # vertex colours ("next" row 2, main.py:464-478): 64 field samples per vertex along -normal, composited front to back
         from avatarcap_b200 import api
         nvc = min(262144, int(mv.shape[0]))
         wvol = torch.from_numpy(synth.blend_weight_volume(frame)).to(dev)
         rend = api.NerfRenderer.for_engine(eng, torch.from_numpy(scene['pose_map'])[None].to(dev), sw, cv, wvol)
         cb = {'cano_smpl_center': torch.from_numpy(center)[None].to(dev), 'cano_bounds': torch.from_numpy(frame['cano_bounds'])[None].to(dev)}
-        t_col, _ = timed(lambda: api.vertex_colors(rend, cb, mv[:nvc], mn[:nvc]), reps=2)
+        t_col, _ = timed(lambda: api.vertex_colors(rend, cb, mv[:nvc], mn[:nvc]), reps=3)
         frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
 
@@ -326,7 +323,7 @@ def run_ours(args):
             'metric': 'Mpoints/s implicit-field eval @256^3 per GPU (occupancy+texture)', 'value': value, 'unit': 'Mpoints/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16x2 split operands (hi/lo, 3 MMA passes), f32 accumulate' if impl == 'tc' else 'f32',
+            'dtype': 'f16x2 split operands (hi/lo, 3 MMA passes), f32 accumulate' if impl in ('tc', 'tc2') else 'f32',
             'data': 'synthetic',
             'config': {'workload': 'OccupancyNet.query + texture head (warp MLP, template MLP, geo + colour heads) over a dense '
                                    '%dx%dx%d canonical grid, x-slabs over %d GPU(s); BASELINE config[1] per GPU' % (res + (world,)),

@@ -12,7 +12,7 @@ from avatarcap_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = ['simt', 'tc']
+IMPLS = ['simt', 'tc', 'tc2']
 
 
 @pytest.fixture(scope='module')
@@ -31,7 +31,7 @@ def scene(eng):
 
 
 def _impl_ok(eng, impl):
-    if impl == 'tc' and not eng.has_tensor_core_path:
+    if impl in ('tc', 'tc2') and not eng.has_tensor_core_path:
         pytest.fail('tensor-core path not available on this build/device: the product path must exist on the B200')
 
 
