@@ -4,6 +4,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include <cstdlib>
 
 static std::string g_create_error;
 
@@ -240,7 +241,11 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
   if (n < 0 || (n > 0 && (!pts || !out_a)) || !center) return avc_fail(ctx, AVC_EINVAL, "host eval: bad argument");
   if (n == 0) return AVC_OK;
   AVC_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int64_t chunk = 1 << 21;                       // 2 Mi points per pipeline slot (24 MB in, 8..32 MB out)
+  int64_t chunk = 1 << 21;                             // 2 Mi points per pipeline slot (24 MB in, 8..32 MB out)
+  if (const char* e = getenv("AVC_HOST_CHUNK")) {      // tuning knob: points per pipeline slot
+    const long long v = atoll(e);
+    if (v >= 1024 && v <= (1ll << 26)) chunk = v;
+  }
   const size_t slot_floats = (size_t)chunk * 11;
   int rc = ensure_staging(ctx, 2 * slot_floats * sizeof(float));
   if (rc) return rc;

@@ -66,3 +66,26 @@ def recon_frame(engine: Engine, frame: Dict, img_feat_map, vol_res, flag: Option
     v, f, n = engine.extract_mesh(vol, bounds, iso)
     lv, ln = _mesh_to_live(engine, v, n, frame)
     return {'volume': vol, 'verts': v, 'faces': f, 'normals': n, 'live_verts': lv, 'live_normals': ln}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Frame-parallel replicas (BASELINE config[5], SURVEY.md section 8e "Frame-parallel"): frame f runs on rank f mod world,
+# no communication on the data path; only the per-frame results are gathered by the caller if it wants them.
+def frames_for_rank(n_frames: int, world: int, rank: int):
+    """Indices of the frames rank `rank` of `world` processes (round robin, like a DataLoader with a DistributedSampler
+    without shuffling)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError('bad rank %d of world %d' % (rank, world))
+    return list(range(rank, int(n_frames), world))
+
+
+def run_frames(engine: Engine, frames, pose_feat_maps, vol_res, impl: Optional[str] = None, iso: float = 0.0):
+    """Dense canonical-avatar frames, one after the other on this rank's GPU: per frame the feature map is (re)bound, the
+    field evaluated over the whole grid, the mesh extracted and skinned to that frame's live pose. Returns the per-frame
+    vertex / face counts (the meshes themselves are dropped frame by frame to bound memory)."""
+    counts = []
+    for fr, fmap in zip(frames, pose_feat_maps):
+        out = avatar_frame(engine, fr, fmap, vol_res, iso=iso, impl=impl)
+        counts.append((int(out['verts'].shape[0]), int(out['faces'].shape[0])))
+        del out
+    return counts

@@ -290,6 +290,33 @@ def run_ours(args):
         frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
 
+    # ---- frame-parallel replicas (BASELINE config[5]: 16 frames x 256^3 on 8 GPUs = 2 frames per GPU): frame f -> rank f mod world,
+    # dense field + marching cubes + skinning per frame, each frame with its own live pose and feature map; encoders excluded
+    # (the feature maps are inputs). No collective on the data path.
+    frames_out = None
+    if args.frames_per_gpu > 0:
+        from avatarcap_b200 import pipeline, synth
+        n_frames = args.frames_per_gpu * world
+        mine = pipeline.frames_for_rank(n_frames, world, rank)
+        fr_list, fm_list = [], []
+        for fi in mine:
+            fr = synth.make_frame(scene['body'], synth.random_pose(synth.SEED + 100 + fi))
+            fr_list.append({'cano_smpl_v': torch.from_numpy(fr['cano_smpl_v']).to(dev), 'smpl_skinning_weights': torch.from_numpy(fr['smpl_skinning_weights']).to(dev),
+                            'cano2live_jnt_mats': torch.from_numpy(fr['cano2live_jnt_mats']).to(dev), 'cano_bounds': fr['cano_bounds'],
+                            'cano_smpl_center': fr['cano_smpl_center']})
+            fm_list.append(torch.from_numpy(synth.feature_map(64, 256, 256, synth.SEED + 200 + fi)).to(dev))
+        fres = (256, 256, 256) if args.res is None else (args.res,) * 3
+        pipeline.run_frames(eng, fr_list[:1], fm_list[:1], fres, impl=impl)               # warm-up
+        barrier()
+        f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+        f0.record(); counts = pipeline.run_frames(eng, fr_list, fm_list, fres, impl=impl); f1.record(); barrier()
+        ft = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        frames_out = {'frames': n_frames, 'frames_per_gpu': args.frames_per_gpu, 'grid': list(fres), 'ms_total': float(ft[0]),
+                      'frames_per_s': n_frames / (float(ft[0]) * 1e-3), 'stages': 'field (occupancy+offsets) + marching cubes + normals + LBS; encoders excluded',
+                      'rank0_vertices': [c[0] for c in counts]}
+
     # ---- end to end through the host-buffer C-ABI entry: H2D of the points and D2H of every output inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -339,6 +366,8 @@ def run_ours(args):
             line['e2e'] = e2e
         if frame_ms:
             line['frame'] = frame_ms
+        if frames_out:
+            line['frames'] = frames_out
         if args.gpus == 1 and not args.no_cpu:
             threads = host_cores()
             sub = strided_sample(scene, res, 64 ** 3)
@@ -362,6 +391,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-frame', action='store_true')
+    ap.add_argument('--frames-per-gpu', type=int, default=2, help='frame-parallel replicas (BASELINE config[5]); 0 disables')
     args = ap.parse_args()
     if args.gpus not in GRIDS:
         raise SystemExit('--gpus must be one of 1, 2, 4, 8')

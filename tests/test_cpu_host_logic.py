@@ -188,3 +188,16 @@ def test_halo_exchange_gloo_world2(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_frames_round_robin_partition():
+    """config[5] frame-parallel replicas: every frame on exactly one rank, loads differ by at most one frame."""
+    from avatarcap_b200 import pipeline
+    for n_frames, world in ((16, 8), (16, 3), (5, 8), (0, 2), (7, 1)):
+        parts = [pipeline.frames_for_rank(n_frames, world, r) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(n_frames))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+        assert all(f % world == r for r, p in enumerate(parts) for f in p)
+    import pytest
+    with pytest.raises(ValueError):
+        pipeline.frames_for_rank(4, 2, 2)
