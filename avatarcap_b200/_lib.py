@@ -31,6 +31,7 @@ SIGNATURES = {
     'avc_load_avatar_weights': (_i, [_vp, _vp, C.c_size_t]),
     'avc_load_recon_weights': (_i, [_vp, _vp, C.c_size_t]),
     'avc_set_feature_map': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    'avc_set_feature_map_hwc': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     'avc_eval_occupancy': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'avc_eval_warp': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _i, _vp]),
     'avc_eval_template': (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp]),

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include <cstdlib>
+#include <cstdio>
 
 static std::string g_create_error;
 
@@ -28,7 +29,7 @@ int avc_ensure_scratch(avc_ctx* ctx, size_t bytes) {
   return AVC_OK;
 }
 
-extern "C" int avc_abi_version(void) { return 2; }
+extern "C" int avc_abi_version(void) { return 3; }
 
 extern "C" int avc_ctx_create(int device, avc_ctx** out) {
   if (!out) return avc_fail(nullptr, AVC_EINVAL, "avc_ctx_create: out is NULL");
@@ -132,8 +133,8 @@ __global__ void chw_to_hwc_kernel(const float* __restrict__ in, float* __restric
   }
 }
 
-extern "C" int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw, int C, int H, int W, void* stream) {
-  if (!ctx || !chw) return avc_fail(ctx, AVC_EINVAL, "avc_set_feature_map: NULL argument");
+static int set_feature_map(avc_ctx* ctx, int which, const float* src, int C, int H, int W, bool hwc, cudaStream_t st) {
+  if (!ctx || !src) return avc_fail(ctx, AVC_EINVAL, "avc_set_feature_map: NULL argument");
   if (which != AVC_MAP_POSE && which != AVC_MAP_IMAGE) return avc_fail(ctx, AVC_EINVAL, "avc_set_feature_map: bad slot %d", which);
   const int want = which == AVC_MAP_POSE ? 64 : 32;
   if (C != want || H < 1 || W < 1) return avc_fail(ctx, AVC_EINVAL, "avc_set_feature_map: slot %d needs C=%d (got %d), H,W >= 1", which, want, C);
@@ -146,10 +147,21 @@ extern "C" int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw, in
     m.cap = need;
   }
   m.C = C; m.H = H; m.W = W;
+  if (hwc) {
+    AVC_CUDA(ctx, cudaMemcpyAsync(m.d_hwc, src, need, cudaMemcpyDeviceToDevice, st));
+    return AVC_OK;
+  }
   dim3 grid((H * W + 31) / 32, (C + 31) / 32), block(32, 8);
-  chw_to_hwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(chw, m.d_hwc, C, H * W);
+  chw_to_hwc_kernel<<<grid, block, 0, st>>>(src, m.d_hwc, C, H * W);
   AVC_LAUNCH_CHECK(ctx, "chw_to_hwc_kernel");
   return AVC_OK;
+}
+
+extern "C" int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw, int C, int H, int W, void* stream) {
+  return set_feature_map(ctx, which, chw, C, H, W, false, (cudaStream_t)stream);
+}
+extern "C" int avc_set_feature_map_hwc(avc_ctx* ctx, int which, const float* hwc, int C, int H, int W, void* stream) {
+  return set_feature_map(ctx, which, hwc, C, H, W, true, (cudaStream_t)stream);
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -256,6 +268,10 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
   for (int s = 0; s < 2; ++s) { cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming); }
   const int64_t n_chunks = (n + chunk - 1) / chunk;
   int status = AVC_OK;
+  // AVC_HOST_TRACE=1: per-chunk timeline (ms from the first H2D) of copy-in, kernel and copy-out, printed to stderr
+  const bool trace = getenv("AVC_HOST_TRACE") != nullptr && n_chunks <= 64;
+  cudaEvent_t tev[64][5];
+  if (trace) for (int64_t c = 0; c < n_chunks; ++c) for (int e = 0; e < 5; ++e) cudaEventCreate(&tev[c][e]);
   // software pipeline: iteration c stages chunk c (memcpy to pinned + H2D), launches its kernel, queues its D2H,
   // and retires chunk c-2's slot (copies its pinned outputs to the caller's buffers) before reusing it.
   for (int64_t c = 0; c < n_chunks + 2 && status == AVC_OK; ++c) {
@@ -273,9 +289,12 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
       float* hp = (float*)ctx->h_pinned + (size_t)s * slot_floats;
       float* dp = (float*)ctx->d_stage + (size_t)s * slot_floats;
       if (!pin_in) memcpy(hp, pts + b * 3, (size_t)m * 3 * sizeof(float));
+      if (trace) cudaEventRecord(tev[c][0], ctx->s_copy_in);
       cudaMemcpyAsync(dp, pin_in ? pts + b * 3 : hp, (size_t)m * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->s_copy_in);
       cudaEventRecord(ev_in[s], ctx->s_copy_in);
+      if (trace) cudaEventRecord(tev[c][1], ctx->s_copy_in);
       cudaStreamWaitEvent(ctx->s_compute, ev_in[s], 0);
+      if (trace) cudaEventRecord(tev[c][2], ctx->s_compute);
       float* d_occ = dp + (size_t)chunk * 3; float* d_off = dp + (size_t)chunk * 4;
       float* d_rgb = dp + (size_t)chunk * 7; float* d_alpha = dp + (size_t)chunk * 10;
       status = recon ? avc_eval_recon(ctx, dp, m, center, d_occ, impl, ctx->s_compute)
@@ -283,18 +302,30 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
                                           out_alpha ? d_alpha : nullptr, if_type, impl, ctx->s_compute);
       if (status != AVC_OK) break;
       cudaEventRecord(ev_k[s], ctx->s_compute);
+      if (trace) cudaEventRecord(tev[c][3], ctx->s_compute);
       cudaStreamWaitEvent(ctx->s_copy_out, ev_k[s], 0);
       cudaMemcpyAsync(pin_a ? out_a + b : hp + (size_t)chunk * 3, d_occ, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       if (out_off) cudaMemcpyAsync(pin_off ? out_off + b * 3 : hp + (size_t)chunk * 4, d_off, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       if (out_rgb) cudaMemcpyAsync(pin_rgb ? out_rgb + b * 3 : hp + (size_t)chunk * 7, d_rgb, (size_t)m * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       if (out_alpha) cudaMemcpyAsync(pin_al ? out_alpha + b : hp + (size_t)chunk * 10, d_alpha, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       cudaEventRecord(ev_out[s], ctx->s_copy_out);
+      if (trace) cudaEventRecord(tev[c][4], ctx->s_copy_out);
       // the next use of this slot's device buffer (chunk c+2) must wait for this D2H
       cudaStreamWaitEvent(ctx->s_copy_in, ev_out[s], 0);
     }
   }
   cudaStreamSynchronize(ctx->s_copy_in); cudaStreamSynchronize(ctx->s_compute); cudaStreamSynchronize(ctx->s_copy_out);
   for (int s = 0; s < 2; ++s) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_k[s]); cudaEventDestroy(ev_out[s]); }
+  if (trace) {
+    fprintf(stderr, "chunk | h2d start  h2d end | kernel start  kernel end | d2h end   (ms)\n");
+    for (int64_t c = 0; c < n_chunks; ++c) {
+      float t[5];
+      for (int e = 0; e < 5; ++e) { t[e] = 0.f; cudaEventElapsedTime(&t[e], tev[0][0], tev[c][e]); }
+      fprintf(stderr, "%5lld | %9.3f %8.3f | %12.3f %11.3f | %7.3f\n", (long long)c, t[0], t[1], t[2], t[3], t[4]);
+      for (int e = 0; e < 5; ++e) cudaEventDestroy(tev[c][e]);
+    }
+    cudaGetLastError();
+  }
   if (status == AVC_OK) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) status = avc_check_cuda(ctx, e, "host eval"); }
   return status;
 }

@@ -1,0 +1,187 @@
+"""Per-frame encoders feeding the per-point path ("next" row 1).
+
+    PoseFeatureEncoder   == WarpingField.unet = UnetNoCond7DS(6, 64, nf=32)     (unets.py:169-229, arch_avatar.py:95,109-111)
+    ImageFeatureEncoder  == ReconNetwork.image_encoder = HGFilter(1,4,6,32,'group','no_down',False)
+                                                                                  (HGFilters.py:124-219, arch_recon.py:28,41-43)
+
+Both are small conv nets that run ONCE per frame; the per-point kernels then gather from their output 16.8 M times. They stay on
+cuDNN (library convolutions), re-stated here functionally from the reference's state_dict so that
+
+  * eval-mode BatchNorm(affine=False) is folded into the conv weights at load time (one kernel less per layer),
+  * the whole forward is captured once into a CUDA graph and replayed per frame (about 60 / 200 tiny launches otherwise,
+    several of them on 2x2 .. 8x8 images where launch latency is everything),
+  * the network runs in channels_last, so the final feature map leaves the last conv already in the (H,W,C) layout the gather
+    kernels read (avc_set_feature_map_hwc: a straight device copy instead of a transpose).
+
+Reference quirks kept (parity is tested against the reference modules themselves, tests/golden/encoder_golden.npz):
+  * `Conv2DBlock.relu` is LeakyReLU(0.2, inplace=True) (unets.py:18-23): it rewrites the previous block's output in place, so
+    every skip connection d1..d6 carries the ACTIVATED tensor;
+  * `forward` applies `upconv3` twice and never `upconv4` (unets.py:214-215); the unused keys are accepted and ignored;
+  * `UpConv2DBlock(up_mode='upsample')` = bilinear x2 with align_corners=False, then a 3x3 conv WITH bias (unets.py:41-44);
+  * HourGlass up-sampling is bicubic with align_corners=True (HGFilters.py:115).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5   # nn.BatchNorm2d default
+
+
+def _t(sd, key, device):
+    v = sd[key]
+    t = torch.from_numpy(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v.detach()
+    return t.to(device=device, dtype=torch.float32)
+
+
+class _GraphedForward:
+    """Static-shape forward replayed from a CUDA graph (device tensors only). Falls back to eager on the CPU (tests)."""
+
+    def __init__(self, fn, device: torch.device, use_graph: bool):
+        self.fn = fn
+        self.device = device
+        self.use_graph = bool(use_graph) and device.type == 'cuda'
+        self._graph = None
+        self._in = None
+        self._out = None
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        x = x.to(device=self.device, dtype=torch.float32)
+        if not self.use_graph:
+            with torch.no_grad():
+                return self.fn(x)
+        if self._graph is None or self._in.shape != x.shape:
+            self._in = torch.empty_like(x, memory_format=torch.channels_last)
+            self._in.copy_(x)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):                       # warm-up outside the capture (cuDNN algorithm selection, workspace)
+                    self.fn(self._in)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g), torch.no_grad():
+                self._out = self.fn(self._in)
+            self._graph = g
+        self._in.copy_(x)
+        self._graph.replay()
+        return self._out                                  # owned by the graph: valid until the next call
+
+
+class PoseFeatureEncoder:
+    """pose_feat_map = unet(smpl_pos_map): (1,6,256,256) -> (1,64,256,256)   (WarpingField.precompute_conv, arch_avatar.py:109-111).
+
+    `state_dict` uses the reference's key names below `prefix` (e.g. 'warping_field.unet.' inside GeoTexAvatar.state_dict()).
+    The returned tensor is channels_last (memory order H,W,C) and, with graphs on, is overwritten by the next call."""
+
+    def __init__(self, state_dict: Dict, prefix: str = '', device='cuda', use_graph: bool = True, allow_tf32: bool = False):
+        self.device = torch.device(device)
+        self.allow_tf32 = allow_tf32
+        d = self.device
+        g = lambda k: _t(state_dict, prefix + k, d)       # noqa: E731
+
+        def folded(wkey, bnkey, bias=None, transpose=False):
+            """conv followed by BatchNorm(affine=False, eval): W' = W * s, b' = (b - mean) * s with s = 1/sqrt(var+eps), per OUT channel."""
+            w = g(wkey)
+            if bnkey is None:
+                return w.contiguous(memory_format=torch.channels_last), bias
+            s = torch.rsqrt(g(bnkey + '.running_var').double() + BN_EPS)
+            shape = (1, -1, 1, 1) if transpose else (-1, 1, 1, 1)
+            w = (w.double() * s.view(shape)).float()
+            b0 = bias.double() if bias is not None else torch.zeros_like(s)
+            b = ((b0 - g(bnkey + '.running_mean').double()) * s).float()
+            return w.contiguous(memory_format=torch.channels_last), b
+        self.down = [folded('conv%d.conv.weight' % i, 'conv%d.bn' % i if 2 <= i <= 6 else None) for i in range(1, 8)]
+        self.up = [folded('upconv%d.up.weight' % i, 'upconv%d.bn' % i, transpose=True) for i in (1, 2, 3)]
+        self.c5 = folded('upconvC5.up.1.weight', 'upconvC5.bn', g('upconvC5.up.1.bias'))
+        self.c6 = folded('upconvC6.up.1.weight', 'upconvC6.bn', g('upconvC6.up.1.bias'))
+        self.c7 = folded('upconvC7.up.1.weight', None, g('upconvC7.up.1.bias'))
+        self._run = _GraphedForward(self._forward, self.device, use_graph)
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=self.allow_tf32):
+            x = x.contiguous(memory_format=torch.channels_last)
+            a = []                                                   # activated skips a1..a6 (the in-place LeakyReLU quirk)
+            h = F.conv2d(x, self.down[0][0], None, stride=2, padding=1)
+            for w, b in self.down[1:]:
+                h = F.leaky_relu(h, 0.2)
+                a.append(h)
+                h = F.conv2d(h, w, b, stride=2, padding=1)
+            # h = d7 (2x2); shared decoder: upconv1, upconv2, upconv3, upconv3 AGAIN (unets.py:211-215)
+            for (w, b), skip in zip((self.up[0], self.up[1], self.up[2], self.up[2]), (a[5], a[4], a[3], a[2])):
+                h = torch.cat([F.conv_transpose2d(F.relu(h), w, b, stride=2, padding=1), skip], 1)
+            for (w, b), skip in ((self.c5, a[1]), (self.c6, a[0]), (self.c7, None)):
+                h = F.interpolate(F.relu(h), scale_factor=2, mode='bilinear', align_corners=False)
+                h = F.conv2d(h, w, b, stride=1, padding=1)
+                if skip is not None:
+                    h = torch.cat([h, skip], 1)
+            return h.contiguous(memory_format=torch.channels_last)
+
+    def __call__(self, smpl_pos_map) -> torch.Tensor:
+        x = torch.as_tensor(smpl_pos_map)
+        if x.dim() != 4 or x.shape[1] != 6 or x.shape[2] % 128 or x.shape[3] % 128:
+            raise ValueError('smpl_pos_map must be (B,6,H,W) with H,W multiples of 128 (7 stride-2 levels), got %s' % (tuple(x.shape),))
+        return self._run(x)
+
+
+class ImageFeatureEncoder:
+    """img_feat_map = HGFilter(cat([front_normal, back_normal], 1))[0][-1]: (1,6,512,512) -> (1,32,256,256)
+    (ReconNetwork.get_feat_maps, arch_recon.py:41-43,51-52). GroupNorm(32, C) everywhere (per-sample statistics: nothing to fold)."""
+
+    def __init__(self, state_dict: Dict, prefix: str = '', device='cuda', use_graph: bool = True, allow_tf32: bool = False):
+        self.device = torch.device(device)
+        self.allow_tf32 = allow_tf32
+        self.p = {}
+        for k in state_dict:
+            if k.startswith(prefix):
+                t = _t(state_dict, k, self.device)
+                self.p[k[len(prefix):]] = t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t
+        self._run = _GraphedForward(self._forward, self.device, use_graph)
+
+    def _gn(self, x, name):
+        return F.group_norm(x, 32, self.p[name + '.weight'], self.p[name + '.bias'], 1e-5)
+
+    def _block(self, x, name):
+        """ConvBlock.forward (HGFilters.py:61-75)."""
+        p = self.p
+        o1 = F.conv2d(F.relu(self._gn(x, name + '.bn1')), p[name + '.conv1.weight'], None, padding=1)
+        o2 = F.conv2d(F.relu(self._gn(o1, name + '.bn2')), p[name + '.conv2.weight'], None, padding=1)
+        o3 = F.conv2d(F.relu(self._gn(o2, name + '.bn3')), p[name + '.conv3.weight'], None, padding=1)
+        out = torch.cat([o1, o2, o3], 1)
+        if (name + '.downsample.2.weight') in p:
+            x = F.conv2d(F.relu(self._gn(x, name + '.bn4')), p[name + '.downsample.2.weight'], None)
+        return out + x
+
+    def _hourglass(self, level, x):
+        """HourGlass._forward (HGFilters.py:97-118)."""
+        up1 = self._block(x, 'm0.b1_%d' % level)
+        low = self._block(F.avg_pool2d(x, 2, stride=2), 'm0.b2_%d' % level)
+        low = self._hourglass(level - 1, low) if level > 1 else self._block(low, 'm0.b2_plus_%d' % level)
+        low = self._block(low, 'm0.b3_%d' % level)
+        return up1 + F.interpolate(low, scale_factor=2, mode='bicubic', align_corners=True)
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
+        p = self.p
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=self.allow_tf32):
+            x = x.contiguous(memory_format=torch.channels_last)
+            x = F.relu(self._gn(F.conv2d(x, p['conv1.weight'], p['conv1.bias'], stride=2, padding=3), 'bn1'))
+            x = self._block(x, 'conv2')                               # down_type == 'no_down'
+            x = self._block(self._block(x, 'conv3'), 'conv4')
+            ll = self._block(self._hourglass(4, x), 'top_m_0')
+            ll = F.relu(self._gn(F.conv2d(ll, p['conv_last0.weight'], p['conv_last0.bias']), 'bn_end0'))
+            out = F.conv2d(ll, p['l0.weight'], p['l0.bias'])           # use_sigmoid=False: no tanh
+            return out.contiguous(memory_format=torch.channels_last)
+
+    def __call__(self, normals) -> torch.Tensor:
+        x = torch.as_tensor(normals)
+        if x.dim() != 4 or x.shape[1] != 6 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError('normal maps must be (B,6,H,W) with H,W multiples of 32, got %s' % (tuple(x.shape),))
+        return self._run(x)
+
+
+def subsample_index(c: int, h: int, w: int, count: int, seed: int) -> np.ndarray:
+    """Seeded flat (h*w) pixel positions used by the golden fixtures (all channels are kept at each position)."""
+    return np.sort(np.random.RandomState(seed).choice(h * w, size=min(count, h * w), replace=False))

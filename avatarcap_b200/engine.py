@@ -92,6 +92,14 @@ class Engine:
         self._check(self.lib.avc_load_recon_weights(self._h, blob, len(blob)))
 
     def set_feature_map(self, which: int, fmap) -> None:
+        """(1,C,H,W) or (C,H,W). A channels_last (1,C,H,W) device tensor -- what encoders.py produces -- already has the
+        (H,W,C) memory order the gather kernels read and is handed over without the transpose."""
+        if (isinstance(fmap, torch.Tensor) and fmap.dim() == 4 and fmap.shape[0] == 1 and fmap.dtype == torch.float32
+                and fmap.device == self.device and fmap.shape[1] > 1 and not fmap.is_contiguous()
+                and fmap.is_contiguous(memory_format=torch.channels_last)):
+            _, Cc, H, W = fmap.shape
+            self._check(self.lib.avc_set_feature_map_hwc(self._h, which, _ptr(fmap), Cc, H, W, self._stream()))
+            return
         t = self._f32(fmap)
         if t.dim() == 4:
             if t.shape[0] != 1:

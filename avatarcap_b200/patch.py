@@ -14,6 +14,8 @@ through the same modules; with grad enabled every patched method falls through t
     network.arch_recon.ReconNetwork.infer       (arch_recon.py:45)
     utils.recon_util.recon_mesh                 (recon_util.py:51)
     utils.smpl_util.SmplUtil.calculate_lbs / skinning / skinning_normal   (smpl_util.py:24,58,76)
+    network.arch_avatar.WarpingField.precompute_conv   (arch_avatar.py:109)   -> encoders.PoseFeatureEncoder  (install(encoders=True))
+    network.arch_recon.ReconNetwork.get_feat_maps      (arch_recon.py:41)     -> encoders.ImageFeatureEncoder
 """
 from __future__ import annotations
 
@@ -22,7 +24,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import api
+from . import api, encoders as enc_mod
 from .engine import Engine, default_engine
 
 _originals: Dict[str, object] = {}
@@ -46,8 +48,18 @@ def _recon_loaded(net) -> None:
         _engine().load_recon(net.state_dict()); _state['recon_key'] = key
 
 
-def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules: Optional[Dict[str, object]] = None) -> None:
-    """Patch the reference modules in sys.path (or the ones passed in `modules`, keyed by dotted name)."""
+def _encoder(slot: str, module, cls):
+    """CUDA-graph encoder rebuilt when the PyTorch module's parameters change (same keying as the weight packers)."""
+    key = (id(module), sum(int(p._version) for p in module.parameters()))
+    if _state.get(slot + '_key') != key:
+        _state[slot] = cls(module.state_dict(), device=_engine().device); _state[slot + '_key'] = key
+    return _state[slot]
+
+
+def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules: Optional[Dict[str, object]] = None,
+            encoders: bool = True) -> None:
+    """Patch the reference modules in sys.path (or the ones passed in `modules`, keyed by dotted name). `encoders=False`
+    leaves the per-frame UNet / HGFilter on the reference's own nn.Modules."""
     if _originals:
         return
     _state['engine'] = engine
@@ -91,6 +103,22 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
         return api.geotex_forward(_engine(), wpts, dists, batch, self.warping_field.pose_feat_map, su.smpl_skinning_weights,
                                   su.cano_smpl_vertices, wv, pts_space, impl=impl)
     arch_avatar.GeoTexAvatar.forward = gforward
+
+    if encoders:
+        o_pc = keep(arch_avatar.WarpingField, 'precompute_conv')
+        def precompute_conv(self, batch):
+            if torch.is_grad_enabled() or not batch['smpl_pos_map'].is_cuda:
+                return o_pc(self, batch)
+            # clone: the graph owns its output buffer and the reference keeps pose_feat_map across calls (arch_avatar.py:111)
+            self.pose_feat_map = _encoder('unet', self.unet, enc_mod.PoseFeatureEncoder)(batch['smpl_pos_map']).clone(memory_format=torch.preserve_format)
+        arch_avatar.WarpingField.precompute_conv = precompute_conv
+
+        o_gfm = keep(arch_recon.ReconNetwork, 'get_feat_maps')
+        def get_feat_maps(self, image):
+            if torch.is_grad_enabled() or not image.is_cuda:
+                return o_gfm(self, image)
+            return [_encoder('hg', self.image_encoder, enc_mod.ImageFeatureEncoder)(image)]      # list like HGFilter's `outputs`
+        arch_recon.ReconNetwork.get_feat_maps = get_feat_maps
 
     o_inf = keep(arch_recon.ReconNetwork, 'infer')
     def infer(self, items):

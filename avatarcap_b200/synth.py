@@ -310,3 +310,98 @@ def volume_points(bounds: np.ndarray, res) -> np.ndarray:
     pts = np.stack([xv.reshape(-1), yv.reshape(-1), zv.reshape(-1)], -1).astype(np.float32)
     ln = (bounds[1] - bounds[0]).astype(np.float32)
     return (pts * ln + bounds[0].astype(np.float32)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------
+# per-frame encoders: seeded weights with the reference's key names
+# ----------------------------------------------------------------------------------------
+
+def _conv2d(rs, sd, prefix, cout, cin, k, bias=True, wshape=None, gain=1.0):
+    """He-style normal init (keeps activations O(1) through 15-25 conv layers); wshape overrides for ConvTranspose2d (in,out,k,k)."""
+    std = gain * math.sqrt(2.0 / (cin * k * k))
+    sd[prefix + '.weight'] = rs.normal(0, std, wshape or (cout, cin, k, k)).astype(np.float32)
+    if bias:
+        sd[prefix + '.bias'] = rs.uniform(-0.1, 0.1, (cout,)).astype(np.float32)
+
+
+def _bn_stats(rs, sd, prefix, c):
+    """BatchNorm2d(affine=False) buffers (unets.py:17,46): non-trivial running stats so that the folding is exercised."""
+    sd[prefix + '.running_mean'] = rs.uniform(-0.2, 0.2, c).astype(np.float32)
+    sd[prefix + '.running_var'] = rs.uniform(0.5, 1.5, c).astype(np.float32)
+    sd[prefix + '.num_batches_tracked'] = np.array(100, dtype=np.int64)
+
+
+def unet_state_dict(seed: int = SEED + 10, prefix: str = '') -> Dict[str, np.ndarray]:
+    """UnetNoCond7DS(input_nc=6, output_nc=64, nf=32, up_mode='upconv') keys (unets.py:169-199, arch_avatar.py:95), including the
+    never-executed `upconv4` (checkpoint compatibility; forward calls upconv3 twice, unets.py:214-215)."""
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, np.ndarray] = {}
+    nf = 32
+    down = [(6, nf), (nf, 2 * nf), (2 * nf, 4 * nf), (4 * nf, 8 * nf), (8 * nf, 8 * nf), (8 * nf, 8 * nf), (8 * nf, 8 * nf)]
+    for i, (cin, cout) in enumerate(down, 1):
+        _conv2d(rs, sd, prefix + 'conv%d.conv' % i, cout, cin, 4, bias=False)
+        if 2 <= i <= 6:
+            _bn_stats(rs, sd, prefix + 'conv%d.bn' % i, cout)
+    for i, (cin, cout) in enumerate([(8 * nf, 8 * nf), (16 * nf, 8 * nf), (16 * nf, 8 * nf), (16 * nf, 4 * nf)], 1):
+        # ConvTranspose2d weight is (in, out, k, k); stride 2 / kernel 4 -> every output sees cin*4 taps
+        _conv2d(rs, sd, prefix + 'upconv%d.up' % i, cout, cin, 2, bias=False, wshape=(cin, cout, 4, 4))
+        _bn_stats(rs, sd, prefix + 'upconv%d.bn' % i, cout)
+    for name, cin, cout, bn in (('C5', 12 * nf, 2 * nf, True), ('C6', 4 * nf, nf, True), ('C7', 2 * nf, 64, False)):
+        _conv2d(rs, sd, prefix + 'upconv%s.up.1' % name, cout, cin, 3, bias=True)
+        if bn:
+            _bn_stats(rs, sd, prefix + 'upconv%s.bn' % name, cout)
+    return sd
+
+
+def _gn(rs, sd, prefix, c):
+    sd[prefix + '.weight'] = rs.uniform(0.7, 1.3, c).astype(np.float32)
+    sd[prefix + '.bias'] = rs.uniform(-0.2, 0.2, c).astype(np.float32)
+
+
+def _convblock(rs, sd, prefix, cin, cout):
+    """HGFilters.ConvBlock with GroupNorm (HGFilters.py:33-75)."""
+    _conv2d(rs, sd, prefix + '.conv1', cout // 2, cin, 3, bias=False)
+    _conv2d(rs, sd, prefix + '.conv2', cout // 4, cout // 2, 3, bias=False)
+    _conv2d(rs, sd, prefix + '.conv3', cout // 4, cout // 4, 3, bias=False)
+    _gn(rs, sd, prefix + '.bn1', cin); _gn(rs, sd, prefix + '.bn2', cout // 2); _gn(rs, sd, prefix + '.bn3', cout // 4); _gn(rs, sd, prefix + '.bn4', cin)
+    if cin != cout:
+        # downsample = Sequential(bn4, ReLU, Conv1x1): bn4 is registered twice (as .bn4 and .downsample.0), same tensors
+        sd[prefix + '.downsample.0.weight'] = sd[prefix + '.bn4.weight']; sd[prefix + '.downsample.0.bias'] = sd[prefix + '.bn4.bias']
+        _conv2d(rs, sd, prefix + '.downsample.2', cout, cin, 1, bias=False, gain=0.7)
+
+
+def hgfilter_state_dict(seed: int = SEED + 11, prefix: str = '') -> Dict[str, np.ndarray]:
+    """HGFilter(stack=1, depth=4, in_ch=6, last_ch=32, norm='group', down_type='no_down', use_sigmoid=False) keys
+    (HGFilters.py:124-175, arch_recon.py:28)."""
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, np.ndarray] = {}
+    _conv2d(rs, sd, prefix + 'conv1', 64, 6, 7, bias=True)
+    _gn(rs, sd, prefix + 'bn1', 64)
+    _convblock(rs, sd, prefix + 'conv2', 64, 128)
+    _convblock(rs, sd, prefix + 'conv3', 128, 128)
+    _convblock(rs, sd, prefix + 'conv4', 128, 256)
+
+    def hourglass(level):
+        _convblock(rs, sd, prefix + 'm0.b1_%d' % level, 256, 256)
+        _convblock(rs, sd, prefix + 'm0.b2_%d' % level, 256, 256)
+        if level > 1:
+            hourglass(level - 1)
+        else:
+            _convblock(rs, sd, prefix + 'm0.b2_plus_%d' % level, 256, 256)
+        _convblock(rs, sd, prefix + 'm0.b3_%d' % level, 256, 256)
+    hourglass(4)
+    _convblock(rs, sd, prefix + 'top_m_0', 256, 256)
+    _conv2d(rs, sd, prefix + 'conv_last0', 256, 256, 1, bias=True)
+    _gn(rs, sd, prefix + 'bn_end0', 256)
+    _conv2d(rs, sd, prefix + 'l0', 32, 256, 1, bias=True, gain=0.5)
+    return sd
+
+
+def smpl_pos_map(seed: int = SEED + 12) -> np.ndarray:
+    """(1,6,256,256) f32 stand-in for the rendered SMPL position map (N(0, 0.3^2), seeded)."""
+    return np.random.RandomState(seed).normal(0, 0.3, (1, 6, 256, 256)).astype(np.float32)
+
+
+def normal_maps(seed: int = SEED + 13) -> np.ndarray:
+    """cat([front_normal, back_normal], 1): (1,6,512,512) f32 ~ U(0,1), seeded."""
+    return np.random.RandomState(seed).uniform(0, 1, (1, 6, 512, 512)).astype(np.float32)

@@ -287,8 +287,19 @@ def run_ours(args):
         rend = api.NerfRenderer.for_engine(eng, torch.from_numpy(scene['pose_map'])[None].to(dev), sw, cv, wvol)
         cb = {'cano_smpl_center': torch.from_numpy(center)[None].to(dev), 'cano_bounds': torch.from_numpy(frame['cano_bounds'])[None].to(dev)}
         t_col, _ = timed(lambda: api.vertex_colors(rend, cb, mv[:nvc], mn[:nvc]), reps=3)
+        # per-frame encoders ("next" row 1): CUDA-graph replay vs eager launches of the same functional forward (cuDNN, f32, no TF32)
+        from avatarcap_b200 import encoders
+        xin = torch.from_numpy(synth.smpl_pos_map()).to(dev); nin = torch.from_numpy(synth.normal_maps()).to(dev)
+        enc_ms = {}
+        for tag, graph in (('', True), ('_eager', False)):
+            pe = encoders.PoseFeatureEncoder(synth.unet_state_dict(), device=dev, use_graph=graph)
+            ie = encoders.ImageFeatureEncoder(synth.hgfilter_state_dict(), device=dev, use_graph=graph)
+            enc_ms['encoder_unet%s_ms' % tag], _ = timed(lambda: pe(xin))
+            enc_ms['encoder_hgfilter%s_ms' % tag], _ = timed(lambda: ie(nin))
+            del pe, ie
         frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
+        frame_ms.update(enc_ms)
 
     # ---- frame-parallel replicas (BASELINE config[5]: 16 frames x 256^3 on 8 GPUs = 2 frames per GPU): frame f -> rank f mod world,
     # dense field + marching cubes + skinning per frame, each frame with its own live pose and feature map; encoders excluded

@@ -83,6 +83,9 @@ int avc_load_recon_weights(avc_ctx* ctx, const void* blob /*[host]*/, size_t nby
  * ReconNetwork.get_feat_maps arch_recon.py:41-43). `chw` is a [dev] (C,H,W) float32 tensor; the library
  * transposes it into an owned (H,W,C) copy so that one bilinear tap is one contiguous read.            */
 int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw /*[dev]*/, int C, int H, int W, void* stream);
+/* same, for an encoder that already produced the (H,W,C) order (a channels_last torch tensor, avatarcap_b200/encoders.py):
+ * plain device copy into the owned buffer, no transpose.                                                          */
+int avc_set_feature_map_hwc(avc_ctx* ctx, int which, const float* hwc /*[dev]*/, int C, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* field evaluation                                                                               */

@@ -1,0 +1,83 @@
+"""Per-frame encoders against golden outputs of the REFERENCE modules
+(tests/golden/gen_encoder_golden.py: UnetNoCond7DS / HGFilter imported from the reference, CPU f32)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from helpers import load_golden  # noqa: E402
+from avatarcap_b200 import encoders, synth  # noqa: E402
+
+
+def _sampled(t, idx):
+    c = t.shape[1]
+    return t[0].reshape(c, -1)[:, torch.as_tensor(idx, device=t.device)].float().cpu().numpy()
+
+
+def _report(name, got, ref):
+    err = float(np.abs(got - ref).max()); rng = float(ref.max() - ref.min())
+    print('%s: max|d| = %.3e (range %.3g, relative %.2e)' % (name, err, rng, err / rng))
+    return err
+
+
+def test_state_dict_keys_cover_reference_names():
+    """The unused upconv4 keys exist (checkpoint compatibility) and both dicts carry the reference's module paths."""
+    u = synth.unet_state_dict(); h = synth.hgfilter_state_dict()
+    assert 'upconv4.up.weight' in u and u['upconv4.up.weight'].shape == (512, 128, 4, 4)
+    assert u['conv1.conv.weight'].shape == (32, 6, 4, 4) and u['upconvC7.up.1.bias'].shape == (64,)
+    assert 'conv2.bn.running_var' in u and 'conv1.bn.running_var' not in u and 'conv7.bn.running_var' not in u
+    assert h['conv1.weight'].shape == (64, 6, 7, 7) and h['l0.weight'].shape == (32, 256, 1, 1)
+    assert 'm0.b2_plus_1.conv1.weight' in h and 'conv2.downsample.2.weight' in h and 'conv3.downsample.2.weight' not in h
+
+
+def test_pose_encoder_cpu_vs_reference_golden():
+    g = load_golden('encoder_golden.npz')
+    enc = encoders.PoseFeatureEncoder(synth.unet_state_dict(), device='cpu', use_graph=False)
+    out = enc(synth.smpl_pos_map())
+    assert tuple(out.shape) == (1, 64, 256, 256) and out.is_contiguous(memory_format=torch.channels_last)
+    assert _report('unet cpu', _sampled(out, g['pose_idx']), g['pose_feat']) < 2e-5          # BN folded, f32
+    with pytest.raises(ValueError):
+        enc(np.zeros((1, 6, 100, 100), np.float32))
+
+
+def test_image_encoder_cpu_vs_reference_golden():
+    g = load_golden('encoder_golden.npz')
+    enc = encoders.ImageFeatureEncoder(synth.hgfilter_state_dict(), device='cpu', use_graph=False)
+    out = enc(synth.normal_maps())
+    assert tuple(out.shape) == (1, 32, 256, 256)
+    assert _report('hgfilter cpu', _sampled(out, g['img_idx']), g['img_feat']) < 1e-4
+
+
+def test_prefix_lookup():
+    sd = {'warping_field.unet.' + k: v for k, v in synth.unet_state_dict().items()}
+    enc = encoders.PoseFeatureEncoder(sd, prefix='warping_field.unet.', device='cpu', use_graph=False)
+    assert enc.c7[0].shape == (64, 64, 3, 3)
+
+
+@pytest.mark.gpu
+def test_encoders_gpu_graph_vs_golden_and_hwc_handoff():
+    from avatarcap_b200.engine import Engine
+    g = load_golden('encoder_golden.npz')
+    pe = encoders.PoseFeatureEncoder(synth.unet_state_dict(), device='cuda')
+    ie = encoders.ImageFeatureEncoder(synth.hgfilter_state_dict(), device='cuda')
+    x = torch.from_numpy(synth.smpl_pos_map()).cuda(); y = torch.from_numpy(synth.normal_maps()).cuda()
+    po = pe(x); assert _report('unet cuda graph', _sampled(po, g['pose_idx']), g['pose_feat']) < 1e-4
+    io = ie(y); assert _report('hgfilter cuda graph', _sampled(io, g['img_idx']), g['img_feat']) < 5e-4
+    # replay with another input, then the first again: the captured graph must follow its static input
+    first = po.clone()
+    other = pe(x * 0.5 + 0.1); assert float((other - first).abs().max()) > 1e-3
+    again = pe(x); assert torch.equal(again, first)
+    # the channels_last output goes to the library without a transpose and must evaluate identically to the (C,H,W) route
+    eng = Engine()
+    eng.load_avatar(synth.avatar_state_dict())
+    frame = synth.make_frame(synth.SynthBody(), None)
+    pts = eng.make_grid(frame['cano_bounds'], (48, 48, 48))
+    eng.set_pose_feature_map(first)                                            # channels_last -> avc_set_feature_map_hwc
+    a = eng.eval_occupancy(pts, frame['cano_smpl_center'])
+    eng.set_pose_feature_map(first.contiguous())                               # (C,H,W) -> transpose kernel
+    b = eng.eval_occupancy(pts, frame['cano_smpl_center'])
+    assert torch.equal(a['occ'], b['occ']) and torch.equal(a['off'], b['off'])
+    eng.close()

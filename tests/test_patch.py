@@ -1,0 +1,94 @@
+"""avatarcap_b200.patch: the drop-in re-binding of the reference's call sites, exercised against
+stand-in modules with the reference's class / attribute / key names (tests/fake_reference.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fake_reference as fr  # noqa: E402
+from avatarcap_b200 import synth  # noqa: E402
+
+
+@pytest.fixture()
+def frame():
+    return synth.make_frame(synth.SynthBody(), None)
+
+
+def test_install_rebinds_and_uninstall_restores(frame):
+    from avatarcap_b200 import patch
+    mods = fr.make_modules(frame)
+    aa = mods['network.arch_avatar']; ar = mods['network.arch_recon']
+    orig = {(c, n): getattr(c, n) for c, n in ((aa.OccupancyNet, 'query'), (aa.WarpingField, 'query'), (aa.WarpingField, 'precompute_conv'),
+                                              (aa.DoubleTNet, 'forward'), (aa.GeoTexAvatar, 'forward'), (ar.ReconNetwork, 'infer'),
+                                              (ar.ReconNetwork, 'get_feat_maps'), (mods['utils.smpl_util'].SmplUtil, 'skinning'))}
+    orig_rm = mods['utils.recon_util'].recon_mesh
+    patch.install(engine=object(), modules=mods)            # the engine is only touched by calls under no_grad
+    try:
+        assert all(getattr(c, n) is not f for (c, n), f in orig.items())
+        assert mods['utils.recon_util'].recon_mesh is not orig_rm
+        # with autograd enabled every patched method falls through to the reference's own code (training, main.py:97-116)
+        net = aa.GeoTexAvatar(frame)
+        with torch.enable_grad():
+            with pytest.raises(fr.Fallthrough):
+                aa.OccupancyNet(net).query({})
+            with pytest.raises(fr.Fallthrough):
+                net.warping_field.precompute_conv({'smpl_pos_map': torch.zeros(1, 6, 256, 256)})
+            with pytest.raises(fr.Fallthrough):
+                net(None, None, None, {}, 'cano')
+        # host tensors never reach the CUDA encoders
+        with torch.no_grad(), pytest.raises(fr.Fallthrough):
+            net.warping_field.precompute_conv({'smpl_pos_map': torch.zeros(1, 6, 256, 256)})
+    finally:
+        patch.uninstall()
+    assert all(getattr(c, n) is f for (c, n), f in orig.items()) and mods['utils.recon_util'].recon_mesh is orig_rm
+
+
+@pytest.mark.gpu
+def test_patched_call_sites_run_on_the_library(frame):
+    from avatarcap_b200 import patch
+    from avatarcap_b200.engine import Engine
+    dev = torch.device('cuda', 0)
+    eng = Engine(dev)
+    mods = fr.make_modules(frame, dev)
+    aa = mods['network.arch_avatar']; ar = mods['network.arch_recon']; su = mods['utils.smpl_util'].smpl_util
+    patch.install(engine=eng, modules=mods)
+    try:
+        net = aa.GeoTexAvatar(frame).to(dev); occ_net = aa.OccupancyNet(net)
+        pts = torch.from_numpy(synth.volume_points(frame['cano_bounds'], (40, 40, 24)))[None].to(dev)
+        batch = {'cano_pts': pts, 'smpl_pos_map': torch.from_numpy(synth.smpl_pos_map()).to(dev),
+                 'cano_smpl_center': torch.from_numpy(frame['cano_smpl_center'])[None].to(dev),
+                 'cano_bounds': torch.from_numpy(frame['cano_bounds'])[None].to(dev)}
+        with torch.no_grad():
+            net.warping_field.precompute_conv(batch)                                   # main.py:359
+            fmap = net.warping_field.pose_feat_map
+            assert tuple(fmap.shape) == (1, 64, 256, 256) and fmap.is_contiguous(memory_format=torch.channels_last)
+            out = occ_net.query(batch)                                                 # main.py:360
+            assert tuple(out['cano_pts_ov'].shape) == (1, pts.shape[1], 1) and tuple(out['nonrigid_offset'].shape) == (1, pts.shape[1], 3)
+            eng.set_pose_feature_map(fmap.contiguous())
+            ref = eng.eval_occupancy(pts[0], frame['cano_smpl_center'])
+            assert torch.equal(out['cano_pts_ov'][0, :, 0], ref['occ']) and torch.equal(out['nonrigid_offset'][0], ref['off'])
+            off = net.warping_field.query(pts, batch); assert torch.equal(off[0], ref['off'])
+            rgb, alpha, occ = net.cano_template(pts + off)
+            assert tuple(rgb.shape) == (1, pts.shape[1], 3) and float((occ[0, :, 0] - ref['occ']).abs().max()) < 1e-4
+            # reconstruction network: HGFilter through the graph encoder, decoder through the field kernel
+            rn = ar.ReconNetwork().to(dev)
+            nm = torch.from_numpy(synth.normal_maps()).to(dev)
+            items = {'cano_pts': pts, 'front_normal': nm[:, :3], 'back_normal': nm[:, 3:], 'cano_smpl_center': batch['cano_smpl_center']}
+            ov = rn.infer(items)
+            assert tuple(ov.shape) == (1, pts.shape[1]) and 0.0 <= float(ov.min()) and float(ov.max()) <= 1.0 and float(ov.std()) > 1e-3
+            # mesh + skinning call sites
+            vol = out['cano_pts_ov'].reshape(40, 40, 24)
+            v, f, n = mods['utils.recon_util'].recon_mesh(vol, (40, 40, 24), frame['cano_bounds'], 0.0)
+            assert isinstance(v, np.ndarray) and v.dtype == np.float32 and f.dtype == np.int32 and v.shape == n.shape and len(f) > 0
+            vt = torch.from_numpy(v)[None].to(dev)
+            lbs = su.calculate_lbs(vt); assert tuple(lbs.shape) == (1, len(v), 24)
+            jm = torch.from_numpy(frame['cano2live_jnt_mats'])[None].to(dev)
+            lv, mats = su.skinning(vt, lbs, jm, return_pt_mats=True)
+            ln = su.skinning_normal(torch.from_numpy(n)[None].to(dev), lbs, jm)
+            assert tuple(lv.shape) == (1, len(v), 3) and tuple(mats.shape) == (1, len(v), 4, 4) and tuple(ln.shape) == (1, len(v), 3)
+    finally:
+        patch.uninstall()
+        eng.close()
