@@ -310,8 +310,9 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
       if (out_alpha) cudaMemcpyAsync(pin_al ? out_alpha + b : hp + (size_t)chunk * 10, d_alpha, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, ctx->s_copy_out);
       cudaEventRecord(ev_out[s], ctx->s_copy_out);
       if (trace) cudaEventRecord(tev[c][4], ctx->s_copy_out);
-      // the next use of this slot's device buffer (chunk c+2) must wait for this D2H
-      cudaStreamWaitEvent(ctx->s_copy_in, ev_out[s], 0);
+      // The next use of this slot's buffers is chunk c+2; the host waits on ev_out[s] (retire, above) before it enqueues
+      // anything of that chunk, which orders it after this D2H. (A stream wait enqueued HERE on s_copy_in would also hold
+      // back chunk c+1's H2D -- it serialised the whole pipeline in the first version: see profiles/r1_host_entry_timeline.txt.)
     }
   }
   cudaStreamSynchronize(ctx->s_copy_in); cudaStreamSynchronize(ctx->s_compute); cudaStreamSynchronize(ctx->s_copy_out);
@@ -322,8 +323,8 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
       float t[5];
       for (int e = 0; e < 5; ++e) { t[e] = 0.f; cudaEventElapsedTime(&t[e], tev[0][0], tev[c][e]); }
       fprintf(stderr, "%5lld | %9.3f %8.3f | %12.3f %11.3f | %7.3f\n", (long long)c, t[0], t[1], t[2], t[3], t[4]);
-      for (int e = 0; e < 5; ++e) cudaEventDestroy(tev[c][e]);
     }
+    for (int64_t c = 0; c < n_chunks; ++c) for (int e = 0; e < 5; ++e) cudaEventDestroy(tev[c][e]);
     cudaGetLastError();
   }
   if (status == AVC_OK) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) status = avc_check_cuda(ctx, e, "host eval"); }

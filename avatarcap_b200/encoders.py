@@ -77,9 +77,13 @@ class PoseFeatureEncoder:
     `state_dict` uses the reference's key names below `prefix` (e.g. 'warping_field.unet.' inside GeoTexAvatar.state_dict()).
     The returned tensor is channels_last (memory order H,W,C) and, with graphs on, is overwritten by the next call."""
 
-    def __init__(self, state_dict: Dict, prefix: str = '', device='cuda', use_graph: bool = True, allow_tf32: bool = False):
+    def __init__(self, state_dict: Dict, prefix: str = '', device='cuda', use_graph: bool = True, allow_tf32: bool = False,
+                 deterministic: bool = True, channels_last: bool = True, benchmark: bool = False):
         self.device = torch.device(device)
         self.allow_tf32 = allow_tf32
+        self.deterministic = deterministic
+        self.benchmark = benchmark
+        self.mf = torch.channels_last if channels_last else torch.contiguous_format
         d = self.device
         g = lambda k: _t(state_dict, prefix + k, d)       # noqa: E731
 
@@ -87,13 +91,13 @@ class PoseFeatureEncoder:
             """conv followed by BatchNorm(affine=False, eval): W' = W * s, b' = (b - mean) * s with s = 1/sqrt(var+eps), per OUT channel."""
             w = g(wkey)
             if bnkey is None:
-                return w.contiguous(memory_format=torch.channels_last), bias
+                return w.contiguous(memory_format=self.mf), bias
             s = torch.rsqrt(g(bnkey + '.running_var').double() + BN_EPS)
             shape = (1, -1, 1, 1) if transpose else (-1, 1, 1, 1)
             w = (w.double() * s.view(shape)).float()
             b0 = bias.double() if bias is not None else torch.zeros_like(s)
             b = ((b0 - g(bnkey + '.running_mean').double()) * s).float()
-            return w.contiguous(memory_format=torch.channels_last), b
+            return w.contiguous(memory_format=self.mf), b
         self.down = [folded('conv%d.conv.weight' % i, 'conv%d.bn' % i if 2 <= i <= 6 else None) for i in range(1, 8)]
         self.up = [folded('upconv%d.up.weight' % i, 'upconv%d.bn' % i, transpose=True) for i in (1, 2, 3)]
         self.c5 = folded('upconvC5.up.1.weight', 'upconvC5.bn', g('upconvC5.up.1.bias'))
@@ -102,8 +106,8 @@ class PoseFeatureEncoder:
         self._run = _GraphedForward(self._forward, self.device, use_graph)
 
     def _forward(self, x: torch.Tensor) -> torch.Tensor:
-        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=self.allow_tf32):
-            x = x.contiguous(memory_format=torch.channels_last)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.benchmark, deterministic=self.deterministic, allow_tf32=self.allow_tf32):
+            x = x.contiguous(memory_format=self.mf)
             a = []                                                   # activated skips a1..a6 (the in-place LeakyReLU quirk)
             h = F.conv2d(x, self.down[0][0], None, stride=2, padding=1)
             for w, b in self.down[1:]:
@@ -131,14 +135,18 @@ class ImageFeatureEncoder:
     """img_feat_map = HGFilter(cat([front_normal, back_normal], 1))[0][-1]: (1,6,512,512) -> (1,32,256,256)
     (ReconNetwork.get_feat_maps, arch_recon.py:41-43,51-52). GroupNorm(32, C) everywhere (per-sample statistics: nothing to fold)."""
 
-    def __init__(self, state_dict: Dict, prefix: str = '', device='cuda', use_graph: bool = True, allow_tf32: bool = False):
+    def __init__(self, state_dict: Dict, prefix: str = '', device='cuda', use_graph: bool = True, allow_tf32: bool = False,
+                 deterministic: bool = True, channels_last: bool = True, benchmark: bool = False):
         self.device = torch.device(device)
         self.allow_tf32 = allow_tf32
+        self.deterministic = deterministic
+        self.benchmark = benchmark
+        self.mf = torch.channels_last if channels_last else torch.contiguous_format
         self.p = {}
         for k in state_dict:
             if k.startswith(prefix):
                 t = _t(state_dict, k, self.device)
-                self.p[k[len(prefix):]] = t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t
+                self.p[k[len(prefix):]] = t.contiguous(memory_format=self.mf) if t.dim() == 4 else t
         self._run = _GraphedForward(self._forward, self.device, use_graph)
 
     def _gn(self, x, name):
@@ -165,8 +173,8 @@ class ImageFeatureEncoder:
 
     def _forward(self, x: torch.Tensor) -> torch.Tensor:
         p = self.p
-        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=self.allow_tf32):
-            x = x.contiguous(memory_format=torch.channels_last)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.benchmark, deterministic=self.deterministic, allow_tf32=self.allow_tf32):
+            x = x.contiguous(memory_format=self.mf)
             x = F.relu(self._gn(F.conv2d(x, p['conv1.weight'], p['conv1.bias'], stride=2, padding=3), 'bn1'))
             x = self._block(x, 'conv2')                               # down_type == 'no_down'
             x = self._block(self._block(x, 'conv3'), 'conv4')

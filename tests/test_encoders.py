@@ -69,7 +69,7 @@ def test_encoders_gpu_graph_vs_golden_and_hwc_handoff():
     # replay with another input, then the first again: the captured graph must follow its static input
     first = po.clone()
     other = pe(x * 0.5 + 0.1); assert float((other - first).abs().max()) > 1e-3
-    again = pe(x); assert torch.equal(again, first)
+    again = pe(x); print('replay difference', float((again - first).abs().max())); assert torch.equal(again, first)       # deterministic cuDNN algorithms
     # the channels_last output goes to the library without a transpose and must evaluate identically to the (C,H,W) route
     eng = Engine()
     eng.load_avatar(synth.avatar_state_dict())
