@@ -61,7 +61,7 @@ def test_prefix_lookup():
 def test_encoders_gpu_graph_vs_golden_and_hwc_handoff():
     from avatarcap_b200.engine import Engine
     g = load_golden('encoder_golden.npz')
-    pe = encoders.PoseFeatureEncoder(synth.unet_state_dict(), device='cuda')
+    pe = encoders.PoseFeatureEncoder(synth.unet_state_dict(), device='cuda', deterministic=True)
     ie = encoders.ImageFeatureEncoder(synth.hgfilter_state_dict(), device='cuda')
     x = torch.from_numpy(synth.smpl_pos_map()).cuda(); y = torch.from_numpy(synth.normal_maps()).cuda()
     po = pe(x); assert _report('unet cuda graph', _sampled(po, g['pose_idx']), g['pose_feat']) < 1e-4
