@@ -199,6 +199,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 columns, NO wait: the caller overlaps the load with arithmetic on the previous piece and calls tmem_ld_wait() before use
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t r[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+}
+// wait for the outstanding tcgen05.ld's; `r` (the registers of the load being waited for) is threaded through the statement as an
+// in/out operand so that no use of those registers can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t r[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t r[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
   uint32_t r0, r1, r2, r3;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
@@ -260,6 +279,19 @@ __device__ __forceinline__ void skip_store8(unsigned char* skip, int r, int g, c
   *reinterpret_cast<uint4*>(base + 4096) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// TMEM-resident A operand: packed fp16 hi, and the NEGATED residual  nlo = hi - v  (one mixed-precision FHADD per value instead of
+// convert-back + subtract); the lo*hi pass of the TS-mode MMAs sets the descriptor's negate-A bit, so the product is unchanged.
+__device__ __forceinline__ void split2_neg(float v0, float v1, uint32_t& hi, uint32_t& nlo) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const unsigned short h0 = (unsigned short)(hi & 0xffffu), h1 = (unsigned short)(hi >> 16);
+  float r0, r1;
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r0) : "h"(h0), "f"(v0));
+  asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(r1) : "h"(h1), "f"(v1));
+  const __half2 l = __floats2half2_rn(r0, r1);
+  nlo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // One 32-column accumulator chunk: TMEM -> scale/bias/activation -> fp16 hi/lo -> TMEM, in place (A operand of the next layer).
@@ -275,18 +307,21 @@ __device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __rest
     v[2 * i + 1] = fmaf(v[2 * i + 1], s4.z, s4.w);
   }
   if (ACT == AVC_ACT_SOFTPLUS) {
-    // softplus(v) = max(v,0) + log1p(t), t = 2^(-|v| log2e) in (0,1]. One MUFU per value (ex2.approx.ftz); log1p(t) is a degree-7
-    // near-minimax polynomial t*q(t) on the FMA pipe (max abs error 3.0e-7 in f32 Horner, the same order as lg2.approx): with
-    // ex2 + lg2 both on the XU pipe (16 lanes/clk/SM) the OffsetDecoder epilogues were XU-bound and slower than their MMAs.
+    // softplus(v) = max(v,0) + log1p(t), t = 2^(-|v| log2e) in (0,1] (ex2.approx.ftz). log1p(t) alternates between the two pipes the
+    // epilogue is bound by: even values take ln2 * lg2.approx(1+t) (XU pipe, 3 instructions), odd values a degree-7 near-minimax
+    // polynomial t*q(t) (FMA pipe, 7 instructions, max abs error 3.0e-7 -- the same order as lg2.approx). All-XU was XU-bound
+    // (2 MUFU/value at 16 lanes/clk/SM), all-polynomial issue-bound.
     float t[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) t[i] = ex2_ftz(-fabsf(v[i]) * 1.4426950408889634f);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < 32; i += 2) {
+      const float l = lg2_ftz(1.f + t[i]);
       float q = 1.076442841e-02f;
-      q = fmaf(q, t[i], -5.514492467e-02f); q = fmaf(q, t[i], 1.346741915e-01f); q = fmaf(q, t[i], -2.258978188e-01f);
-      q = fmaf(q, t[i], 3.282421529e-01f); q = fmaf(q, t[i], -4.994717836e-01f); q = fmaf(q, t[i], 9.999811649e-01f);
-      v[i] = fmaf(q, t[i], fmaxf(v[i], 0.f));
+      q = fmaf(q, t[i + 1], -5.514492467e-02f); q = fmaf(q, t[i + 1], 1.346741915e-01f); q = fmaf(q, t[i + 1], -2.258978188e-01f);
+      q = fmaf(q, t[i + 1], 3.282421529e-01f); q = fmaf(q, t[i + 1], -4.994717836e-01f); q = fmaf(q, t[i + 1], 9.999811649e-01f);
+      v[i] = fmaf(l, 0.6931471805599453f, fmaxf(v[i], 0.f));
+      v[i + 1] = fmaf(q, t[i + 1], fmaxf(v[i + 1], 0.f));
     }
   } else {
 #pragma unroll
@@ -294,10 +329,71 @@ __device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __rest
   }
   uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+  for (int i = 0; i < 16; ++i) split2_neg(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
   tmem_st16(taddr, hi);            // k-steps 2c, 2c+1: hi in columns [0,16) of the chunk
-  tmem_st16(taddr + 16u, lo);      //                   lo in columns [16,32)
+  tmem_st16(taddr + 16u, lo);      //                   -lo in columns [16,32)
   tmem_st_wait();
+}
+
+// scale/bias/activation + hi / -lo split of ONE 16-column piece held in registers (raw accumulator bits in, packed words out)
+template <int ACT>
+__device__ __forceinline__ void hidden_piece(const uint32_t raw[16], const float* __restrict__ sbp, uint32_t hi[8], uint32_t nlo[8]) {
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 s4 = *reinterpret_cast<const float4*>(sbp + 4 * i);   // {scale0, bias0, scale1, bias1}
+    v[2 * i] = fmaf(__uint_as_float(raw[2 * i]), s4.x, s4.y);
+    v[2 * i + 1] = fmaf(__uint_as_float(raw[2 * i + 1]), s4.z, s4.w);
+  }
+  if (ACT == AVC_ACT_SOFTPLUS) {           // see hidden_chunk
+    float t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = ex2_ftz(-fabsf(v[i]) * 1.4426950408889634f);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const float l = lg2_ftz(1.f + t[i]);
+      float q = 1.076442841e-02f;
+      q = fmaf(q, t[i + 1], -5.514492467e-02f); q = fmaf(q, t[i + 1], 1.346741915e-01f); q = fmaf(q, t[i + 1], -2.258978188e-01f);
+      q = fmaf(q, t[i + 1], 3.282421529e-01f); q = fmaf(q, t[i + 1], -4.994717836e-01f); q = fmaf(q, t[i + 1], 9.999811649e-01f);
+      v[i] = fmaf(l, 0.6931471805599453f, fmaxf(v[i], 0.f));
+      v[i + 1] = fmaf(q, t[i + 1], fmaxf(v[i + 1], 0.f));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = act_tc<ACT>(v[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split2_neg(v[2 * i], v[2 * i + 1], hi[i], nlo[i]);
+}
+
+// Two 32-column chunks (c0, c1) of one accumulator half, software-pipelined in 16-column pieces: the TMEM load of piece p+1 is in
+// flight while piece p is computed, and the stores are only waited for once per chunk, right before its a_ready arrive. The
+// fixed tcgen05.ld / st / wait latencies (about 600 cycles per chunk when exposed) were half of a ReLU chunk's epilogue time.
+// In-place layout of a chunk: piece p (fp32 columns 16p..16p+15) -> hi words in columns 8p..8p+7, -lo words in 16+8p..16+8p+7;
+// piece 0's -lo lands on piece 1's fp32 columns, so piece 1 must be in registers (wait::ld) before piece 0 is stored.
+template <int ACT>
+__device__ __forceinline__ void hidden_pair(uint32_t t0, uint32_t t1, const float* __restrict__ sb0, const float* __restrict__ sb1,
+                                            void* bar0, void* bar1, uint32_t rank, int lane) {
+  uint32_t ra[16], rb[16], hi[8], nlo[8];
+  tmem_ld16_issue(t0, ra); tmem_ld_wait(ra);
+  tmem_ld16_issue(t0 + 16u, rb);
+  hidden_piece<ACT>(ra, sb0, hi, nlo);
+  tmem_ld_wait(rb);                                 // piece (c0,1) is in rb: its columns may now be overwritten
+  tmem_st8(t0, hi); tmem_st8(t0 + 16u, nlo);
+  tmem_ld16_issue(t1, ra);
+  hidden_piece<ACT>(rb, sb0 + 32, hi, nlo);
+  tmem_ld_wait(ra);
+  tmem_st8(t0 + 8u, hi); tmem_st8(t0 + 24u, nlo);
+  tmem_ld16_issue(t1 + 16u, rb);
+  hidden_piece<ACT>(ra, sb1, hi, nlo);              // chunk c0's stores drain meanwhile
+  tmem_st_wait(); tc_fence_before(); __syncwarp();
+  if (lane == 0) mbar_arrive_leader_relaxed(bar0, rank);
+  tmem_ld_wait(rb);
+  tmem_st8(t1, hi); tmem_st8(t1 + 16u, nlo);
+  hidden_piece<ACT>(rb, sb1 + 32, hi, nlo);
+  tmem_st8(t1 + 8u, hi); tmem_st8(t1 + 24u, nlo);
+  tmem_st_wait(); tc_fence_before(); __syncwarp();
+  if (lane == 0) mbar_arrive_leader_relaxed(bar1, rank);
 }
 
 struct Taps { int i00, i01, i10, i11; float w00, w01, w10, w11; };
@@ -574,7 +670,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
                     // hi*hi and hi*lo back to back with A(hi) held in the collector buffer (one TMEM operand fetch for two MMAs), then lo*hi
                     mma_ts_c(d_addr, a_hi, bh[u], idesc, acc, 1); acc = 1u;
                     mma_ts_c(d_addr, a_hi, bl[u], idesc, 1u, 2);
-                    mma_ts(d_addr, a_lo, bh[u], idesc, 1u);
+                    mma_ts(d_addr, a_lo, bh[u], idesc | (1u << 13), 1u);      // negate A: TMEM holds -lo (split2_neg)
                   }
                   tc_commit(&S.empty[stage]);
                 }
@@ -676,22 +772,20 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
         if (o.epi == EPI_HIDDEN) {
           const float* sb = s_sb + o.sb_off;
           const int n_chunks = o.n >> 5;
-          for (int c = grp; c < n_chunks; c += 2) {
+          for (int c = grp; c < n_chunks; c += 4) {                                                  // one accumulator half per iteration
             if (c == 4 + grp) {                                                                   // second N-half (only 256-wide ops get here)
               if (tid == 0) trace_ev(a.trace, tl, oi, 4);
               mbar_wait(&S.d_ready[1], ph_d1); ph_d1 ^= 1; tc_fence_after();
               if (tid == 0) trace_ev(a.trace, tl, oi, 5);
             }
-            const uint32_t taddr = t_lane + (uint32_t)(o.d_col + c * 32);
-            const float* sbc = sb + 64 * c;
-            switch (o.act) {                                 // one branch per chunk, none per value
-              case AVC_ACT_RELU: hidden_chunk<AVC_ACT_RELU>(taddr, sbc); break;
-              case AVC_ACT_LRELU: hidden_chunk<AVC_ACT_LRELU>(taddr, sbc); break;
-              case AVC_ACT_SOFTPLUS: hidden_chunk<AVC_ACT_SOFTPLUS>(taddr, sbc); break;
-              default: hidden_chunk<AVC_ACT_NONE>(taddr, sbc); break;
+            const uint32_t t0 = t_lane + (uint32_t)(o.d_col + c * 32), t1 = t0 + 64u;              // chunks c and c+2
+            const float* sb0 = sb + 64 * c; const float* sb1 = sb0 + 128;
+            switch (o.act) {                                 // one branch per half, none per value
+              case AVC_ACT_RELU: hidden_pair<AVC_ACT_RELU>(t0, t1, sb0, sb1, &S.a_ready[c], &S.a_ready[c + 2], rank, lane); break;
+              case AVC_ACT_LRELU: hidden_pair<AVC_ACT_LRELU>(t0, t1, sb0, sb1, &S.a_ready[c], &S.a_ready[c + 2], rank, lane); break;
+              case AVC_ACT_SOFTPLUS: hidden_pair<AVC_ACT_SOFTPLUS>(t0, t1, sb0, sb1, &S.a_ready[c], &S.a_ready[c + 2], rank, lane); break;
+              default: hidden_pair<AVC_ACT_NONE>(t0, t1, sb0, sb1, &S.a_ready[c], &S.a_ready[c + 2], rank, lane); break;
             }
-            tc_fence_before(); __syncwarp();
-            if (lane == 0) mbar_arrive_leader_relaxed(&S.a_ready[c], rank);
           }
           if (tid == 0) trace_ev(a.trace, tl, oi, 6);
         } else {

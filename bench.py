@@ -27,8 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_PT = {'occ': 1_773_568, 'occ+tex': 1_970_944, 'recon': 387_072}     # SURVEY.md section 8 / BASELINE.md section 2
-# dram__bytes_read.sum + dram__bytes_write.sum of field_tc_kernel at 256^3, one launch (profiles/r1_ncu_tc_v6_256cube.md)
-NCU_TRAFFIC_BYTES = 712_916_736
+# dram__bytes_read.sum + dram__bytes_write.sum of field_tc2_kernel at 256^3, one launch (profiles/r1_ncu_tc2_256cube.md: 229.7 + 487.8 MB)
+NCU_TRAFFIC_BYTES = 717_489_152
 GRIDS = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512, 512, 512)}
 
 
