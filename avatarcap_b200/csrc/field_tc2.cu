@@ -36,6 +36,7 @@ constexpr int STAGE_BYTES = STAGE_KSTEPS * 8192;   // per k-step of one N-half: 
 constexpr int SKIP_KSTEPS = 5;            // up to K=80 of skip input
 constexpr int SKIP_BYTES = SKIP_KSTEPS * 8192;   // per k-step: hi slab 4 KB + lo slab 4 KB (128 rows x 16 k x 2 B)
 constexpr int MAX_OPS = 24;
+constexpr int DOTW_F4_MAX = 520;          // head weights as float4 {w0,w1,w2,0} per input channel + one bias row per head (avatar: 257+129+129)
 constexpr int SB_FLOATS_MAX = 8704;       // scale/bias pairs of all layers (avatar: 4272 channels*2)
 
 enum { EPI_HIDDEN = 1, EPI_WARP_OUT = 2, EPI_GEO_OUT = 3, EPI_CLR_OUT = 4, EPI_RECON_OUT = 5 };
@@ -57,6 +58,10 @@ struct TcOp {
   int signal_done;    // compute warps arrive on epi_done after this op's epilogue
   unsigned int w_off; // byte offset of this op's weight stream in the f16 section
   int wait_a;         // the TMEM A chunks are produced by the preceding epilogue (0: already complete, e.g. the colour head re-reads s7)
+  int dot_w;          // >= 0: the op's activations feed a tiny (<= 3 output) linear head evaluated on the CUDA cores in this op's
+                      // epilogue; float4 index of that head's weights in s_dotw, `epi` then names the OUTPUT stage. -1: plain hidden layer
+  int dot_k;          // K of that head (channels of this op)
+  int dot_layer;      // the head's layer in the blob (f32 section: W[n][K], scale[n], bias[n])
 };
 
 struct TcArgs {
@@ -77,6 +82,7 @@ struct __align__(16) TcShared {
   unsigned long long a_ready[8];
   unsigned long long d_ready[2], epi_done;   // d_ready[h]: N-half h of the current op is complete
   unsigned int tmem_base; int pad[3];
+  float4 dot_xch[2][TILE];                  // partial head sums of the two column groups of a row
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -335,10 +341,9 @@ __device__ __forceinline__ void hidden_chunk(uint32_t taddr, const float* __rest
   tmem_st_wait();
 }
 
-// scale/bias/activation + hi / -lo split of ONE 16-column piece held in registers (raw accumulator bits in, packed words out)
+// scale/bias/activation of ONE 16-column piece held in registers (raw accumulator bits in)
 template <int ACT>
-__device__ __forceinline__ void hidden_piece(const uint32_t raw[16], const float* __restrict__ sbp, uint32_t hi[8], uint32_t nlo[8]) {
-  float v[16];
+__device__ __forceinline__ void act_piece(const uint32_t raw[16], const float* __restrict__ sbp, float v[16]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 s4 = *reinterpret_cast<const float4*>(sbp + 4 * i);   // {scale0, bias0, scale1, bias1}
@@ -362,8 +367,44 @@ __device__ __forceinline__ void hidden_piece(const uint32_t raw[16], const float
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = act_tc<ACT>(v[i]);
   }
+}
+// ... + hi / -lo split (packed words out)
+template <int ACT>
+__device__ __forceinline__ void hidden_piece(const uint32_t raw[16], const float* __restrict__ sbp, uint32_t hi[8], uint32_t nlo[8]) {
+  float v[16];
+  act_piece<ACT>(raw, sbp, v);
 #pragma unroll
   for (int i = 0; i < 8; ++i) split2_neg(v[2 * i], v[2 * i + 1], hi[i], nlo[i]);
+}
+// ... + accumulation into a <= 3-output linear head in fp32 (wp: one float4 {w0,w1,w2,0} per channel, broadcast reads)
+template <int ACT>
+__device__ __forceinline__ void dot_piece(const uint32_t raw[16], const float* __restrict__ sbp, const float4* __restrict__ wp, float acc[3]) {
+  float v[16];
+  act_piece<ACT>(raw, sbp, v);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float4 w = wp[i];
+    acc[0] = fmaf(v[i], w.x, acc[0]); acc[1] = fmaf(v[i], w.y, acc[1]); acc[2] = fmaf(v[i], w.z, acc[2]);
+  }
+}
+// The last hidden layer of a head (256->3 warp offsets, 128->2 geometry, 128->3 colour, 128->1 recon) followed by its tiny output
+// layer: the activations never go back to TMEM, the output layer is 3 FMAs per channel right here. As tensor-core ops these
+// N=16 layers cost 3.6-4.2 k cycles of pure dependency latency each (arrive -> 24..48 tiny MMAs -> commit -> wait -> tcgen05.ld).
+template <int ACT>
+__device__ __forceinline__ void dot_pair(uint32_t t0, uint32_t t1, const float* __restrict__ sb0, const float* __restrict__ sb1,
+                                         const float4* __restrict__ w0, const float4* __restrict__ w1, float acc[3]) {
+  uint32_t ra[16], rb[16];
+  tmem_ld16_issue(t0, ra); tmem_ld_wait(ra);
+  tmem_ld16_issue(t0 + 16u, rb);
+  dot_piece<ACT>(ra, sb0, w0, acc);
+  tmem_ld_wait(rb);
+  tmem_ld16_issue(t1, ra);
+  dot_piece<ACT>(rb, sb0 + 32, w0 + 16, acc);
+  tmem_ld_wait(ra);
+  tmem_ld16_issue(t1 + 16u, rb);
+  dot_piece<ACT>(ra, sb1, w1, acc);
+  tmem_ld_wait(rb);
+  dot_piece<ACT>(rb, sb1 + 32, w1 + 16, acc);
 }
 
 // Two 32-column chunks (c0, c1) of one accumulator half, software-pipelined in 16-column pieces: the TMEM load of piece p+1 is in
@@ -445,8 +486,15 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
     const AvcLayerDesc& L = hdr->layers[layer];
     o.layer = layer; o.n = nn; o.n_row_off = row_off; o.np = L.np; o.ks_smem = ks_s; o.ks_smem_w0 = ks_s_w0; o.ks_tmem = ks_t; o.ks_tmem_w0 = ks_t_w0;
     o.a_col = a_col; o.d_col = d_col; o.accumulate = accum; o.wait_epi = wait_epi; o.commit_d = commit; o.epi = epi; o.act = L.act;
-    o.sb_off = sb_off[layer] + 2 * row_off; o.signal_done = signal; o.wait_a = 1;
+    o.sb_off = sb_off[layer] + 2 * row_off; o.signal_done = signal; o.wait_a = 1; o.dot_w = -1; o.dot_k = 0; o.dot_layer = -1;
     o.w_off = stream_pos[layer]; stream_pos[layer] += (unsigned int)(nn * 64 * (ks_s + ks_t));
+  };
+  int dot_pos = 0;
+  // fold the head `head_layer` (n <= 3 outputs) into the epilogue of the op added last; `epi_out` is the head's output stage
+  auto head = [&](int head_layer, int epi_out, int signal) {
+    TcOp& o = S.ops[n - 1];
+    o.dot_w = dot_pos; o.dot_k = o.n; o.dot_layer = head_layer; o.epi = epi_out; o.signal_done = signal;
+    dot_pos += o.n + 1;
   };
   const int X = 0, Y = 256;
   if (kind == AVC_KIND_AVATAR) {
@@ -458,7 +506,7 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
       add(4, 256, 0, 5, 0, 16, 5, Y, X, 0, 0, 1, EPI_HIDDEN, 0);       // conv5: [h0 | x4]; weight k-steps 0..4 = h0, 5..20 = x4
       add(5, 256, 0, 0, 0, 16, 0, X, Y, 0, 0, 1, EPI_HIDDEN, 0);
       add(6, 256, 0, 0, 0, 16, 0, Y, X, 0, 0, 1, EPI_HIDDEN, 0);       // x7 in X
-      add(7, 16, 0, 0, 0, 16, 0, X, Y, 0, 0, 1, EPI_WARP_OUT, 0);      // offsets; epilogue also writes the PE into the skip buffer
+      head(7, EPI_WARP_OUT, 0);                                        // offsets = out_layer(x7) in conv7's epilogue, which then writes the PE
     }
     if (mode != AVC_MODE_WARP_ONLY) {
       add(8, 256, 0, 4, 0, 0, 0, 0, X, 0, 1, 1, EPI_HIDDEN, 0);        // fc0: PE (K=64, smem)
@@ -469,12 +517,12 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
       add(13, 256, 0, 0, 0, 16, 0, X, Y, 0, 0, 1, EPI_HIDDEN, 0);
       add(14, 256, 0, 0, 0, 16, 0, Y, X, 0, 0, 1, EPI_HIDDEN, 0);      // shared feature s7 in X (kept for the colour head)
       add(15, 128, 0, 0, 0, 16, 0, X, Y, 0, 0, 1, EPI_HIDDEN, 0);      // geo fc0 -> Y[0,128)
-      add(16, 16, 0, 0, 0, 8, 0, Y, Y + 128, 0, 0, 1, EPI_GEO_OUT, texture ? 1 : 0);
+      head(16, EPI_GEO_OUT, texture ? 1 : 0);
       if (texture) {
         add(17, 256, 0, 0, 0, 16, 0, X, Y, 0, 1, 1, EPI_HIDDEN, 0);    // clr fc0 (waits until the geo head has been read out of Y)
         S.ops[n - 1].wait_a = 0;                                       // s7 was completed for geo fc0 already
         add(18, 128, 0, 0, 0, 16, 0, Y, X, 0, 0, 1, EPI_HIDDEN, 0);    // clr fc1 -> X[0,128)
-        add(19, 16, 0, 0, 0, 8, 0, X, X + 128, 0, 0, 1, EPI_CLR_OUT, 0);
+        head(19, EPI_CLR_OUT, 0);
       }
     }
   } else {
@@ -483,7 +531,7 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
     add(0, 256, 256, 3, 0, 0, 0, 0, X, 0, 0, 1, EPI_HIDDEN, 0);        // fc0 rows 256..511: y1b in X
     add(1, 256, 0, 3, 32, 16, 16, X, Y, 1, 0, 1, EPI_HIDDEN, 0);       // fc1 over h0 (k-steps 32..34) and y1b (16..31), accumulating
     add(2, 128, 0, 3, 16, 16, 0, Y, X, 0, 0, 1, EPI_HIDDEN, 0);        // fc2: [y2 | h0] -> X[0,128)
-    add(3, 16, 0, 0, 0, 8, 0, X, X + 128, 0, 0, 1, EPI_RECON_OUT, 0);
+    head(3, EPI_RECON_OUT, 0);
   }
   S.n_ops = n;
 }
@@ -494,7 +542,8 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
   unsigned char* ring = dsm;                                       // N_STAGES * STAGE_BYTES
   unsigned char* skip = dsm + N_STAGES * STAGE_BYTES;              // SKIP_BYTES
   float* s_sb = reinterpret_cast<float*>(skip + SKIP_BYTES);       // {scale,bias} pairs of every layer
-  TcShared& S = *reinterpret_cast<TcShared*>(reinterpret_cast<unsigned char*>(s_sb) + SB_FLOATS_MAX * sizeof(float));
+  float4* s_dotw = reinterpret_cast<float4*>(s_sb + SB_FLOATS_MAX);  // head weights {w0,w1,w2,0} per channel (+ a bias row per head)
+  TcShared& S = *reinterpret_cast<TcShared*>(reinterpret_cast<unsigned char*>(s_dotw) + DOTW_F4_MAX * sizeof(float4));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool texture = (a.out_rgb != nullptr);
@@ -525,6 +574,19 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
         s_sb[base + 2 * c + 1] = a.f32[L.tc_sb_off + L.np + c];
       }
       base += 2 * L.np;
+    }
+    // head weights: the blob keeps W[n][K] for layers with n <= 4 (packer.py); scale folded in, bias row appended
+    for (int oi = 0; oi < n_ops; ++oi) {
+      const TcOp& o = a.ops[oi];
+      if (o.dot_w < 0) continue;
+      const AvcLayerDesc& L = a.hdr->layers[o.dot_layer];
+      const int K = o.dot_k;
+      for (int k = tid; k <= K; k += NT) {
+        float w[3] = {0.f, 0.f, 0.f};
+        for (int j = 0; j < L.n && j < 3; ++j)
+          w[j] = k < K ? a.f32[L.wt_off + j * K + k] * a.f32[L.sb_off + j] : a.f32[L.sb_off + L.n + j];
+        s_dotw[o.dot_w + k] = make_float4(w[0], w[1], w[2], 0.f);
+      }
     }
   }
   __syncthreads();
@@ -789,12 +851,46 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
           }
           if (tid == 0) trace_ev(a.trace, tl, oi, 6);
         } else {
-          float v[4];
-          tmem_ld4(t_lane + (uint32_t)o.d_col, v);
-          const float* sb = s_sb + o.sb_off;
           float r[4];
+          if (o.dot_w >= 0) {
+            // last hidden layer of a head + its <= 3-output linear layer on the CUDA cores (dot_pair)
+            float acc[3] = {0.f, 0.f, 0.f};
+            const float* sb = s_sb + o.sb_off;
+            const int n_chunks = o.n >> 5;
+            for (int c = grp; c < n_chunks; c += 4) {
+              if (c == 4 + grp) {
+                if (tid == 0) trace_ev(a.trace, tl, oi, 4);
+                mbar_wait(&S.d_ready[1], ph_d1); ph_d1 ^= 1; tc_fence_after();
+                if (tid == 0) trace_ev(a.trace, tl, oi, 5);
+              }
+              const uint32_t t0 = t_lane + (uint32_t)(o.d_col + c * 32), t1 = t0 + 64u;
+              const float* sb0 = sb + 64 * c; const float* sb1 = sb0 + 128;
+              const float4* w0 = s_dotw + o.dot_w + c * 32; const float4* w1 = w0 + 64;
+              switch (o.act) {
+                case AVC_ACT_RELU: dot_pair<AVC_ACT_RELU>(t0, t1, sb0, sb1, w0, w1, acc); break;
+                case AVC_ACT_LRELU: dot_pair<AVC_ACT_LRELU>(t0, t1, sb0, sb1, w0, w1, acc); break;
+                case AVC_ACT_SOFTPLUS: dot_pair<AVC_ACT_SOFTPLUS>(t0, t1, sb0, sb1, w0, w1, acc); break;
+                default: dot_pair<AVC_ACT_NONE>(t0, t1, sb0, sb1, w0, w1, acc); break;
+              }
+            }
+            // the two warps of a lane quadrant hold the sums over alternate 32-column chunks of the same 32 points
+            S.dot_xch[grp][row] = make_float4(acc[0], acc[1], acc[2], 0.f);
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            const float4 oth = S.dot_xch[grp ^ 1][row];
+            const float4 bias = s_dotw[o.dot_w + o.dot_k];
+            // fixed summation order (group 0 + group 1) so that both warps of the quadrant get bit-identical results
+            const float e0 = grp == 0 ? acc[0] : oth.x, e1 = grp == 0 ? acc[1] : oth.y, e2 = grp == 0 ? acc[2] : oth.z;
+            const float f0 = grp == 0 ? oth.x : acc[0], f1 = grp == 0 ? oth.y : acc[1], f2 = grp == 0 ? oth.z : acc[2];
+            r[0] = (e0 + f0) + bias.x; r[1] = (e1 + f1) + bias.y; r[2] = (e2 + f2) + bias.z; r[3] = 0.f;
+            asm volatile("bar.sync 3, 256;" ::: "memory");          // dot_xch may be rewritten by the next head
+            if (tid == 0) trace_ev(a.trace, tl, oi, 6);
+          } else {
+            float v[4];
+            tmem_ld4(t_lane + (uint32_t)o.d_col, v);
+            const float* sb = s_sb + o.sb_off;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) r[i] = fmaf(v[i], sb[2 * i], sb[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) r[i] = fmaf(v[i], sb[2 * i], sb[2 * i + 1]);
+          }
           if (o.epi == EPI_WARP_OUT) {
             qx = px + r[0]; qy = py + r[1]; qz = pz + r[2];                       // cano_pts_chunk + offset_chunk  arch_avatar.py:372
             if (grp == 0 && valid && a.out_off) { a.out_off[g * 3] = r[0]; a.out_off[g * 3 + 1] = r[1]; a.out_off[g * 3 + 2] = r[2]; }
@@ -830,7 +926,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
   }
 }
 
-constexpr size_t TC_SMEM = (size_t)N_STAGES * STAGE_BYTES + SKIP_BYTES + SB_FLOATS_MAX * sizeof(float) + sizeof(TcShared) + 64;
+constexpr size_t TC_SMEM = (size_t)N_STAGES * STAGE_BYTES + SKIP_BYTES + SB_FLOATS_MAX * sizeof(float) + DOTW_F4_MAX * sizeof(float4) + sizeof(TcShared) + 64;
 
 int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, const float* pts, int64_t n, const float center[3], float* out0,
               float* out_off, float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st) {

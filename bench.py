@@ -287,6 +287,14 @@ def run_ours(args):
         rend = api.NerfRenderer.for_engine(eng, torch.from_numpy(scene['pose_map'])[None].to(dev), sw, cv, wvol)
         cb = {'cano_smpl_center': torch.from_numpy(center)[None].to(dev), 'cano_bounds': torch.from_numpy(frame['cano_bounds'])[None].to(dev)}
         t_col, _ = timed(lambda: api.vertex_colors(rend, cb, mv[:nvc], mn[:nvc]), reps=3)
+        # reconstruction decoder (ReconNetwork.infer's per-point part) over the same dense grid and over the masked points
+        eng.load_recon(synth.recon_state_dict()); eng.set_image_feature_map(synth.feature_map(32, 256, 256, synth.SEED + 5))
+        t_rec, _ = timed(lambda: eng.eval_recon(pts, center, impl=impl), reps=3)
+        t_rec_m, _ = timed(lambda: eng.eval_recon(vpts, center, impl=impl), reps=3)
+        peaks_r, _ = measured_peaks()
+        peak_r = float(peaks_r.get('bf16_tflops_sustained', peaks_r.get('bf16_tflops', 1590.0)))
+        recon_ms = {'recon_dense_ms': t_rec, 'recon_dense_mpts': n / t_rec / 1e3, 'recon_masked_ms': t_rec_m,
+                    'recon_roofline_frac': n * FLOP_PER_PT['recon'] / (t_rec * 1e-3) / 1e12 / peak_r}
         # per-frame encoders ("next" row 1): CUDA-graph replay vs eager launches of the same functional forward (cuDNN, f32, no TF32)
         from avatarcap_b200 import encoders
         xin = torch.from_numpy(synth.smpl_pos_map()).to(dev); nin = torch.from_numpy(synth.normal_maps()).to(dev)
@@ -299,7 +307,7 @@ def run_ours(args):
             del pe, ie
         frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
-        frame_ms.update(enc_ms)
+        frame_ms.update(enc_ms); frame_ms.update(recon_ms)
 
     # ---- frame-parallel replicas (BASELINE config[5]: 16 frames x 256^3 on 8 GPUs = 2 frames per GPU): frame f -> rank f mod world,
     # dense field + marching cubes + skinning per frame, each frame with its own live pose and feature map; encoders excluded
