@@ -32,7 +32,7 @@ constexpr int TILE = 128;                 // points per tile == UMMA M
 constexpr int NT = 352;                   // 8 compute warps + 2 alternating MMA-issuer warps + producer warp
 constexpr int N_STAGES = 4;
 constexpr int STAGE_KSTEPS = 4;           // k-steps per ring stage (== two 32-column A chunks)
-constexpr int STAGE_BYTES = STAGE_KSTEPS * 8192;   // per k-step of one N-half: hi (128 rows * 32 B) + lo (128 rows * 32 B)
+constexpr int STAGE_BYTES = STAGE_KSTEPS * 4096;   // per k-step of one N-half, THIS CTA's 64 of the 128 weight rows: hi 2 KB + lo 2 KB
 constexpr int SKIP_KSTEPS = 5;            // up to K=80 of skip input
 constexpr int SKIP_BYTES = SKIP_KSTEPS * 8192;   // per k-step: hi slab 4 KB + lo slab 4 KB (128 rows x 16 k x 2 B)
 constexpr int MAX_OPS = 24;
@@ -468,6 +468,13 @@ __device__ __forceinline__ void gather8(const float* __restrict__ hwc, int C, co
   }
 }
 
+// One step of the input stage (skip operand of the first layer) for point (px,py,pz) with bilinear taps t:
+//   avatar: h0 in tensor-core order [f0..f63, x, y, z, 0...] (packer permutes the 67 columns accordingly)   arch_avatar.py:121-136
+//           slices 0..3 = 8 feature channels each of this warp group's 32, slice 4 = the xyz / zero-pad rows (group 1)
+//   recon : h0 = [f0..f31, z - cz, 0...]   arch_recon.py:62-70; slices 0..1 = features, slice 2 = z row (group 1)
+struct TcArgs;
+__device__ __forceinline__ void input_slice(const TcArgs& a, unsigned char* buf, int row, int grp, int sl, const Taps& t, float px, float py, float pz);
+
 // debug timeline: event e of op `oi` in the CTA-local tile number `t` (only CTA 0, first 4 tiles)
 __device__ __forceinline__ void trace_ev(long long* trace, int t, int oi, int e) {
   if (trace && blockIdx.x == 0 && t < 4) trace[(t * MAX_OPS + oi) * 8 + e] = clock64();
@@ -536,12 +543,34 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
   S.n_ops = n;
 }
 
+__device__ __forceinline__ void input_slice(const TcArgs& a, unsigned char* buf, int row, int grp, int sl, const Taps& t, float px, float py, float pz) {
+  float v[8];
+  if (a.kind == AVC_KIND_AVATAR) {
+    if (sl < 4) { gather8(a.map, a.mC, t, grp * 32 + sl * 8, v); skip_store8(buf, row, grp * 4 + sl, v); }
+    else if (grp == 1) {
+      v[0] = px; v[1] = py; v[2] = pz; v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
+      skip_store8(buf, row, 8, v);
+      v[0] = v[1] = v[2] = 0.f;
+      skip_store8(buf, row, 9, v);
+    }
+  } else {
+    if (sl < 2) { gather8(a.map, a.mC, t, grp * 16 + sl * 8, v); skip_store8(buf, row, grp * 2 + sl, v); }
+    else if (grp == 1) {
+      v[0] = pz - a.cz; v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
+      skip_store8(buf, row, 4, v);
+      v[0] = 0.f;
+      skip_store8(buf, row, 5, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) unsigned char dsm[];
   unsigned char* ring = dsm;                                       // N_STAGES * STAGE_BYTES
-  unsigned char* skip = dsm + N_STAGES * STAGE_BYTES;              // SKIP_BYTES
-  float* s_sb = reinterpret_cast<float*>(skip + SKIP_BYTES);       // {scale,bias} pairs of every layer
+  unsigned char* skip0 = dsm + N_STAGES * STAGE_BYTES;             // 2 x SKIP_BYTES: tile t uses buffer t & 1, the other one is being
+                                                                   // filled with the next tile's input (gather prefetch)
+  float* s_sb = reinterpret_cast<float*>(skip0 + 2 * SKIP_BYTES);  // {scale,bias} pairs of every layer
   float4* s_dotw = reinterpret_cast<float4*>(s_sb + SB_FLOATS_MAX);  // head weights {w0,w1,w2,0} per channel (+ a bias row per head)
   TcShared& S = *reinterpret_cast<TcShared*>(reinterpret_cast<unsigned char*>(s_dotw) + DOTW_F4_MAX * sizeof(float4));
 
@@ -663,11 +692,12 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       uint32_t ph_a = 0, ph_epi = 0;   // per-barrier phase bits (tracked by both warps, waited on by the stage owner)
       uint32_t g = 0;                  // global stage counter
-      const uint32_t skip_addr = smem_u32(skip), ring_addr = smem_u32(ring);
+      const uint32_t skip_base = smem_u32(skip0), ring_addr = smem_u32(ring);
       const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);   // LBO, SBO, version
       int tl = 0;
       if (me == 1) asm volatile("bar.arrive 1, 64;" ::: "memory");      // warp 8 owns stage 0
       for (int64_t pair = pair0; pair < n_pairs; pair += pair_step) {
+        const uint32_t skip_addr = skip_base + (uint32_t)(tl & 1) * SKIP_BYTES;
         for (int oi = 0; oi < n_ops; ++oi) {
           const TcOp& o = a.ops[oi];
           // A 256-wide layer is issued as two N=128 halves, each over the full K. The epilogue of half 0 (accumulator columns
@@ -762,42 +792,45 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t ph_d0 = 0, ph_d1 = 0;
     int tl = 0;
+    float nx_x = 0.f, nx_y = 0.f, nx_z = 0.f;          // the next tile's point (gather prefetch)
     for (int64_t pair = pair0; pair < n_pairs; pair += pair_step) {
       const int64_t tile = pair * 2 + rank;
       const int64_t g = tile * TILE + row;
       const bool valid = g < a.n;
-      float px = 0.f, py = 0.f, pz = 0.f;
-      if (valid) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; }
-      float qx = px, qy = py, qz = pz;
-      // ---------------- input stage: skip operand of the first layer ------------------------------------------------
-      bool need_pe = false;
-      if (a.kind == AVC_KIND_AVATAR && a.mode != AVC_MODE_TEMPLATE_ONLY) {
-        // h0 in tensor-core order [f0..f63, x, y, z, 0...] (packer permutes the 67 columns accordingly)   arch_avatar.py:121-136
-        const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { gather8(a.map, a.mC, t, grp * 32 + q * 8, v); skip_store8(skip, row, grp * 4 + q, v); }
-        if (grp == 1) {
-          v[0] = px; v[1] = py; v[2] = pz; v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
-          skip_store8(skip, row, 8, v);
-          v[0] = v[1] = v[2] = 0.f;
-          skip_store8(skip, row, 9, v);
-        }
-      } else if (a.kind == AVC_KIND_RECON) {
-        // h0 = [f0..f31, z - cz, 0...]   arch_recon.py:62-70
-        const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { gather8(a.map, a.mC, t, grp * 16 + q * 8, v); skip_store8(skip, row, grp * 2 + q, v); }
-        if (grp == 1) {
-          v[0] = pz - a.cz; v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = 0.f;
-          skip_store8(skip, row, 4, v);
-          v[0] = 0.f;
-          skip_store8(skip, row, 5, v);
+      unsigned char* skip = skip0 + (tl & 1) * SKIP_BYTES;          // this tile's skip operand; the other buffer receives the next tile's
+      unsigned char* skip_nx = skip0 + ((tl & 1) ^ 1) * SKIP_BYTES;
+      const bool gathers = a.kind == AVC_KIND_RECON || a.mode != AVC_MODE_TEMPLATE_ONLY;     // input = bilinear feature gather
+      const int n_slices = a.kind == AVC_KIND_RECON ? 3 : 5;
+      float px, py, pz;
+      if (tl == 0) {
+        px = py = pz = 0.f;
+        if (valid) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; }
+        if (gathers) {
+          const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
+          for (int sl = 0; sl < n_slices; ++sl) input_slice(a, skip, row, grp, sl, t, px, py, pz);
         }
       } else {
-        need_pe = true;   // template only: PE of the input points
+        px = nx_x; py = nx_y; pz = nx_z;                            // loaded (and its input staged) during the previous tile
       }
+      float qx = px, qy = py, qz = pz;
+      bool need_pe = !gathers;                                      // template only: the input stage is the PE of the points themselves
+      // gather prefetch of the NEXT tile: one step per op, taken right before the wait for that op's accumulator -- the compute warps
+      // idle there (the "tail" between their last A chunk and the first accumulator half of the next layer, ~1.9 k cycles)
+      const bool has_next = gathers && pair + pair_step < n_pairs;
+      const int pf_first = (a.kind == AVC_KIND_AVATAR && a.mode == AVC_MODE_QUERY) ? 8 : 1;
+      int pf = 0;
+      Taps nt;
+      auto prefetch_step = [&]() {
+        if (pf == 0) {
+          const int64_t g2 = ((pair + pair_step) * 2 + rank) * TILE + row;
+          nx_x = nx_y = nx_z = 0.f;
+          if (g2 < a.n) { nx_x = a.pts[g2 * 3]; nx_y = a.pts[g2 * 3 + 1]; nx_z = a.pts[g2 * 3 + 2]; }
+          nt = make_taps(nx_x - a.cx, -(nx_y - a.cy), a.mH, a.mW);
+        } else {
+          input_slice(a, skip_nx, row, grp, pf - 1, nt, nx_x, nx_y, nx_z);
+        }
+        ++pf;
+      };
       for (int oi = 0; oi <= n_ops; ++oi) {
         if (need_pe) {
           // positional encoding of q into the skip buffer: k = [q(3), {sin(2^f q)(3), cos(2^f q)(3)}_f=0..9, 0]   net_util.py:28-37
@@ -829,6 +862,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
         if (oi == n_ops) break;
         const TcOp& o = a.ops[oi];
         if (!o.commit_d) continue;
+        if (has_next && oi >= pf_first && pf <= n_slices) prefetch_step();
         mbar_wait(&S.d_ready[0], ph_d0); ph_d0 ^= 1; tc_fence_after();
         if (tid == 0) trace_ev(a.trace, tl, oi, 3);
         if (o.epi == EPI_HIDDEN) {
@@ -914,6 +948,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
           }
         }
       }
+      if (has_next) while (pf <= n_slices) prefetch_step();        // short programs have fewer ops than prefetch steps
       ++tl;
     }
   }
@@ -926,7 +961,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
   }
 }
 
-constexpr size_t TC_SMEM = (size_t)N_STAGES * STAGE_BYTES + SKIP_BYTES + SB_FLOATS_MAX * sizeof(float) + DOTW_F4_MAX * sizeof(float4) + sizeof(TcShared) + 64;
+constexpr size_t TC_SMEM = (size_t)N_STAGES * STAGE_BYTES + 2 * SKIP_BYTES + SB_FLOATS_MAX * sizeof(float) + DOTW_F4_MAX * sizeof(float4) + sizeof(TcShared) + 64;
 
 int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, const float* pts, int64_t n, const float center[3], float* out0,
               float* out_off, float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st) {
