@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       const bool gathers = a.kind == AVC_KIND_RECON || a.mode != AVC_MODE_TEMPLATE_ONLY;     // input = bilinear feature gather
       const int n_slices = a.kind == AVC_KIND_RECON ? 3 : 5;
       float px, py, pz;
-      if (tl == 0) {
+      if (tl == 0 || !gathers) {                                      // template-only programs have no prefetch: load every tile's points here
         px = py = pz = 0.f;
         if (valid) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; }
         if (gathers) {

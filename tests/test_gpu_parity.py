@@ -275,6 +275,12 @@ def test_config1_dense_64(eng, impl):
         impl, err, ref['cano_pts_ov'].min(), ref['cano_pts_ov'].max(), maxabs(o['off'].cpu().numpy(), ref['nonrigid_offset'])))
     assert err < 1e-4
     assert maxabs(o['off'].cpu().numpy(), ref['nonrigid_offset']) < 2e-6
+    # the split entry points (WarpingField.query, DoubleTNet.forward) over MANY tiles per CTA must reproduce the fused query
+    off = eng.eval_warp(pts, fr['cano_smpl_center'], impl=impl)
+    assert torch.equal(off, o['off'])
+    rgb, alpha, occ = eng.eval_template(pts + off, impl=impl)
+    assert maxabs(occ.cpu().numpy(), ref['cano_pts_ov'][:, 0]) < 1e-4
+    assert maxabs(occ.cpu().numpy(), o['occ'].cpu().numpy()) < 2e-5
     # mesh parity on the evaluated field: vertex count within 1e-3, Chamfer within 1e-3 m
     from oracle import mesh_oracle as mo
     vol_g = o['occ'].reshape(64, 64, 64)
