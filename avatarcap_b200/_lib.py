@@ -12,6 +12,7 @@ OK, EINVAL, ECUDA, ESTATE, ECAPACITY, EFORMAT, EVALUE = 0, -1, -2, -3, -4, -5, -
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC2 = 0, 1, 2, 3
 IF_SDF, IF_OCCUPANCY = 0, 1
 MAP_POSE, MAP_IMAGE = 0, 1
+RASTER_CULL_BACK, RASTER_FLIP_X = 1, 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _F3 = C.c_float * 3
@@ -52,6 +53,8 @@ SIGNATURES = {
     'avc_ray_samples': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
     'avc_nerf_raw': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_f), _i64, _vp, _vp]),
     'avc_composite': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp]),
+    'avc_rasterize': (_i, [_vp, _vp, _i64, _vp, _i64, _vp, C.POINTER(_f), _i, _i, C.POINTER(_f), _i, _i, _vp, _vp]),
+    'avc_canonicalize_normals': (_i, [_vp, _vp, _vp, _i64, C.POINTER(_f), _f, _f, _f, _f, _vp, _i, _vp, _i, _i, _vp, _vp]),
     'avc_posed_to_cano': (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, C.POINTER(_f), _vp, C.POINTER(_i), _vp, _vp, _vp]),
 }
 

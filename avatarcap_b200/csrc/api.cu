@@ -29,7 +29,7 @@ int avc_ensure_scratch(avc_ctx* ctx, size_t bytes) {
   return AVC_OK;
 }
 
-extern "C" int avc_abi_version(void) { return 3; }
+extern "C" int avc_abi_version(void) { return 4; }
 
 extern "C" int avc_ctx_create(int device, avc_ctx** out) {
   if (!out) return avc_fail(nullptr, AVC_EINVAL, "avc_ctx_create: out is NULL");

@@ -313,6 +313,41 @@ class Engine:
         return rgb, acc, dep
 
 
+    # ------------------------------------------------------------------ off-screen rasteriser / normal canonicalisation
+    def rasterize(self, verts, faces, attrs, mvp, width: int, height: int, bg=(0., 0., 0.), cull: bool = True, flip_x: bool = False,
+                  channels: int = 4) -> torch.Tensor:
+        """Renderer.render() (utils/renderer.py:428-451) -> (height, width, channels) float32 device tensor, row 0 = top.
+        faces None = triangle soup (glDrawArrays); attrs None = the 'position' shader."""
+        v = self._f32(verts, 3)
+        f = None
+        if faces is not None:
+            f = (faces if isinstance(faces, torch.Tensor) else torch.as_tensor(np.asarray(faces))).to(self.device, torch.int32).contiguous()
+            if f.dim() != 2 or f.shape[1] != 3:
+                raise ValueError('faces must be (F,3)')
+        a = None if attrs is None else self._f32(attrs, 3)
+        if a is not None and a.shape[0] != v.shape[0]:
+            raise ValueError('one attribute row per vertex expected')
+        nf = f.shape[0] if f is not None else v.shape[0] // 3
+        m = (C.c_float * 16)(*[float(x) for x in np.asarray(mvp, dtype=np.float32).reshape(16)])
+        out = torch.empty((height, width, channels), device=self.device, dtype=torch.float32)
+        flags = (_lib.RASTER_CULL_BACK if cull else 0) | (_lib.RASTER_FLIP_X if flip_x else 0)
+        self._check(self.lib.avc_rasterize(self._h, _ptr(v), v.shape[0], _ptr(f), nf, _ptr(a), m, int(width), int(height), _lib.f3(bg), flags,
+                                           int(channels), _ptr(out), self._stream()))
+        return out
+
+    def canonicalize_normals(self, live_verts, vert_mats, mv, fx, fy, cx, cy, position_map, normal_map) -> torch.Tensor:
+        """Per-vertex part of canonicalize_normal_map (normal_fusion/normal_fusion.py:27-62) -> (V,3) canonical normals."""
+        v = self._f32(live_verts, 3); vm = self._f32(vert_mats).reshape(-1, 16)
+        pm = self._f32(position_map); nm = self._f32(normal_map, 3)
+        if vm.shape[0] != v.shape[0] or pm.dim() != 3 or nm.dim() != 3 or pm.shape[:2] != nm.shape[:2] or pm.shape[2] not in (3, 4):
+            raise ValueError('canonicalize_normals: inconsistent shapes')
+        m = (C.c_float * 16)(*[float(x) for x in np.asarray(mv, dtype=np.float32).reshape(16)])
+        out = torch.empty_like(v)
+        self._check(self.lib.avc_canonicalize_normals(self._h, _ptr(v), _ptr(vm), v.shape[0], m, float(fx), float(fy), float(cx), float(cy), _ptr(pm),
+                                                      int(pm.shape[2]), _ptr(nm), int(nm.shape[0]), int(nm.shape[1]), _ptr(out), self._stream()))
+        return out
+
+
 _default: Dict[int, Engine] = {}
 
 

@@ -68,6 +68,34 @@ def recon_frame(engine: Engine, frame: Dict, img_feat_map, vol_res, flag: Option
     return {'volume': vol, 'verts': v, 'faces': f, 'normals': n, 'live_verts': lv, 'live_normals': ln}
 
 
+def fused_normal_maps(engine: Engine, avatar: Dict[str, torch.Tensor], frame: Dict, normal_map, cam: Dict, w2c, img: int = 512,
+                      integrate_manner: str = 'cover', neck_xy=None, iter_num: int = 100):
+    """Step 2 of run_avatarcap (main.py:369, 400-428) on the device: the avatar's canonical front / back normal maps
+    (render_cano_mesh), the image-observed normals brought to the canonical space (canonicalize_normal_map) and their fusion
+    ('cover' :421, or 'merge' :416-420 -- the Adam rotation-grid optimiser, PyTorch autograd as in the reference).
+    `avatar` is avatar_frame()'s result; cam = {'fx','fy','cx','cy'}; w2c the (4,4) world->camera matrix (items['w2c_RT']).
+    -> {'front_normal': (1,3,S,S), 'back_normal': (1,3,S,S)} ready for ReconNetwork.get_feat_maps (arch_recon.py:41-52)."""
+    from . import render
+    center = np.asarray(frame['cano_smpl_center'], np.float32)
+    v, f, n = avatar['verts'], avatar['faces'], avatar['normals']
+    front_avatar, back_avatar = render.render_cano_mesh_device(engine, v, n, f, center, img)                 # main.py:369
+    lbs = engine.lbs_weights(v, frame['cano_smpl_v'], frame['smpl_skinning_weights'])                        # main.py:385
+    live_v, vert_mats = engine.skin_points(v, lbs, frame['cano2live_jnt_mats'], return_pt_mats=True)        # main.py:386
+    front_img, _, _ = render.canonicalize_normal_map_device(engine, v, live_v, f, normal_map, vert_mats, w2c, cam['fx'], cam['fy'], cam['cx'],
+                                                            cam['cy'], center, img)                          # main.py:408-410
+    if integrate_manner == 'cover':
+        front = render.merge_normal_images_cover(front_avatar.clone(), front_img)
+    elif integrate_manner == 'merge':
+        if neck_xy is None:
+            raise ValueError('merge needs neck_xy')
+        front = torch.from_numpy(render.merge_normal_images(front_avatar, front_img, iter_num, neck_xy, device=engine.device)).to(engine.device)
+    else:
+        raise ValueError('Invalid integration manner!')                                                      # main.py:423
+    # "suppose that the performer is facing the camera": the back keeps the avatar normal (main.py:425-426)
+    return {'front_normal': front.permute(2, 0, 1)[None].contiguous(), 'back_normal': back_avatar.permute(2, 0, 1)[None].contiguous(),
+            'front_avatar_normal': front_avatar, 'front_image_normal': front_img, 'live_verts': live_v, 'vert_mats': vert_mats}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Frame-parallel replicas (BASELINE config[5], SURVEY.md section 8e "Frame-parallel"): frame f runs on rank f mod world,
 # no communication on the data path; only the per-frame results are gathered by the caller if it wants them.

@@ -167,6 +167,18 @@ def body_inside(points: np.ndarray, pose75: np.ndarray) -> np.ndarray:
     return inside
 
 
+def body_sdf(points: np.ndarray, pose75: np.ndarray) -> np.ndarray:
+    """Smooth signed field of the capsule body (positive inside, the reference's SDF convention, avatarcap_dataset.py:124):
+    max over bones of (radius - distance). Gives closed test meshes for the rasteriser / fusion stages."""
+    mats = joint_affine_mats(pose75)
+    pj = np.einsum('jab,jb->ja', mats[:, :3, :3], _REST_JOINTS) + mats[:, :3, 3]
+    p = np.asarray(points, dtype=np.float64)
+    f = np.full(len(p), -1e9)
+    for j in range(1, N_JOINTS):
+        f = np.maximum(f, _BONE_RADIUS[j] - _point_segment_dist(p, pj[PARENTS[j]], pj[j]))
+    return f.astype(np.float32)
+
+
 def random_pose(seed: int, max_abs: float = 0.5) -> np.ndarray:
     rs = np.random.RandomState(seed)
     p = np.zeros(75)

@@ -308,6 +308,20 @@ def run_ours(args):
         frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
         frame_ms.update(enc_ms); frame_ms.update(recon_ms)
+        # fusion stage ("next" row 4, main.py:369-428): avatar normal maps of the masked-frame mesh (2 orthographic 512^2 views), and
+        # canonicalize_normal_map (perspective position pass + per-vertex canonicalisation + 2 views) -- the reference does these in OpenGL
+        try:
+            from avatarcap_b200 import render
+            t_r1, (nf_, nb_) = timed(lambda: render.render_cano_mesh_device(eng, mv, mn, mf, center, 512))
+            lbs_w = eng.lbs_weights(mv, cv, sw); live_v, vmats = eng.skin_points(mv, lbs_w, jm, return_pt_mats=True)
+            lc = 0.5 * (live_v.max(0)[0] + live_v.min(0)[0]).cpu().numpy()
+            w2c = np.identity(4, np.float32); w2c[:3, :3] = np.diag([1., -1., -1.]).astype(np.float32); w2c[:3, 3] = -(w2c[:3, :3] @ lc) + np.float32([0, 0, 2.6])
+            nmap = torch.zeros((512, 512, 3), device=dev); nmap[..., 2] = -1.0
+            t_r2, _ = timed(lambda: render.canonicalize_normal_map_device(eng, mv, live_v, mf, nmap, vmats, w2c, 550., 550., 256., 256., center, 512))
+            frame_ms.update({'avatar_normal_maps_ms': t_r1, 'canonicalize_normal_map_ms': t_r2,
+                             'normal_map_coverage': float((nf_.norm(dim=-1) > 0).float().mean())})
+        except Exception as ex:                                      # a secondary stage must never sink the headline measurement
+            frame_ms['raster_error'] = repr(ex)[:200]
 
     # ---- frame-parallel replicas (BASELINE config[5]: 16 frames x 256^3 on 8 GPUs = 2 frames per GPU): frame f -> rank f mod world,
     # dense field + marching cubes + skinning per frame, each frame with its own live pose and feature map; encoders excluded

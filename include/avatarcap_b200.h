@@ -209,6 +209,28 @@ int avc_nerf_raw(avc_ctx* ctx, const float* cano_q /*[dev] (n,3)*/, const uint8_
 int avc_composite(avc_ctx* ctx, const float* raw /*[dev] (n_rays,S,4)*/, const float* z_vals /*[dev] (n_rays,S)*/, int64_t n_rays, int n_samples,
                   int white_bkgd, float* out_rgb, float* out_acc, float* out_depth, void* stream);
 
+/* ---------------------------------------------------------------------------------------------- */
+/* off-screen rasteriser + normal canonicalisation ("next" row 4: the GL passes between the two field evaluations)   */
+/* ---------------------------------------------------------------------------------------------- */
+#define AVC_RASTER_CULL_BACK 1   /* glEnable(GL_CULL_FACE): drop clockwise triangles (utils/renderer.py:438) */
+#define AVC_RASTER_FLIP_X 2      /* mirror the image left-right (cv.flip(img, 1), utils/visualize_util.py:51) */
+/* Renderer.set_model + set_mvp_mat + render (utils/renderer.py:403-451) with the 'vertex_attribute' shader (:9-29), or the
+ * 'position' shader (:32-51) when attrs is NULL (attribute = object-space vertex position). Indexed mesh, or a triangle soup
+ * (faces NULL: glDrawArrays over 3*n_faces consecutive vertices). mvp row-major (glUniformMatrix4fv(..., GL_TRUE, mvp)).
+ * out_image (height, width, channels) float32, channels 3 or 4 (RGBA, alpha 1 where covered, 0 on the background),
+ * row 0 = top (data[::-1], :448). Depth test GL_LESS on a 24-bit depth, pixel-centre sampling, top-left fill rule.        */
+int avc_rasterize(avc_ctx* ctx, const float* verts /*[dev] (n_verts,3)*/, int64_t n_verts, const int32_t* faces /*[dev] (n_faces,3)|NULL*/,
+                  int64_t n_faces, const float* attrs /*[dev] (n_verts,3)|NULL*/, const float mvp[16] /*[host]*/, int width, int height,
+                  const float bg[3] /*[host]|NULL*/, int flags, int channels, float* out_image /*[dev]*/, void* stream);
+/* per-vertex part of canonicalize_normal_map (normal_fusion/normal_fusion.py:27-62): project the live vertices with the pinhole
+ * camera (mv world->camera row-major, fx fy cx cy), nearest-sample the rendered position map (visibility: |v - p| < 0.05) and the
+ * image normal map, flip y/z, rotate by inv(mv) and by the inverse of each vertex's skinning matrix; zeros where not valid.
+ * position_map (height,width,pos_channels) with pos_channels 3 or 4; normal_map (height,width,3); out_normals (n,3).               */
+int avc_canonicalize_normals(avc_ctx* ctx, const float* live_verts /*[dev] (n,3)*/, const float* vert_mats /*[dev] (n,4,4)*/, int64_t n,
+                             const float mv[16] /*[host]*/, float fx, float fy, float cx, float cy, const float* position_map /*[dev]*/,
+                             int pos_channels, const float* normal_map /*[dev]*/, int height, int width, float* out_normals /*[dev]*/,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

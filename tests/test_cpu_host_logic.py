@@ -121,7 +121,7 @@ def test_abi_header_matches_binding():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.avc_abi_version() == 3
+    assert lib.avc_abi_version() == 4
 
 
 def test_engine_fails_loudly_without_gpu():
