@@ -21,6 +21,7 @@ int avc_check_cuda(avc_ctx* ctx, cudaError_t e, const char* what) {
 }
 
 int avc_ensure_scratch(avc_ctx* ctx, size_t bytes) {
+  ctx->mc_last.valid = false;      // whoever asks for the scratch is about to overwrite it
   if (bytes <= ctx->scratch_cap) return AVC_OK;
   if (ctx->d_scratch) { cudaFree(ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_cap = 0; }
   const size_t cap = bytes + (bytes >> 3) + 4096;

@@ -67,6 +67,8 @@ struct avc_ctx {
   void* d_stage = nullptr;   size_t stage_cap = 0;
   cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
   int64_t* h_counts = nullptr;   // pinned, small
+  // marching cubes: what the last avc_mc_count scanned (block sums still in d_scratch), for avc_mc_emit_counted
+  struct { const void* vol = nullptr; int res[3] = {0, 0, 0}; float iso = 0.f; int lo = 0, hi = 0; int64_t counts[3] = {0, 0, 0}; bool valid = false; } mc_last;
   int dbg_flags = 0;             // avc_debug_set_trace(flags): timing experiments of the tensor-core kernel
   void* d_trace = nullptr;       // optional debug timeline buffer for the tensor-core kernel (avc_debug_set_trace)
 };

@@ -372,20 +372,33 @@ extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], fl
   rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, (cudaStream_t)stream);
   if (rc) return rc;
   *n_verts = ctx->h_counts[1]; *n_faces = ctx->h_counts[2];
+  auto& L = ctx->mc_last;
+  L.vol = vol; L.res[0] = res[0]; L.res[1] = res[1]; L.res[2] = res[2]; L.iso = iso; L.lo = x_halo_lo; L.hi = x_halo_hi;
+  for (int c = 0; c < 3; ++c) L.counts[c] = ctx->h_counts[c];
+  L.valid = true;
   return AVC_OK;
 }
 
-extern "C" int avc_mc_emit(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
-                           int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
-                           void* stream) {
+static int mc_emit_impl(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
+                        int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
+                        void* stream, bool trust_last_count) {
   if (!ctx || !vol || !res || !bounds || !verts || !faces) return avc_fail(ctx, AVC_EINVAL, "avc_mc_emit: NULL argument");
   if (gres_x < res[0] - x_halo_lo - x_halo_hi || x_origin < -x_halo_lo) return avc_fail(ctx, AVC_EINVAL, "avc_mc_emit: bad slab placement");
   cudaStream_t st = (cudaStream_t)stream;
+  const auto& L = ctx->mc_last;
+  // the block sums and totals of the preceding avc_mc_count are still in the scratch buffer: skip the second count + scan + host sync
+  const bool reuse = trust_last_count && L.valid && L.vol == vol && L.res[0] == res[0] && L.res[1] == res[1] && L.res[2] == res[2] && L.iso == iso &&
+                     L.lo == x_halo_lo && L.hi == x_halo_hi;
+  int64_t counts[3] = {L.counts[0], L.counts[1], L.counts[2]};
   McDims d; int nblk; int* d_blk; int64_t* d_tot; int* d_vbase;
-  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);
+  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);     // same size as for the count: no reallocation
   if (rc) return rc;
-  rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, st);
-  if (rc) return rc;
+  if (reuse) {
+    for (int c = 0; c < 3; ++c) ctx->h_counts[c] = counts[c];
+  } else {
+    rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, st);
+    if (rc) return rc;
+  }
   const int64_t nv = ctx->h_counts[1], nf = ctx->h_counts[2];
   if (nv > cap_v || nf > cap_f)
     return avc_fail(ctx, AVC_ECAPACITY, "avc_mc_emit: need %lld vertices / %lld faces, capacity %lld / %lld", (long long)nv, (long long)nf,
@@ -417,4 +430,16 @@ extern "C" int avc_mc_emit(avc_ctx* ctx, const float* vol, const int res[3], con
   mc_faces_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, e, d_blk, d_vbase);
   AVC_LAUNCH_CHECK(ctx, "mc_faces_kernel");
   return AVC_OK;
+}
+
+extern "C" int avc_mc_emit(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
+                           int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
+                           void* stream) {
+  return mc_emit_impl(ctx, vol, res, bounds, iso, x_halo_lo, x_halo_hi, x_origin, gres_x, verts, normals, faces, cap_v, cap_f, stream, false);
+}
+
+extern "C" int avc_mc_emit_counted(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
+                                   int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
+                                   void* stream) {
+  return mc_emit_impl(ctx, vol, res, bounds, iso, x_halo_lo, x_halo_hi, x_origin, gres_x, verts, normals, faces, cap_v, cap_f, stream, true);
 }

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(RS_NT) canonicalize_normals_kernel(const float
 extern "C" int avc_rasterize(avc_ctx* ctx, const float* verts, int64_t n_verts, const int32_t* faces, int64_t n_faces, const float* attrs,
                              const float mvp[16], int width, int height, const float bg[3], int flags, int channels, float* out_image,
                              void* stream) {
-  if (!ctx || !verts || !mvp || !out_image) return avc_fail(ctx, AVC_EINVAL, "avc_rasterize: NULL argument");
+  if (!ctx || !mvp || !out_image || (!verts && n_verts > 0) || (!verts && !faces && n_faces > 0)) return avc_fail(ctx, AVC_EINVAL, "avc_rasterize: NULL argument");
   if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return avc_fail(ctx, AVC_EINVAL, "avc_rasterize: bad image size %dx%d", width, height);
   if (channels != 3 && channels != 4) return avc_fail(ctx, AVC_EINVAL, "avc_rasterize: channels must be 3 or 4");
   if (n_verts < 0 || n_faces < 0 || n_verts > 0x7fffffffLL || n_faces > 0x7fffffffLL) return avc_fail(ctx, AVC_EINVAL, "avc_rasterize: mesh too large for 32-bit indices");

@@ -221,7 +221,8 @@ class Engine:
         normals = torch.empty((nv, 3), device=self.device, dtype=torch.float32) if with_normals else None
         b = np.asarray(bounds, dtype=np.float32).reshape(6)
         gx = vol.shape[0] if gres_x is None else gres_x
-        self._check(self.lib.avc_mc_emit(self._h, _ptr(vol), _lib.i3(vol.shape), _lib.f6(b), float(iso), halo_lo, halo_hi, x_origin, gx,
+        # the count above scanned exactly this volume and nothing touched the context since: emit reuses its block sums
+        self._check(self.lib.avc_mc_emit_counted(self._h, _ptr(vol), _lib.i3(vol.shape), _lib.f6(b), float(iso), halo_lo, halo_hi, x_origin, gx,
                                          _ptr(verts), _ptr(normals), _ptr(faces), max(nv, 1), max(nf, 1), self._stream()))
         return verts, faces, normals
 

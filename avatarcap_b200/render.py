@@ -229,8 +229,9 @@ def merge_normal_images(src_img, tar_img, iter_num: int, neck_xy, device: Option
     import cv2 as cv
     dev = torch.device(device) if device is not None else (torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu'))
     with torch.enable_grad():
-        src_img = torch.as_tensor(np.asarray(src_img)).to(torch.float32).to(dev)
-        tar_img = torch.as_tensor(np.asarray(tar_img)).to(torch.float32).to(dev)
+        as_t = lambda x: (x.detach() if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(dev, torch.float32)   # noqa: E731
+        src_img = as_t(src_img)
+        tar_img = as_t(tar_img)
         src_mask = torch.linalg.norm(src_img, dim=-1) > 0.
         tar_mask = torch.linalg.norm(tar_img, dim=-1) > 0.
         kernel = cv.getStructuringElement(cv.MORPH_RECT, (3, 3))

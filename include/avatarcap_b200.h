@@ -152,6 +152,14 @@ int avc_mc_emit(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], cons
                 float* verts /*[dev] (cap_v,3)*/, float* normals /*[dev] (cap_v,3)|NULL*/, int32_t* faces /*[dev] (cap_f,3)*/,
                 int64_t cap_v, int64_t cap_f, void* stream);
 
+/* avc_mc_emit for the volume the IMMEDIATELY preceding avc_mc_count call on this context scanned (same pointer, extents, iso, halo):
+ * reuses that call's block sums instead of counting and synchronising a second time. The caller guarantees the volume was not
+ * modified in between; any other library call in between, or any differing argument, silently falls back to avc_mc_emit.       */
+int avc_mc_emit_counted(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], const float bounds[6] /*[host]*/, float iso,
+                        int x_halo_lo, int x_halo_hi, int x_origin, int gres_x,
+                        float* verts /*[dev] (cap_v,3)*/, float* normals /*[dev] (cap_v,3)|NULL*/, int32_t* faces /*[dev] (cap_f,3)*/,
+                        int64_t cap_v, int64_t cap_f, void* stream);
+
 /* ---------------------------------------------------------------------------------------------- */
 /* LBS -- replaces utils/smpl_util.py and the pytorch3d KNN it calls                              */
 /* ---------------------------------------------------------------------------------------------- */

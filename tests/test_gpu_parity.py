@@ -222,6 +222,34 @@ def test_mesh_sphere_and_noise(eng):
         api.recon_mesh(eng, torch.from_numpy(vol).cuda(), vol.shape, bounds, 100.0)
 
 
+def test_mc_emit_counted_reuse_and_fallback(eng):
+    """avc_mc_emit_counted: reuses the preceding count's scan, and recounts when anything intervened or an argument differs"""
+    import ctypes as C
+    from avatarcap_b200 import _lib
+    rs = np.random.RandomState(12)
+    bounds = np.array([[-1, -1, -0.4], [1, 1, 0.4]], np.float32)
+    vol = torch.from_numpy(rs.normal(0, 1, (40, 36, 20)).astype(np.float32)).to(eng.device)
+    vol2 = torch.from_numpy(rs.normal(0, 1, (40, 36, 20)).astype(np.float32)).to(eng.device)
+    ref = [t.clone() for t in eng.extract_mesh(vol, bounds, 0.0)]                       # count + emit_counted
+    ref2 = [t.clone() for t in eng.extract_mesh(vol2, bounds, 0.25)]
+
+    def emit(fn, v_, iso, nv, nf):
+        verts = torch.empty((nv, 3), device=eng.device); faces = torch.empty((nf, 3), device=eng.device, dtype=torch.int32); nrm = torch.empty_like(verts)
+        eng._check(fn(eng._h, C.c_void_p(v_.data_ptr()), _lib.i3(v_.shape), _lib.f6(bounds.reshape(6)), float(iso), 0, 0, 0, v_.shape[0],
+                      C.c_void_p(verts.data_ptr()), C.c_void_p(nrm.data_ptr()), C.c_void_p(faces.data_ptr()), nv, nf, eng._stream()))
+        return verts, faces, nrm
+    nv, nf = eng.mc_count(vol, 0.0)
+    eng.rasterize(np.zeros((3, 3), np.float32), None, None, np.identity(4, np.float32), 8, 8)       # overwrites the scratch buffer
+    for a, b in zip(emit(eng.lib.avc_mc_emit_counted, vol, 0.0, nv, nf), ref):
+        assert torch.equal(a, b)
+    nv, nf = eng.mc_count(vol, 0.0)                                                                 # count for vol, emit for vol2 / other iso
+    nv2, nf2 = ref2[0].shape[0], ref2[1].shape[0]
+    for a, b in zip(emit(eng.lib.avc_mc_emit_counted, vol2, 0.25, nv2, nf2), ref2):
+        assert torch.equal(a, b)
+    for a, b in zip(emit(eng.lib.avc_mc_emit, vol, 0.0, nv, nf), ref):
+        assert torch.equal(a, b)
+
+
 def test_mesh_normals_vs_reference_golden(eng):
     """Sobel + trilinear normals against the reference's own conv3d / grid_sample output (mesh_golden.npz)."""
     from oracle import mesh_oracle as mo
