@@ -72,7 +72,7 @@ __device__ __forceinline__ int grid_cell(const GridDesc& G, float x, float y, fl
   return (cx * G.dy + cy) * G.dz + cz;
 }
 
-__global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restrict__ ref, int m, GridDesc* __restrict__ G, int* __restrict__ cnt) {
+__global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restrict__ ref, int m, float h_min, GridDesc* __restrict__ G, int* __restrict__ cnt) {
   __shared__ float s_mn[3][32], s_mx[3][32];
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
   for (int i = threadIdx.x; i < m; i += blockDim.x)
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restri
     for (int c = 0; c < 3; ++c) for (int w = 0; w < 32; ++w) { mn[c] = fminf(mn[c], s_mn[c][w]); mx[c] = fmaxf(mx[c], s_mx[c][w]); }
     const float ext = fmaxf(fmaxf(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
     GridDesc g;
-    g.h = fmaxf(0.04f, ext / 60.f); g.inv_h = 1.f / g.h;
+    g.h = fmaxf(h_min, ext / 60.f); g.inv_h = 1.f / g.h;
     g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
     g.dx = (int)floorf((mx[0] - mn[0]) * g.inv_h) + 1; g.dy = (int)floorf((mx[1] - mn[1]) * g.inv_h) + 1; g.dz = (int)floorf((mx[2] - mn[2]) * g.inv_h) + 1;
     g.m = m; g.cells = g.dx * g.dy * g.dz;          // <= 61^3 < GRID_MAX_CELLS
@@ -388,7 +388,8 @@ int build_grid(avc_ctx* ctx, const float* ref, int m, cudaStream_t st, GridView*
   char* base = (char*)ctx->d_grid;
   GridDesc* G = (GridDesc*)base; int* cnt = (int*)(base + 256); int* start = cnt + GRID_MAX_CELLS;
   float4* sorted = (float4*)(base + 256 + (size_t)GRID_MAX_CELLS * 4 + ((size_t)GRID_MAX_CELLS + 4) * 4);
-  grid_bounds_kernel<<<1, 1024, 0, st>>>(ref, m, G, cnt);
+  static const float h_min = [] { const char* e = getenv("AVC_KNN_CELL"); const float v = e ? (float)atof(e) : 0.f; return v >= 0.01f && v <= 1.f ? v : 0.04f; }();   // tuning knob (metres)
+  grid_bounds_kernel<<<1, 1024, 0, st>>>(ref, m, h_min, G, cnt);
   AVC_LAUNCH_CHECK(ctx, "grid_bounds_kernel");
   grid_count_kernel<<<(m + 255) / 256, 256, 0, st>>>(ref, m, G, cnt);
   AVC_LAUNCH_CHECK(ctx, "grid_count_kernel");

@@ -31,10 +31,26 @@ __device__ __forceinline__ float ldv(const float* __restrict__ vol, int64_t idx)
 // per-voxel classification: cut flags of the 3 owned edges (bit0 x, bit1 y, bit2 z) and the cell's case index (or -1)
 struct VoxInfo { int cut; int ccase; bool in_scan; bool owned; };
 
-__device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const McDims& d, int64_t v) {
+// voxel coordinates of a linear index: ONE 64-bit division pair per thread, its other voxels step in z (vox_next)
+struct Vox3 { int i, j, k; };
+__device__ __forceinline__ Vox3 vox_of(const McDims& d, int64_t v) {
+  Vox3 c;
+  if (d.nvox <= 0x7fffffffLL) {       // 32-bit division is several times cheaper than the 64-bit one
+    const unsigned int u = (unsigned int)v, t = u / (unsigned int)d.rz;
+    c.k = (int)(u - t * (unsigned int)d.rz); c.i = (int)(t / (unsigned int)d.ry); c.j = (int)(t - (unsigned int)c.i * (unsigned int)d.ry);
+  } else {
+    c.k = (int)(v % d.rz); const int64_t t = v / d.rz; c.j = (int)(t % d.ry); c.i = (int)(t / d.ry);
+  }
+  return c;
+}
+__device__ __forceinline__ void vox_next(const McDims& d, Vox3& c) {
+  if (++c.k == d.rz) { c.k = 0; if (++c.j == d.ry) { c.j = 0; ++c.i; } }
+}
+
+__device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const McDims& d, int64_t v, const Vox3& c) {
   VoxInfo r; r.cut = 0; r.ccase = -1; r.in_scan = false; r.owned = false;
   if (v >= d.nvox) return r;
-  const int k = (int)(v % d.rz); const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
+  const int i = c.i, j = c.j, k = c.k;
   if (i < d.lo || i >= d.scan_end) return r;
   r.in_scan = true; r.owned = i < d.hi_excl;
   const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
@@ -52,6 +68,12 @@ __device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const
               ((int)b011 << 6) | ((int)b111 << 7);
   }
   return r;
+}
+
+// triangle counts per case, staged once per CTA (MC_NT == 256 threads == 256 cases)
+__device__ __forceinline__ void stage_ntri(unsigned char* s_ntri) {
+  s_ntri[threadIdx.x] = g_mc_ntri[threadIdx.x];
+  __syncthreads();
 }
 
 // block-wide exclusive scan of one int per thread; returns the exclusive prefix, *total = block sum
@@ -73,45 +95,73 @@ __device__ __forceinline__ int block_excl_scan(int val, int* total) {
 
 // pass A: per-block totals {vertices in scan range, owned vertices, triangles}
 __global__ void __launch_bounds__(MC_NT) mc_count_kernel(const float* __restrict__ vol, McDims d, int* __restrict__ blk) {
+  __shared__ unsigned char s_ntri[256];
+  stage_ntri(s_ntri);
   const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
   int nv = 0, nvo = 0, nt = 0;
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
-    const VoxInfo r = classify(vol, d, v0 + q);
-    const int c = __popc(r.cut);
-    if (r.in_scan) nv += c;
-    if (r.owned) { nvo += c; if (r.ccase >= 0) nt += c_mc_ntri[r.ccase]; }
+    const VoxInfo r = classify(vol, d, v0 + q, c);
+    vox_next(d, c);
+    const int n = __popc(r.cut);
+    if (r.in_scan) nv += n;
+    if (r.owned) { nvo += n; if (r.ccase >= 0) nt += s_ntri[r.ccase]; }
   }
-  int tv, tvo, tt;
-  block_excl_scan(nv, &tv); block_excl_scan(nvo, &tvo); block_excl_scan(nt, &tt);
-  if (threadIdx.x == 0) { blk[3 * blockIdx.x] = tv; blk[3 * blockIdx.x + 1] = tvo; blk[3 * blockIdx.x + 2] = tt; }
+  // the three counts fit one word each only loosely (nt <= 20, nv <= 12 per thread): reduce them packed, 10 bits apart would overflow
+  // at 256 threads, so use two warp-shuffle reductions on a 64-bit word (21 bits per field)
+  unsigned long long w = (unsigned long long)nv | ((unsigned long long)nvo << 21) | ((unsigned long long)nt << 42);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+  __shared__ unsigned long long s_w[MC_NT / 32];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int i = 0; i < MC_NT / 32; ++i) t += s_w[i];
+    blk[3 * blockIdx.x] = (int)(t & 0x1fffff); blk[3 * blockIdx.x + 1] = (int)((t >> 21) & 0x1fffff); blk[3 * blockIdx.x + 2] = (int)(t >> 42);
+  }
 }
 
-// pass B: exclusive scan over blocks (single CTA); totals -> tot[0..2] (int64)
+// pass B: exclusive scan over blocks (single CTA, 8 consecutive blocks per thread per round); totals -> tot[0..2] (int64)
+constexpr int SCAN_EPT = 8;
 __global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(int* __restrict__ blk, int nblk, int64_t* __restrict__ tot) {
   __shared__ long long carry[3];
   __shared__ long long wsum[3][32];
   if (threadIdx.x < 3) carry[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < nblk; base += 1024) {
-    const int b = base + threadIdx.x;
-    long long x[3], inc[3];
+  for (int base = 0; base < nblk; base += 1024 * SCAN_EPT) {
+    const int b0 = base + threadIdx.x * SCAN_EPT;
+    int x[SCAN_EPT][3];
+    long long sum[3] = {0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { x[c] = b < nblk ? blk[3 * b + c] : 0; inc[c] = x[c]; }
+    for (int e = 0; e < SCAN_EPT; ++e)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { x[e][c] = b0 + e < nblk ? blk[3 * (b0 + e) + c] : 0; sum[c] += x[e][c]; }
+    long long inc[3] = {sum[0], sum[1], sum[2]};
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
       for (int c = 0; c < 3; ++c) { const long long t = __shfl_up_sync(0xffffffffu, inc[c], o); if (lane >= o) inc[c] += t; }
     if (lane == 31) { wsum[0][wid] = inc[0]; wsum[1][wid] = inc[1]; wsum[2][wid] = inc[2]; }
     __syncthreads();
-    long long pre[3] = {0, 0, 0}, tt[3] = {0, 0, 0};
-    for (int w = 0; w < 32; ++w)
+    long long pre[3], tt[3] = {0, 0, 0};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { const long long s = wsum[c][w]; if (w < wid) pre[c] += s; tt[c] += s; }
-    if (b < nblk)
+    for (int c = 0; c < 3; ++c) {
+      // warp `wid` needs the sum of the warp totals below it: one shuffle scan over the 32 totals instead of a 32-step loop
+      long long v = wsum[c][lane], sc = v;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) blk[3 * b + c] = (int)(carry[c] + pre[c] + inc[c] - x[c]);
+      for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+      tt[c] = __shfl_sync(0xffffffffu, sc, 31);
+      const long long below = __shfl_sync(0xffffffffu, sc - v, wid);
+      pre[c] = carry[c] + below + inc[c] - sum[c];
+    }
+#pragma unroll
+    for (int e = 0; e < SCAN_EPT; ++e)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { if (b0 + e < nblk) blk[3 * (b0 + e) + c] = (int)pre[c]; pre[c] += x[e][c]; }
     __syncthreads();
     if (threadIdx.x < 3) carry[threadIdx.x] += tt[threadIdx.x];
     __syncthreads();
@@ -125,8 +175,13 @@ __global__ void __launch_bounds__(MC_NT) mc_vbase_kernel(const float* __restrict
                                                          int* __restrict__ vbase, long long* __restrict__ edges) {
   const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
   int c[MC_VPT], cut[MC_VPT]; int nv = 0;
+  Vox3 vc = vox_of(d, v0 < d.nvox ? v0 : 0);
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) { const VoxInfo r = classify(vol, d, v0 + q); cut[q] = r.in_scan ? r.cut : 0; c[q] = __popc(cut[q]); nv += c[q]; }
+  for (int q = 0; q < MC_VPT; ++q) {
+    const VoxInfo r = classify(vol, d, v0 + q, vc);
+    vox_next(d, vc);
+    cut[q] = r.in_scan ? r.cut : 0; c[q] = __popc(cut[q]); nv += c[q];
+  }
   int tot; int p = blk[3 * blockIdx.x] + block_excl_scan(nv, &tot);
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
@@ -222,24 +277,37 @@ __global__ void __launch_bounds__(128) mc_verts_kernel(const float* __restrict__
 // pass D2: faces of the cell whose lowest corner is each owned voxel
 __global__ void __launch_bounds__(MC_NT) mc_faces_kernel(const float* __restrict__ vol, McDims d, McEmit e, const int* __restrict__ blk,
                                                          const int* __restrict__ vbase) {
+  __shared__ unsigned char s_ntri[256];
+  __shared__ uint4 s_tri[256];                                      // 16 edge numbers per case
+  s_tri[threadIdx.x] = reinterpret_cast<const uint4*>(g_mc_tri)[threadIdx.x];
+  stage_ntri(s_ntri);
   const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
   int ccase[MC_VPT]; int nt = 0;
-#pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) { const VoxInfo r = classify(vol, d, v0 + q); ccase[q] = (r.owned ? r.ccase : -1); if (ccase[q] >= 0) nt += c_mc_ntri[ccase[q]]; }
-  int tot; int tbase = blk[3 * blockIdx.x + 2] + block_excl_scan(nt, &tot);
-  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
+  const Vox3 c0 = vox_of(d, v0 < d.nvox ? v0 : 0);
+  Vox3 vc = c0;
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
+    const VoxInfo r = classify(vol, d, v0 + q, vc);
+    vox_next(d, vc);
+    ccase[q] = (r.owned ? r.ccase : -1); if (ccase[q] >= 0) nt += s_ntri[ccase[q]];
+  }
+  int tot; int tbase = blk[3 * blockIdx.x + 2] + block_excl_scan(nt, &tot);
+  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
+  vc = c0;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) {
+    const int i = vc.i, j = vc.j;
+    vox_next(d, vc);
     if (ccase[q] < 0) continue;
     const int64_t v = v0 + q;
-    const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
-    const int ntri = c_mc_ntri[ccase[q]];
+    const int ntri = s_ntri[ccase[q]];
+    const signed char* tri = reinterpret_cast<const signed char*>(&s_tri[ccase[q]]);
     for (int tix = 0; tix < ntri; ++tix) {
       int ids[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const int ed = c_mc_tri[ccase[q]][3 * tix + c];
-        const int corner = c_mc_edge_corner[ed], ax = c_mc_edge_axis[ed];
+        const int ed = tri[3 * tix + c];
+        const int corner = (int)((AVC_MC_EDGE_CORNER_NIBBLES >> (4 * ed)) & 0xF), ax = ed >> 2;
         const int64_t ov = v + (corner & 1) * sx + ((corner >> 1) & 1) * sy + ((corner >> 2) & 1);
         // rank of `ax` among the owner's cut edges: recompute the owner's lower-axis cut flags
         int rank = 0;

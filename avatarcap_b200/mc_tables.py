@@ -121,19 +121,27 @@ MAX_TRI = TRI.shape[1] // 3
 
 
 def emit_cuda_include(path: str) -> None:
+    """Tables live in GLOBAL memory and are staged into shared memory by each CTA: they are indexed by the per-thread case number,
+    and a divergent index serialises __constant__ accesses (one address per cycle per warp)."""
     a = np.array(EDGES, dtype=np.int32)
+    assert [int(x) for x in EDGE_AXIS] == [e >> 2 for e in range(12)]
+    corner_nibbles = sum(int(c) << (4 * e) for e, c in enumerate(a[:, 0]))
+    lines = ['// GENERATED by `python -m avatarcap_b200.mc_tables` -- do not edit.',
+             '// Marching-cubes case tables (see avatarcap_b200/mc_tables.py for the construction).',
+             '#define AVC_MC_MAX_TRI %d' % MAX_TRI,
+             '__device__ const unsigned char g_mc_ntri[256] = {%s};' % ','.join(str(int(x)) for x in NTRI),
+             '// triangle list per case: 3 edge numbers per triangle, -1 padded to 16 bytes (one uint4 per case)',
+             '__device__ __align__(16) const signed char g_mc_tri[256][16] = {']
+    for c in range(256):
+        lines.append('  {%s},' % ','.join(str(int(x)) for x in list(TRI[c]) + [-1] * (16 - MAX_TRI * 3)))
+    lines.append('};')
+    lines.append('// edge e: axis = e >> 2; lower corner offset (dx | dy<<1 | dz<<2) = nibble e of this constant')
+    lines.append('#define AVC_MC_EDGE_CORNER_NIBBLES 0x%xull' % corner_nibbles)
+    txt = '\n'.join(lines) + '\n'
+    if os.path.exists(path) and open(path).read() == txt:
+        return                      # unchanged: keep the timestamp so that make does not rebuild everything
     with open(path, 'w') as f:
-        f.write('// GENERATED by `python -m avatarcap_b200.mc_tables` -- do not edit.\n')
-        f.write('// Marching-cubes case tables (see avatarcap_b200/mc_tables.py for the construction).\n')
-        f.write('#define AVC_MC_MAX_TRI %d\n' % MAX_TRI)
-        f.write('__constant__ unsigned char c_mc_ntri[256] = {%s};\n' % ','.join(str(int(x)) for x in NTRI))
-        f.write('__constant__ signed char c_mc_tri[256][%d] = {\n' % (MAX_TRI * 3))
-        for c in range(256):
-            f.write('  {%s},\n' % ','.join(str(int(x)) for x in TRI[c]))
-        f.write('};\n')
-        f.write('// edge e: lower corner offset (dx,dy,dz) packed as dx|dy<<1|dz<<2, and its axis\n')
-        f.write('__constant__ unsigned char c_mc_edge_corner[12] = {%s};\n' % ','.join(str(int(x)) for x in a[:, 0]))
-        f.write('__constant__ unsigned char c_mc_edge_axis[12] = {%s};\n' % ','.join(str(int(x)) for x in EDGE_AXIS))
+        f.write(txt)
 
 
 if __name__ == '__main__':
