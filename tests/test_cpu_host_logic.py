@@ -142,8 +142,10 @@ def test_mc_tables_consistency():
         assert mc_tables.EDGE_MASK[c] == cut
         assert mc_tables.EDGE_MASK[c] == mc_tables.EDGE_MASK[255 - c]     # complementary case cuts the same edges
     inc = open(os.path.join(ROOT, 'avatarcap_b200', 'csrc', 'mc_tables.inc')).read()
-    row = ','.join(str(int(x)) for x in mc_tables.TRI[37])
+    row = ','.join(str(int(x)) for x in list(mc_tables.TRI[37]) + [-1])   # rows are padded to 16 bytes
     assert '{%s}' % row in inc                                             # the committed CUDA include is up to date
+    nib = sum(int(a) << (4 * e) for e, a in enumerate(np.array(mc_tables.EDGES)[:, 0]))
+    assert '0x%xull' % nib in inc and [int(x) for x in mc_tables.EDGE_AXIS] == [e >> 2 for e in range(12)]
 
 
 def test_slab_ranges_and_merge():
