@@ -142,24 +142,37 @@ __device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, const fl
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// all vertices of the cells (i, j, k0..k1): cells that differ only in k are adjacent in the sorted array, so a whole z-run is ONE
+// [start, end) range -- two index loads per run instead of two per cell
+template <int K>
+__device__ __forceinline__ void knn_visit_run(const GridView& V, const GridDesc& G, int i, int j, int k0, int k1, float qx, float qy, float qz, Top4& best) {
+  const int c = (i * G.dy + j) * G.dz;
+  const int e = __ldg(V.start + c + k1 + 1);
+  for (int p = __ldg(V.start + c + k0); p < e; ++p) { const float4 v = __ldg(V.sorted + p); top_insert<K>(best, dist2_rn(qx, qy, qz, v), __float_as_int(v.w)); }
+}
+
 template <int K>
 __device__ __forceinline__ bool knn_grid(const GridView& V, float qx, float qy, float qz, Top4& best) {
   const GridDesc G = *V.G;
   top_init(best);
   int cx, cy, cz; grid_cell(G, qx, qy, qz, cx, cy, cz);
-  bool done = false;
-  for (int r = 0; r <= GRID_RMAX && !done; ++r) {
+  // shells 0 and 1 together (shell 0 alone can never satisfy the stop test): the 3x3x3 cube as 9 z-runs
+  for (int i = max(cx - 1, 0); i <= min(cx + 1, G.dx - 1); ++i)
+    for (int j = max(cy - 1, 0); j <= min(cy + 1, G.dy - 1); ++j)
+      knn_visit_run<K>(V, G, i, j, max(cz - 1, 0), min(cz + 1, G.dz - 1), qx, qy, qz, best);
+  float rh = G.h * 0.999f;                         // 0.1 % slack for the float rounding of the cell assignment
+  bool done = best.d[K - 1] <= rh * rh;
+  for (int r = 2; r <= GRID_RMAX && !done; ++r) {
     for (int i = max(cx - r, 0); i <= min(cx + r, G.dx - 1); ++i)
       for (int j = max(cy - r, 0); j <= min(cy + r, G.dy - 1); ++j) {
-        const bool shell_ij = (abs(i - cx) == r) || (abs(j - cy) == r);
-        for (int k = max(cz - r, 0); k <= min(cz + r, G.dz - 1); ++k) {
-          if (!shell_ij && abs(k - cz) != r) continue;             // only the shell of radius r
-          const int c = (i * G.dy + j) * G.dz + k;
-          const int e = __ldg(V.start + c + 1);
-          for (int p = __ldg(V.start + c); p < e; ++p) { const float4 v = __ldg(V.sorted + p); top_insert<K>(best, dist2_rn(qx, qy, qz, v), __float_as_int(v.w)); }
+        if ((abs(i - cx) == r) || (abs(j - cy) == r)) {            // a row of the shell's side faces: the whole z-run
+          knn_visit_run<K>(V, G, i, j, max(cz - r, 0), min(cz + r, G.dz - 1), qx, qy, qz, best);
+        } else {                                                   // interior row: only the two end cells belong to the shell
+          if (cz - r >= 0) knn_visit_run<K>(V, G, i, j, cz - r, cz - r, qx, qy, qz, best);
+          if (cz + r <= G.dz - 1) knn_visit_run<K>(V, G, i, j, cz + r, cz + r, qx, qy, qz, best);
         }
       }
-    const float rh = (float)r * G.h * 0.999f;      // 0.1 % slack for the float rounding of the cell assignment
+    rh = (float)r * G.h * 0.999f;
     done = best.d[K - 1] <= rh * rh;
   }
   return done;          // false: far from every vertex -> the caller falls back to the block-cooperative brute-force scan
@@ -179,13 +192,13 @@ __global__ void __launch_bounds__(KNN_NT) near_flag_kernel(const float* __restri
   if (ob < r2 * 1.0001f) {
     const int R = (int)floorf(sqrtf(r2) * G.inv_h) + 1;   // >= ceil, with a full cell of slack when radius is a multiple of h
     int cx, cy, cz; grid_cell(G, qx, qy, qz, cx, cy, cz);
+    const int k0 = max(cz - R, 0), k1 = min(cz + R, G.dz - 1);          // a z-run of cells is one contiguous range of the sorted array
     for (int i = max(cx - R, 0); i <= min(cx + R, G.dx - 1) && !hit; ++i)
-      for (int j = max(cy - R, 0); j <= min(cy + R, G.dy - 1) && !hit; ++j)
-        for (int k = max(cz - R, 0); k <= min(cz + R, G.dz - 1) && !hit; ++k) {
-          const int c = (i * G.dy + j) * G.dz + k;
-          const int e = __ldg(V.start + c + 1);
-          for (int p = __ldg(V.start + c); p < e; ++p) if (dist2_rn(qx, qy, qz, __ldg(V.sorted + p)) < r2) { hit = true; break; }
-        }
+      for (int j = max(cy - R, 0); j <= min(cy + R, G.dy - 1) && !hit; ++j) {
+        const int c = (i * G.dy + j) * G.dz;
+        const int e = __ldg(V.start + c + k1 + 1);
+        for (int p = __ldg(V.start + c + k0); p < e; ++p) if (dist2_rn(qx, qy, qz, __ldg(V.sorted + p)) < r2) { hit = true; break; }
+      }
   }
   out[g] = hit ? 1 : 0;
 }
