@@ -16,10 +16,17 @@ through the same modules; with grad enabled every patched method falls through t
     utils.smpl_util.SmplUtil.calculate_lbs / skinning / skinning_normal   (smpl_util.py:24,58,76)
     network.arch_avatar.WarpingField.precompute_conv   (arch_avatar.py:109)   -> encoders.PoseFeatureEncoder  (install(encoders=True))
     network.arch_recon.ReconNetwork.get_feat_maps      (arch_recon.py:41)     -> encoders.ImageFeatureEncoder
+    utils.renderer.Renderer                     (renderer.py:326)   'vertex_attribute' / 'position' -> render.Renderer (no GL); phong_* -> the original
+    utils.visualize_util.render_cano_mesh       (visualize_util.py:11)   when handed a render.Renderer
+    normal_fusion.normal_fusion.canonicalize_normal_map   (normal_fusion.py:12)   when handed render.Renderer objects
+    utils.obj_io.save_mesh_as_ply               (obj_io.py:223)
+main.py binds `Renderer` and `canonicalize_normal_map` with `from ... import ...` (main.py:19,21): an already imported `main` /
+`__main__` module is re-bound too.
 """
 from __future__ import annotations
 
 import importlib
+import sys
 from typing import Dict, Optional
 
 import torch
@@ -56,14 +63,32 @@ def _encoder(slot: str, module, cls):
     return _state[slot]
 
 
+def _rebind_importers(name: str, original, replacement) -> None:
+    """`from module import name` copies the binding: re-point the driver script's copy (main.py:19,21) as well."""
+    for mod_name in ('main', '__main__'):
+        m = sys.modules.get(mod_name)
+        if m is not None and getattr(m, name, None) is original:
+            _originals['%s.%s' % (mod_name, name)] = (m, name, original)
+            setattr(m, name, replacement)
+
+
 def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules: Optional[Dict[str, object]] = None,
-            encoders: bool = True) -> None:
+            encoders: bool = True, render: bool = True) -> None:
     """Patch the reference modules in sys.path (or the ones passed in `modules`, keyed by dotted name). `encoders=False`
-    leaves the per-frame UNet / HGFilter on the reference's own nn.Modules."""
+    leaves the per-frame UNet / HGFilter on the reference's own nn.Modules; `render=False` leaves the OpenGL renderer, the
+    normal canonicalisation and the PLY writer alone."""
     if _originals:
         return
     _state['engine'] = engine
     get = (lambda name: modules[name]) if modules else importlib.import_module
+
+    def get_optional(name):
+        if modules is not None:
+            return modules.get(name)
+        try:
+            return importlib.import_module(name)
+        except ImportError:                      # e.g. no glfw / PyOpenGL on a render-less box: nothing to re-bind there
+            return None
     arch_avatar = get('network.arch_avatar'); arch_recon = get('network.arch_recon')
     recon_util = get('utils.recon_util'); smpl_util_mod = get('utils.smpl_util')
 
@@ -157,6 +182,47 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
         e = _engine()
         return torch.stack([e.skin_normals(normals[b], lbs[b], cano2live_jnt_mats[b]) for b in range(normals.shape[0])], 0)
     SU.calculate_lbs = calculate_lbs; SU.skinning = skinning; SU.skinning_normal = skinning_normal
+
+
+    if render:
+        _install_render(get_optional, keep)
+
+
+def _install_render(get_optional, keep) -> None:
+    from . import mesh_io, render as render_mod
+    renderer_mod = get_optional('utils.renderer'); vis = get_optional('utils.visualize_util')
+    nf = get_optional('normal_fusion.normal_fusion'); obj_io = get_optional('utils.obj_io')
+    if renderer_mod is not None:
+        o_R = keep(renderer_mod, 'Renderer')
+
+        class Renderer:
+            """utils/renderer.py:326 -- the two data-path shaders run in the CUDA library, the phong previews stay on OpenGL."""
+            def __new__(cls, img_w, img_h, mvp=None, shader_name='vertex_attribute', bg_color=(0, 0, 0), window_name=''):
+                if shader_name in ('vertex_attribute', 'position'):
+                    return render_mod.Renderer(img_w, img_h, mvp, shader_name, bg_color, window_name, engine=_engine())
+                args = (img_w, img_h) if mvp is None else (img_w, img_h, mvp)
+                return o_R(*args, shader_name=shader_name, bg_color=bg_color, window_name=window_name)
+        renderer_mod.Renderer = Renderer
+        _rebind_importers('Renderer', o_R, Renderer)
+    if vis is not None:
+        o_rcm = keep(vis, 'render_cano_mesh')
+        def render_cano_mesh(renderer, vertices, normals, faces, mesh_center=None, colors=None):
+            if not isinstance(renderer, render_mod.Renderer):
+                return o_rcm(renderer, vertices, normals, faces, *(() if mesh_center is None else (mesh_center,)), colors=colors)
+            import numpy as np
+            return render_mod.render_cano_mesh(renderer, vertices, normals, faces, np.zeros(3) if mesh_center is None else mesh_center, colors)
+        vis.render_cano_mesh = render_cano_mesh
+    if nf is not None:
+        o_cnm = keep(nf, 'canonicalize_normal_map')
+        def canonicalize_normal_map(pos_renderer, attri_renderer, *args, **kwargs):
+            if isinstance(pos_renderer, render_mod.Renderer) and isinstance(attri_renderer, render_mod.Renderer):
+                return render_mod.canonicalize_normal_map(pos_renderer, attri_renderer, *args, **kwargs)
+            return o_cnm(pos_renderer, attri_renderer, *args, **kwargs)
+        nf.canonicalize_normal_map = canonicalize_normal_map
+        _rebind_importers('canonicalize_normal_map', o_cnm, canonicalize_normal_map)
+    if obj_io is not None:
+        keep(obj_io, 'save_mesh_as_ply')
+        obj_io.save_mesh_as_ply = mesh_io.save_mesh_as_ply
 
 
 def uninstall() -> None:

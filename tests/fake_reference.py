@@ -118,6 +118,31 @@ class SmplUtil:
         raise Fallthrough('SmplUtil.skinning_normal')
 
 
+class GLRenderer:
+    """utils/renderer.py Renderer: needs a GL context in the reference, so every use is a fall-through here."""
+    def __init__(self, img_w, img_h, mvp=None, shader_name='vertex_attribute', bg_color=(0, 0, 0), window_name=''):
+        self.img_w, self.img_h, self.shader_name = img_w, img_h, shader_name
+
+    def render(self):
+        raise Fallthrough('Renderer.render')
+
+
+def make_render_modules():
+    def render_cano_mesh(renderer, vertices, normals, faces, mesh_center=None, colors=None):
+        raise Fallthrough('render_cano_mesh')
+
+    def canonicalize_normal_map(pos_renderer, attri_renderer, *a, **k):
+        raise Fallthrough('canonicalize_normal_map')
+
+    def save_mesh_as_ply(path, vertices, faces=None, normals=None, colors=None):
+        raise Fallthrough('save_mesh_as_ply')
+    rm = types.ModuleType('utils.renderer'); rm.Renderer = GLRenderer
+    vis = types.ModuleType('utils.visualize_util'); vis.render_cano_mesh = render_cano_mesh
+    nf = types.ModuleType('normal_fusion.normal_fusion'); nf.canonicalize_normal_map = canonicalize_normal_map
+    oi = types.ModuleType('utils.obj_io'); oi.save_mesh_as_ply = save_mesh_as_ply
+    return {'utils.renderer': rm, 'utils.visualize_util': vis, 'normal_fusion.normal_fusion': nf, 'utils.obj_io': oi}
+
+
 def make_modules(frame, device='cpu'):
     def recon_mesh(occ_volume, volume_res, bounds, iso_value=0.5):
         raise Fallthrough('recon_mesh')
@@ -128,4 +153,6 @@ def make_modules(frame, device='cpu'):
     su = types.ModuleType('utils.smpl_util'); su.SmplUtil = SmplUtil
     su.smpl_util = SmplUtil(torch.from_numpy(frame['smpl_skinning_weights']).to(device))
     su.smpl_util.set_cano_smpl_vertices(torch.from_numpy(frame['cano_smpl_v']).to(device))
-    return {'network.arch_avatar': aa, 'network.arch_recon': ar, 'utils.recon_util': ru, 'utils.smpl_util': su}
+    mods = {'network.arch_avatar': aa, 'network.arch_recon': ar, 'utils.recon_util': ru, 'utils.smpl_util': su}
+    mods.update(make_render_modules())
+    return mods

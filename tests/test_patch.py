@@ -41,9 +41,49 @@ def test_install_rebinds_and_uninstall_restores(frame):
         # host tensors never reach the CUDA encoders
         with torch.no_grad(), pytest.raises(fr.Fallthrough):
             net.warping_field.precompute_conv({'smpl_pos_map': torch.zeros(1, 6, 256, 256)})
+        # render stage: phong previews stay on the (fake) GL renderer and the GL-renderer call paths fall through
+        R = mods['utils.renderer'].Renderer
+        gl = R(512, 512, shader_name='phong_geometry', bg_color=(1, 1, 1), window_name='Phong')
+        assert isinstance(gl, fr.GLRenderer) and gl.shader_name == 'phong_geometry'
+        with pytest.raises(fr.Fallthrough):
+            mods['utils.visualize_util'].render_cano_mesh(gl, None, None, None, np.zeros(3))
+        with pytest.raises(fr.Fallthrough):
+            mods['normal_fusion.normal_fusion'].canonicalize_normal_map(gl, gl, None)
+        # the PLY writer needs no GPU: same bytes as the reference's (golden made by utils/obj_io.py itself)
+        import tempfile
+        from helpers import load_golden
+        g = load_golden('ply_golden.npz')
+        with tempfile.TemporaryDirectory() as td:
+            mods['utils.obj_io'].save_mesh_as_ply(td + '/a.ply', g['v'], g['f'], g['n'], g['c'])
+            assert np.array_equal(np.frombuffer(open(td + '/a.ply', 'rb').read(), np.uint8), g['bytes_nc'])
     finally:
         patch.uninstall()
     assert all(getattr(c, n) is f for (c, n), f in orig.items()) and mods['utils.recon_util'].recon_mesh is orig_rm
+    assert mods['utils.renderer'].Renderer is fr.GLRenderer
+
+
+def test_install_rebinds_driver_module_copies(frame):
+    """main.py:19,21 copy `Renderer` / `canonicalize_normal_map` into the driver's namespace at import time"""
+    import types
+    from avatarcap_b200 import patch
+    mods = fr.make_modules(frame)
+    main = types.ModuleType('main')
+    main.Renderer = mods['utils.renderer'].Renderer
+    main.canonicalize_normal_map = mods['normal_fusion.normal_fusion'].canonicalize_normal_map
+    had = sys.modules.get('main')
+    sys.modules['main'] = main
+    try:
+        patch.install(engine=object(), modules=mods)
+        assert main.Renderer is mods['utils.renderer'].Renderer and main.Renderer is not fr.GLRenderer
+        assert main.canonicalize_normal_map is mods['normal_fusion.normal_fusion'].canonicalize_normal_map
+        patch.uninstall()
+        assert main.Renderer is fr.GLRenderer
+    finally:
+        patch.uninstall()
+        if had is None:
+            del sys.modules['main']
+        else:
+            sys.modules['main'] = had
 
 
 @pytest.mark.gpu
@@ -71,6 +111,14 @@ def test_patched_call_sites_run_on_the_library(frame):
             ref = eng.eval_occupancy(pts[0], frame['cano_smpl_center'])
             assert torch.equal(out['cano_pts_ov'][0, :, 0], ref['occ']) and torch.equal(out['nonrigid_offset'][0], ref['off'])
             off = net.warping_field.query(pts, batch); assert torch.equal(off[0], ref['off'])
+            # render stage through the patched names (main.py:330-331, 369, 408)
+            R = mods['utils.renderer'].Renderer
+            from avatarcap_b200 import render as render_mod
+            nr = R(128, 128, shader_name='vertex_attribute', window_name='Normal'); pr = R(128, 128, shader_name='position', window_name='Position')
+            assert isinstance(nr, render_mod.Renderer) and isinstance(pr, render_mod.Renderer) and nr.engine is eng
+            tri_v = np.array([[-0.5, -0.5, 0], [0.5, -0.5, 0], [0, 0.5, 0]], np.float32); tri_n = np.array([[0, 0, 1]] * 3, np.float32)
+            fimg, bimg = mods['utils.visualize_util'].render_cano_mesh(nr, tri_v, tri_n, np.array([[0, 1, 2]], np.int32), np.zeros(3))
+            assert fimg.shape == (128, 128, 3) and fimg[..., 2].max() == 1.0 and not bimg.any()        # the back view culls the triangle
             rgb, alpha, occ = net.cano_template(pts + off)
             assert tuple(rgb.shape) == (1, pts.shape[1], 3) and float((occ[0, :, 0] - ref['occ']).abs().max()) < 1e-4
             # reconstruction network: HGFilter through the graph encoder, decoder through the field kernel
