@@ -41,7 +41,7 @@ typedef struct avc_ctx avc_ctx;
 #define AVC_IMPL_AUTO   0     /* tensor-core kernel when available, else SIMT                  */
 #define AVC_IMPL_SIMT   1     /* fp32 CUDA-core kernel (bit-near the reference's fp32 math)    */
 #define AVC_IMPL_TC     2     /* tcgen05 kernel, fp16 hi/lo split operands, fp32 accumulate     */
-#define AVC_IMPL_TC2    3     /* experimental: the same kernel with cta_group::2 (CTA pairs share every MMA) */
+#define AVC_IMPL_TC2    3     /* the same kernel on CTA pairs (cta_group::2, M = 256 per MMA): what AUTO resolves to on sm_100 */
 
 /* implicit-field type, config.py:12-22 */
 #define AVC_IF_SDF        0

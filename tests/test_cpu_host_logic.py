@@ -124,6 +124,20 @@ def test_abi_header_matches_binding():
     assert lib.avc_abi_version() == 4
 
 
+def test_header_is_plain_c99_and_the_c_client_compiles():
+    """the drop-in boundary is a C ABI: include/avatarcap_b200.h and the C client tests/abi_smoke.c must compile as C99 (no C++ leaks)"""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    cuda_inc = os.path.join(os.environ.get('CUDA_HOME', '/usr/local/cuda'), 'include')
+    if not os.path.exists(os.path.join(cuda_inc, 'cuda_runtime_api.h')):
+        pytest.skip('no CUDA headers')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-fsyntax-only', '-I', os.path.join(ROOT, 'include'), '-isystem', cuda_inc,
+                        os.path.join(ROOT, 'tests', 'abi_smoke.c')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_engine_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip('has a GPU')

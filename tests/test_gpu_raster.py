@@ -162,3 +162,24 @@ def test_full_frame_with_fusion_stage(eng):
     rec = pipeline.recon_frame(eng, frame_dev, fmap, res, iso=0.5)
     assert rec['volume'].shape == res and torch.isfinite(rec['volume']).all()
     assert rec['live_verts'].shape == rec['verts'].shape
+
+
+def test_c_client_of_the_abi(tmp_path):
+    """tests/abi_smoke.c: a plain C99 program (no torch, no Python) drives grid, marching cubes, the rasteriser and the error paths"""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    if shutil.which('gcc') is None or not os.path.exists(os.path.join(cuda, 'include', 'cuda_runtime_api.h')):
+        pytest.skip('no gcc / CUDA headers on this box')
+    exe = str(tmp_path / 'abi_smoke')
+    libdir = os.path.join(root, 'avatarcap_b200')
+    cmd = ['gcc', '-std=c99', '-O1', os.path.join(root, 'tests', 'abi_smoke.c'), '-I', os.path.join(root, 'include'), '-I', os.path.join(cuda, 'include'),
+           '-L', libdir, '-lavatarcap_b200', '-L', os.path.join(cuda, 'lib64'), '-lcudart', '-lm', '-Wl,-rpath,' + libdir, '-Wl,-rpath,' + os.path.join(cuda, 'lib64'),
+           '-o', exe]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(r.stdout.strip(), r.stderr.strip())
+    assert r.returncode == 0 and 'abi_smoke ok' in r.stdout, r.stdout + r.stderr
