@@ -260,7 +260,7 @@ __device__ __forceinline__ void blend_mats(const float lbs[24], const float* s_m
 __global__ void __launch_bounds__(KNN_NT) lbs_weights_kernel(const float* __restrict__ pts, int64_t n, const float* __restrict__ cano_v, int m,
                                                              const float* __restrict__ skin_w, float* __restrict__ out_lbs, GridView V) {
   __shared__ float s_ref[KNN_TILE * 3];
-  const int64_t g = (int64_t)blockIdx.x * KNN_NT + threadIdx.x;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // block size is a launch-time knob (knn_block)
   const bool active = g < n;
   float qx = 0, qy = 0, qz = 0;
   if (active) { qx = pts[g * 3]; qy = pts[g * 3 + 1]; qz = pts[g * 3 + 2]; }
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(KNN_NT) skin_mesh_kernel(const float* __restri
   __shared__ float s_ref[KNN_TILE * 3];
   __shared__ float s_m[24 * 16];
   for (int t = threadIdx.x; t < 24 * 16; t += blockDim.x) s_m[t] = jm[t];
-  const int64_t g = (int64_t)blockIdx.x * KNN_NT + threadIdx.x;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // block size is a launch-time knob (knn_block)
   const bool active = g < n;
   float x = 0, y = 0, z = 0;
   if (active) { x = verts[g * 3]; y = verts[g * 3 + 1]; z = verts[g * 3 + 2]; }
@@ -386,6 +386,9 @@ __global__ void __launch_bounds__(KNN_NT) posed_to_cano_kernel(const float* __re
 }
 
 inline int nblocks(int64_t n) { return (int)((n + KNN_NT - 1) / KNN_NT); }
+// KNN-4 kernels end their grid search at a block-wide vote (cooperative fallback): smaller blocks wait less for their slowest thread
+inline int knn_block() { const char* e = getenv("AVC_KNN_BLOCK"); const int v = e ? atoi(e) : 0; return (v == 64 || v == 128 || v == 256) ? v : 256; }
+inline int nblocks_b(int64_t n, int b) { return (int)((n + b - 1) / b); }
 
 // (re)build the uniform grid over `ref` on the stream (4 tiny kernels); small sets keep the shared-memory brute force
 int build_grid(avc_ctx* ctx, const float* ref, int m, cudaStream_t st, GridView* gv) {
@@ -401,7 +404,7 @@ int build_grid(avc_ctx* ctx, const float* ref, int m, cudaStream_t st, GridView*
   char* base = (char*)ctx->d_grid;
   GridDesc* G = (GridDesc*)base; int* cnt = (int*)(base + 256); int* start = cnt + GRID_MAX_CELLS;
   float4* sorted = (float4*)(base + 256 + (size_t)GRID_MAX_CELLS * 4 + ((size_t)GRID_MAX_CELLS + 4) * 4);
-  static const float h_min = [] { const char* e = getenv("AVC_KNN_CELL"); const float v = e ? (float)atof(e) : 0.f; return v >= 0.01f && v <= 1.f ? v : 0.04f; }();   // tuning knob (metres)
+  const float h_min = [] { const char* e = getenv("AVC_KNN_CELL"); const float v = e ? (float)atof(e) : 0.f; return v >= 0.01f && v <= 1.f ? v : 0.04f; }();   // tuning knob (metres), read per call
   grid_bounds_kernel<<<1, 1024, 0, st>>>(ref, m, h_min, G, cnt);
   AVC_LAUNCH_CHECK(ctx, "grid_bounds_kernel");
   grid_count_kernel<<<(m + 255) / 256, 256, 0, st>>>(ref, m, G, cnt);
@@ -440,7 +443,8 @@ extern "C" int avc_lbs_weights(avc_ctx* ctx, const float* pts, int64_t n, const 
   if (n == 0) return AVC_OK;
   GridView gv; int rc = build_grid(ctx, cano_verts, m, (cudaStream_t)stream, &gv);
   if (rc) return rc;
-  lbs_weights_kernel<<<nblocks(n), KNN_NT, 0, (cudaStream_t)stream>>>(pts, n, cano_verts, m, skin_weights, out_lbs, gv);
+  const int kb = knn_block();
+  lbs_weights_kernel<<<nblocks_b(n, kb), kb, 0, (cudaStream_t)stream>>>(pts, n, cano_verts, m, skin_weights, out_lbs, gv);
   AVC_LAUNCH_CHECK(ctx, "lbs_weights_kernel");
   return AVC_OK;
 }
@@ -470,7 +474,8 @@ extern "C" int avc_skin_mesh(avc_ctx* ctx, const float* verts, const float* norm
   if (n == 0) return AVC_OK;
   GridView gv; int rc = build_grid(ctx, cano_verts, m, (cudaStream_t)stream, &gv);
   if (rc) return rc;
-  skin_mesh_kernel<<<nblocks(n), KNN_NT, 0, (cudaStream_t)stream>>>(verts, normals, n, cano_verts, m, skin_weights, jnt_mats, out_verts, out_normals, gv);
+  const int kb = knn_block();
+  skin_mesh_kernel<<<nblocks_b(n, kb), kb, 0, (cudaStream_t)stream>>>(verts, normals, n, cano_verts, m, skin_weights, jnt_mats, out_verts, out_normals, gv);
   AVC_LAUNCH_CHECK(ctx, "skin_mesh_kernel");
   return AVC_OK;
 }

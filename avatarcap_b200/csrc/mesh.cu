@@ -10,6 +10,7 @@
 // All of this is HBM-bound scan/compaction work: the volume is read with coalesced z-fastest accesses, warp
 // ballots/shuffles do the in-block scans, and the only intermediate is a 4 B/voxel vertex-base array.
 #include "common.cuh"
+#include <stdlib.h>
 #include "mc_tables.inc"
 
 namespace {
@@ -170,17 +171,22 @@ __global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(int* __restrict__ 
 }
 
 // pass C: vbase[v] = exclusive vertex prefix of voxel v (canonical order: voxel linear index, then axis)
-// Also compacts the sign-changing edges: edges[vid] = voxel*4 + axis, so that the vertex kernel runs one thread per vertex.
+// Also compacts the sign-changing edges: edges[vid] = voxel*4 + axis, so that the vertex kernel runs one thread per vertex, and
+// (tris != NULL) the triangles: tris[t] = voxel << 11 | case << 3 | triangle number, so that the face kernel runs one thread per
+// TRIANGLE instead of re-classifying every voxel with a tenth of the lanes doing the emission.
 __global__ void __launch_bounds__(MC_NT) mc_vbase_kernel(const float* __restrict__ vol, McDims d, const int* __restrict__ blk,
-                                                         int* __restrict__ vbase, long long* __restrict__ edges) {
+                                                         int* __restrict__ vbase, long long* __restrict__ edges, long long* __restrict__ tris) {
+  __shared__ unsigned char s_ntri[256];
+  stage_ntri(s_ntri);
   const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  int c[MC_VPT], cut[MC_VPT]; int nv = 0;
+  int c[MC_VPT], cut[MC_VPT], ccase[MC_VPT]; int nv = 0, nt = 0;
   Vox3 vc = vox_of(d, v0 < d.nvox ? v0 : 0);
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
     const VoxInfo r = classify(vol, d, v0 + q, vc);
     vox_next(d, vc);
     cut[q] = r.in_scan ? r.cut : 0; c[q] = __popc(cut[q]); nv += c[q];
+    ccase[q] = r.owned ? r.ccase : -1; if (ccase[q] >= 0) nt += s_ntri[ccase[q]];
   }
   int tot; int p = blk[3 * blockIdx.x] + block_excl_scan(nv, &tot);
 #pragma unroll
@@ -190,6 +196,15 @@ __global__ void __launch_bounds__(MC_NT) mc_vbase_kernel(const float* __restrict
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) if ((cut[q] >> ax) & 1) edges[e++] = (long long)(v0 + q) * 4 + ax;
     p += c[q];
+  }
+  if (tris) {
+    int tb = blk[3 * blockIdx.x + 2] + block_excl_scan(nt, &tot);
+#pragma unroll
+    for (int q = 0; q < MC_VPT; ++q) {
+      if (ccase[q] < 0) continue;
+      const int ntri = s_ntri[ccase[q]];
+      for (int tix = 0; tix < ntri; ++tix) tris[tb++] = ((long long)(v0 + q) << 11) | ((long long)ccase[q] << 3) | tix;
+    }
   }
 }
 
@@ -324,6 +339,37 @@ __global__ void __launch_bounds__(MC_NT) mc_faces_kernel(const float* __restrict
     }
     tbase += ntri;
   }
+}
+
+// pass D2': one thread per TRIANGLE (records written by mc_vbase_kernel): dense warps, no second classification of the volume
+__global__ void __launch_bounds__(MC_NT) mc_tris_kernel(const float* __restrict__ vol, McDims d, McEmit e, const long long* __restrict__ tris,
+                                                        const int* __restrict__ vbase, int64_t n_faces) {
+  __shared__ uint4 s_tri[256];                                      // 16 edge numbers per case
+  s_tri[threadIdx.x] = reinterpret_cast<const uint4*>(g_mc_tri)[threadIdx.x];
+  __syncthreads();
+  const int64_t f = (int64_t)blockIdx.x * MC_NT + threadIdx.x;
+  if (f >= n_faces) return;
+  const long long key = tris[f];
+  const int64_t v = key >> 11; const int cc = (int)((key >> 3) & 255), tix = (int)(key & 7);
+  const Vox3 c0 = vox_of(d, v);
+  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
+  const signed char* tri = reinterpret_cast<const signed char*>(&s_tri[cc]);
+  int ids[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int ed = tri[3 * tix + c];
+    const int corner = (int)((AVC_MC_EDGE_CORNER_NIBBLES >> (4 * ed)) & 0xF), ax = ed >> 2;
+    const int64_t ov = v + (corner & 1) * sx + ((corner >> 1) & 1) * sy + ((corner >> 2) & 1);
+    int rank = 0;                                                  // rank of `ax` among the owner voxel's cut edges (x < y < z)
+    if (ax > 0) {
+      const bool o0 = ldv(vol, ov) > d.iso;
+      const int oi = c0.i + (corner & 1), oj = c0.j + ((corner >> 1) & 1);
+      if (oi + 1 < d.rx && ((ldv(vol, ov + sx) > d.iso) != o0)) ++rank;
+      if (ax > 1 && oj + 1 < d.ry && ((ldv(vol, ov + sy) > d.iso) != o0)) ++rank;
+    }
+    ids[c] = vbase[ov] + rank;
+  }
+  e.faces[f * 3 + 0] = ids[2]; e.faces[f * 3 + 1] = ids[1]; e.faces[f * 3 + 2] = ids[0];   // faces[:, [2,1,0]]  recon_util.py:69
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -474,15 +520,20 @@ static int mc_emit_impl(avc_ctx* ctx, const float* vol, const int res[3], const 
   if (ctx->h_counts[0] > 0x7fffffffLL || nf > 0x7fffffffLL) return avc_fail(ctx, AVC_EINVAL, "mesh too large for int32 indices");
   if (nv == 0 && nf == 0) return AVC_OK;
   // compact edge list (8 B per vertex in the scan range), separate buffer so the scan scratch above stays valid
-  const size_t need_edges = (size_t)(ctx->h_counts[0] + 1) * sizeof(long long);
-  if (need_edges > ctx->scratch2_cap) {
+  // ... and the compact triangle list (8 B per face) behind it; AVC_MC_FACES=voxel selects the older per-voxel face pass (A/B knob)
+  const char* fmode = getenv("AVC_MC_FACES");
+  const bool per_triangle = !(fmode && strcmp(fmode, "voxel") == 0) && d.nvox < ((int64_t)1 << 52);
+  const size_t n_edges = (size_t)(ctx->h_counts[0] + 1);
+  const size_t need2 = (n_edges + (per_triangle ? (size_t)nf + 1 : 0)) * sizeof(long long);
+  if (need2 > ctx->scratch2_cap) {
     if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
     ctx->d_scratch2 = nullptr; ctx->scratch2_cap = 0;
-    AVC_CUDA(ctx, cudaMalloc(&ctx->d_scratch2, need_edges + (need_edges >> 3)));
-    ctx->scratch2_cap = need_edges + (need_edges >> 3);
+    AVC_CUDA(ctx, cudaMalloc(&ctx->d_scratch2, need2 + (need2 >> 3)));
+    ctx->scratch2_cap = need2 + (need2 >> 3);
   }
   long long* d_edges = reinterpret_cast<long long*>(ctx->d_scratch2);
-  mc_vbase_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk, d_vbase, d_edges);
+  long long* d_tris = per_triangle ? d_edges + n_edges : nullptr;
+  mc_vbase_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk, d_vbase, d_edges, d_tris);
   AVC_LAUNCH_CHECK(ctx, "mc_vbase_kernel");
   McEmit e;
   const int gres[3] = {gres_x, res[1], res[2]};
@@ -495,8 +546,15 @@ static int mc_emit_impl(avc_ctx* ctx, const float* vol, const int res[3], const 
     mc_verts_kernel<<<(unsigned)((nv + 127) / 128), 128, 0, st>>>(vol, d, e, d_edges, nv);
     AVC_LAUNCH_CHECK(ctx, "mc_verts_kernel");
   }
-  mc_faces_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, e, d_blk, d_vbase);
-  AVC_LAUNCH_CHECK(ctx, "mc_faces_kernel");
+  if (per_triangle) {
+    if (nf > 0) {
+      mc_tris_kernel<<<(unsigned)((nf + MC_NT - 1) / MC_NT), MC_NT, 0, st>>>(vol, d, e, d_tris, d_vbase, nf);
+      AVC_LAUNCH_CHECK(ctx, "mc_tris_kernel");
+    }
+  } else {
+    mc_faces_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, e, d_blk, d_vbase);
+    AVC_LAUNCH_CHECK(ctx, "mc_faces_kernel");
+  }
   return AVC_OK;
 }
 
