@@ -25,6 +25,7 @@ struct McDims {
   int scan_end;          // planes lo <= i < scan_end take part in the vertex scan (hi_excl, or hi_excl+1 with a hi halo)
   float iso;
   int64_t nvox;
+  int vec4;              // rz % 4 == 0 and a 16-byte aligned volume: a thread's 4 voxels are one float4 of one z-row (classify4)
 };
 
 __device__ __forceinline__ float ldv(const float* __restrict__ vol, int64_t idx) { return __ldg(vol + idx); }
@@ -71,6 +72,55 @@ __device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const
   return r;
 }
 
+// the same for a thread's MC_VPT = 4 consecutive voxels when they are one aligned float4 of a single z-row (d.vec4): 4 rows x
+// (float4 + the next element) instead of up to 8 scalar loads per voxel
+struct Vox4 { int cut[MC_VPT]; int ccase[MC_VPT]; bool in_scan, owned; };
+__device__ __forceinline__ void load_row5(const float* __restrict__ p, bool more, float iso, bool b[5]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  b[0] = v.x > iso; b[1] = v.y > iso; b[2] = v.z > iso; b[3] = v.w > iso;
+  b[4] = more ? (__ldg(p + 4) > iso) : false;
+}
+__device__ __forceinline__ void classify4(const float* __restrict__ vol, const McDims& d, int64_t v0, const Vox3& c, Vox4& r) {
+  r.in_scan = false; r.owned = false;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) { r.cut[q] = 0; r.ccase[q] = -1; }
+  if (v0 >= d.nvox) return;
+  if (c.i < d.lo || c.i >= d.scan_end) return;
+  r.in_scan = true; r.owned = c.i < d.hi_excl;
+  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
+  const bool hx = c.i + 1 < d.rx, hy = c.j + 1 < d.ry, hz3 = c.k + 4 < d.rz;       // voxels q < 3 always have a +z neighbour in the row
+  bool A[5], B[5], C[5], E[5];
+  load_row5(vol + v0, hz3, d.iso, A);
+#pragma unroll
+  for (int q = 0; q < 5; ++q) { B[q] = false; C[q] = false; E[q] = false; }
+  if (hx) load_row5(vol + v0 + sx, hz3, d.iso, B);
+  if (hy) load_row5(vol + v0 + sy, hz3, d.iso, C);
+  const bool cells = r.owned && hx && hy;
+  if (cells) load_row5(vol + v0 + sx + sy, hz3, d.iso, E);
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) {
+    const bool hz = q < 3 || hz3;
+    r.cut[q] = ((hx && B[q] != A[q]) ? 1 : 0) | ((hy && C[q] != A[q]) ? 2 : 0) | ((hz && A[q + 1] != A[q]) ? 4 : 0);
+    if (cells && hz)
+      r.ccase[q] = (int)A[q] | ((int)B[q] << 1) | ((int)C[q] << 2) | ((int)E[q] << 3) | ((int)A[q + 1] << 4) | ((int)B[q + 1] << 5) |
+                   ((int)C[q + 1] << 6) | ((int)E[q + 1] << 7);
+  }
+}
+// classification of a thread's 4 voxels by either path
+__device__ __forceinline__ void classify_thread(const float* __restrict__ vol, const McDims& d, int64_t v0, Vox4& r) {
+  Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
+  if (d.vec4) { classify4(vol, d, v0, c, r); return; }
+  r.in_scan = false; r.owned = false;
+#pragma unroll
+  for (int q = 0; q < MC_VPT; ++q) {
+    const VoxInfo x = classify(vol, d, v0 + q, c);
+    vox_next(d, c);
+    // per-voxel flags folded into the values: cut counts only inside the scan range, the case only for owned cells
+    r.cut[q] = x.in_scan ? x.cut : 0; r.ccase[q] = x.owned ? x.ccase : -1;
+    r.in_scan = r.in_scan || x.in_scan; r.owned = r.owned || x.owned;
+  }
+}
+
 // triangle counts per case, staged once per CTA (MC_NT == 256 threads == 256 cases)
 __device__ __forceinline__ void stage_ntri(unsigned char* s_ntri) {
   s_ntri[threadIdx.x] = g_mc_ntri[threadIdx.x];
@@ -99,15 +149,25 @@ __global__ void __launch_bounds__(MC_NT) mc_count_kernel(const float* __restrict
   __shared__ unsigned char s_ntri[256];
   stage_ntri(s_ntri);
   const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
   int nv = 0, nvo = 0, nt = 0;
+  if (d.vec4) {
+    Vox4 r; classify4(vol, d, v0, vox_of(d, v0 < d.nvox ? v0 : 0), r);
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) {
-    const VoxInfo r = classify(vol, d, v0 + q, c);
-    vox_next(d, c);
-    const int n = __popc(r.cut);
-    if (r.in_scan) nv += n;
-    if (r.owned) { nvo += n; if (r.ccase >= 0) nt += s_ntri[r.ccase]; }
+    for (int q = 0; q < MC_VPT; ++q) {
+      const int n = __popc(r.cut[q]);
+      nv += n;                                         // cut is 0 outside the scan range
+      if (r.owned) { nvo += n; if (r.ccase[q] >= 0) nt += s_ntri[r.ccase[q]]; }
+    }
+  } else {
+    Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
+#pragma unroll
+    for (int q = 0; q < MC_VPT; ++q) {
+      const VoxInfo r = classify(vol, d, v0 + q, c);
+      vox_next(d, c);
+      const int n = __popc(r.cut);
+      if (r.in_scan) nv += n;
+      if (r.owned) { nvo += n; if (r.ccase >= 0) nt += s_ntri[r.ccase]; }
+    }
   }
   // the three counts fit one word each only loosely (nt <= 20, nv <= 12 per thread): reduce them packed, 10 bits apart would overflow
   // at 256 threads, so use two warp-shuffle reductions on a 64-bit word (21 bits per field)
@@ -180,13 +240,13 @@ __global__ void __launch_bounds__(MC_NT) mc_vbase_kernel(const float* __restrict
   stage_ntri(s_ntri);
   const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
   int c[MC_VPT], cut[MC_VPT], ccase[MC_VPT]; int nv = 0, nt = 0;
-  Vox3 vc = vox_of(d, v0 < d.nvox ? v0 : 0);
+  {
+    Vox4 r; classify_thread(vol, d, v0, r);
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) {
-    const VoxInfo r = classify(vol, d, v0 + q, vc);
-    vox_next(d, vc);
-    cut[q] = r.in_scan ? r.cut : 0; c[q] = __popc(cut[q]); nv += c[q];
-    ccase[q] = r.owned ? r.ccase : -1; if (ccase[q] >= 0) nt += s_ntri[ccase[q]];
+    for (int q = 0; q < MC_VPT; ++q) {
+      cut[q] = r.cut[q]; c[q] = __popc(cut[q]); nv += c[q];
+      ccase[q] = r.ccase[q]; if (ccase[q] >= 0) nt += s_ntri[ccase[q]];
+    }
   }
   int tot; int p = blk[3 * blockIdx.x] + block_excl_scan(nv, &tot);
 #pragma unroll
@@ -420,7 +480,7 @@ int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi
   if (halo_lo < 0 || halo_hi < 0 || halo_lo + halo_hi >= res[0]) return avc_fail(ctx, AVC_EINVAL, "bad halo widths");
   d->rx = res[0]; d->ry = res[1]; d->rz = res[2];
   d->lo = halo_lo; d->hi_excl = res[0] - halo_hi; d->scan_end = halo_hi > 0 ? d->hi_excl + 1 : d->hi_excl;
-  d->iso = iso; d->nvox = (int64_t)res[0] * res[1] * res[2];
+  d->iso = iso; d->nvox = (int64_t)res[0] * res[1] * res[2]; d->vec4 = 0;
   if (d->nvox > (int64_t)1 << 40) return avc_fail(ctx, AVC_EINVAL, "volume too large");
   *nblk = (int)((d->nvox + MC_VPB - 1) / MC_VPB);
   const size_t need = (size_t)*nblk * 3 * sizeof(int) + 64 + (size_t)d->nvox * sizeof(int) + 256;
@@ -467,6 +527,11 @@ extern "C" int avc_scatter_fill(avc_ctx* ctx, const uint8_t* flag, int64_t n_tot
   return AVC_OK;
 }
 
+// float4 classification path: every thread's 4 voxels must be one aligned float4 inside a single z-row (AVC_MC_SCALAR=1 forces the scalar path)
+static int mc_vec4_ok(const float* vol, const int res[3]) {
+  return ((res[2] & 3) == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0 && !getenv("AVC_MC_SCALAR")) ? 1 : 0;
+}
+
 static int mc_run_count(avc_ctx* ctx, const float* vol, const McDims& d, int nblk, int* d_blk, int64_t* d_tot, cudaStream_t st) {
   mc_count_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk);
   AVC_LAUNCH_CHECK(ctx, "mc_count_kernel");
@@ -483,6 +548,7 @@ extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], fl
   McDims d; int nblk; int* d_blk; int64_t* d_tot; int* d_vbase;
   int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);
   if (rc) return rc;
+  d.vec4 = mc_vec4_ok(vol, res);
   rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, (cudaStream_t)stream);
   if (rc) return rc;
   *n_verts = ctx->h_counts[1]; *n_faces = ctx->h_counts[2];
@@ -507,6 +573,7 @@ static int mc_emit_impl(avc_ctx* ctx, const float* vol, const int res[3], const 
   McDims d; int nblk; int* d_blk; int64_t* d_tot; int* d_vbase;
   int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);     // same size as for the count: no reallocation
   if (rc) return rc;
+  d.vec4 = mc_vec4_ok(vol, res);
   if (reuse) {
     for (int c = 0; c < 3; ++c) ctx->h_counts[c] = counts[c];
   } else {

@@ -37,14 +37,19 @@ out = {}
 for name, vol in vols.items():
     r = {}
     ref = None
-    for mode in ('voxel', 'triangle'):
-        os.environ['AVC_MC_FACES'] = mode
+    for mode in ('voxel', 'triangle', 'triangle+scalar'):
+        os.environ['AVC_MC_FACES'] = mode.split('+')[0]
+        if mode.endswith('scalar'):
+            os.environ['AVC_MC_SCALAR'] = '1'
+        else:
+            os.environ.pop('AVC_MC_SCALAR', None)
         r['mesh_ms_' + mode] = t(lambda: eng.extract_mesh(vol, fr['cano_bounds'], 0.0))
         m = eng.extract_mesh(vol, fr['cano_bounds'], 0.0)
         if ref is None:
             ref = [x.clone() for x in m]
         else:
             r['identical'] = all(torch.equal(a, b) for a, b in zip(ref, m))
+    os.environ.pop('AVC_MC_SCALAR', None); os.environ.pop('AVC_MC_FACES', None)
     v, f, n = ref
     r['verts'] = int(v.shape[0])
     for kb in ('256', '128', '64'):

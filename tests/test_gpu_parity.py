@@ -262,15 +262,28 @@ def test_mesh_normals_vs_reference_golden(eng):
     assert maxabs(n.cpu().numpy(), ref) < 5e-4
 
 
-def test_mesh_slabs_equal_whole(eng):
-    """multi-GPU seam rule: slabs along x with (2,3) halo planes reproduce the single-volume mesh exactly"""
+@pytest.mark.parametrize('res', [(37, 20, 22), (37, 20, 24)])
+def test_mesh_slabs_equal_whole(eng, res):
+    """multi-GPU seam rule: slabs along x with (2,3) halo planes reproduce the single-volume mesh exactly
+    (Rz = 22: scalar classification; Rz = 24: the float4 path) -- and both equal the CPU oracle"""
+    import os
     from avatarcap_b200 import shard
+    from oracle import mesh_oracle as mo
     rs = np.random.RandomState(4)
-    res = (37, 20, 22)
     ii, jj, kk = np.meshgrid(*[np.arange(r) for r in res], indexing='ij')
     vol = (9.0 - np.sqrt((ii - 18) ** 2 + (jj - 10) ** 2 + (kk - 11) ** 2) + 0.8 * rs.normal(0, 1, res)).astype(np.float32)
     bounds = np.array([[-0.9, -1.0, -0.35], [0.95, 0.9, 0.3]], np.float32)
     v, f, n = eng.extract_mesh(torch.from_numpy(vol), bounds, 0.0)
+    rv, rf, rn = mo.recon_mesh(vol, res, bounds, 0.0)
+    assert np.array_equal(f.cpu().numpy(), rf) and maxabs(v.cpu().numpy(), rv) < 1e-6
+    # the A/B knobs select the older code paths: same mesh bit for bit
+    for knob in ('AVC_MC_SCALAR', 'AVC_MC_FACES'):
+        os.environ[knob] = '1' if knob == 'AVC_MC_SCALAR' else 'voxel'
+        try:
+            v2, f2, n2 = eng.extract_mesh(torch.from_numpy(vol), bounds, 0.0)
+        finally:
+            del os.environ[knob]
+        assert torch.equal(v2, v) and torch.equal(f2, f) and torch.equal(n2, n)
     for world in (2, 3, 5):
         parts = []
         for r in range(world):
