@@ -62,8 +62,8 @@ __device__ __forceinline__ void knn_scan(const float* __restrict__ ref, int m, f
 // at least r*h away (projection onto the grid box is non-expansive), so the search stops as soon as the K-th best squared
 // distance is <= (r*h)^2; queries that are far from every vertex fall back to a scan of the whole set.
 constexpr int GRID_MAX_CELLS = 1 << 18;
-constexpr int GRID_RMAX = 3;
-struct GridDesc { float ox, oy, oz, h, inv_h; int dx, dy, dz, m, cells; };
+constexpr int GRID_RMAX = 8;    // default number of shells before the brute-force fallback (AVC_KNN_RMAX overrides, 1..12)
+struct GridDesc { float ox, oy, oz, h, inv_h; int dx, dy, dz, m, cells, rmax; };
 
 __device__ __forceinline__ int grid_cell(const GridDesc& G, float x, float y, float z, int& cx, int& cy, int& cz) {
   cx = min(max((int)floorf((x - G.ox) * G.inv_h), 0), G.dx - 1);
@@ -72,7 +72,7 @@ __device__ __forceinline__ int grid_cell(const GridDesc& G, float x, float y, fl
   return (cx * G.dy + cy) * G.dz + cz;
 }
 
-__global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restrict__ ref, int m, float h_min, GridDesc* __restrict__ G, int* __restrict__ cnt) {
+__global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restrict__ ref, int m, float h_min, int rmax, GridDesc* __restrict__ G, int* __restrict__ cnt) {
   __shared__ float s_mn[3][32], s_mx[3][32];
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
   for (int i = threadIdx.x; i < m; i += blockDim.x)
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restri
     g.h = fmaxf(h_min, ext / 60.f); g.inv_h = 1.f / g.h;
     g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
     g.dx = (int)floorf((mx[0] - mn[0]) * g.inv_h) + 1; g.dy = (int)floorf((mx[1] - mn[1]) * g.inv_h) + 1; g.dz = (int)floorf((mx[2] - mn[2]) * g.inv_h) + 1;
-    g.m = m; g.cells = g.dx * g.dy * g.dz;          // <= 61^3 < GRID_MAX_CELLS
+    g.rmax = rmax; g.m = m; g.cells = g.dx * g.dy * g.dz;          // <= 61^3 < GRID_MAX_CELLS
     *G = g;
   }
   for (int i = threadIdx.x; i < GRID_MAX_CELLS; i += blockDim.x) cnt[i] = 0;
@@ -162,7 +162,7 @@ __device__ __forceinline__ bool knn_grid(const GridView& V, float qx, float qy, 
       knn_visit_run<K>(V, G, i, j, max(cz - 1, 0), min(cz + 1, G.dz - 1), qx, qy, qz, best);
   float rh = G.h * 0.999f;                         // 0.1 % slack for the float rounding of the cell assignment
   bool done = best.d[K - 1] <= rh * rh;
-  for (int r = 2; r <= GRID_RMAX && !done; ++r) {
+  for (int r = 2; r <= G.rmax && !done; ++r) {
     for (int i = max(cx - r, 0); i <= min(cx + r, G.dx - 1); ++i)
       for (int j = max(cy - r, 0); j <= min(cy + r, G.dy - 1); ++j) {
         if ((abs(i - cx) == r) || (abs(j - cy) == r)) {            // a row of the shell's side faces: the whole z-run
@@ -405,7 +405,8 @@ int build_grid(avc_ctx* ctx, const float* ref, int m, cudaStream_t st, GridView*
   GridDesc* G = (GridDesc*)base; int* cnt = (int*)(base + 256); int* start = cnt + GRID_MAX_CELLS;
   float4* sorted = (float4*)(base + 256 + (size_t)GRID_MAX_CELLS * 4 + ((size_t)GRID_MAX_CELLS + 4) * 4);
   const float h_min = [] { const char* e = getenv("AVC_KNN_CELL"); const float v = e ? (float)atof(e) : 0.f; return v >= 0.01f && v <= 1.f ? v : 0.04f; }();   // tuning knob (metres), read per call
-  grid_bounds_kernel<<<1, 1024, 0, st>>>(ref, m, h_min, G, cnt);
+  const int rmax = [] { const char* e = getenv("AVC_KNN_RMAX"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 12 ? v : GRID_RMAX; }();
+  grid_bounds_kernel<<<1, 1024, 0, st>>>(ref, m, h_min, rmax, G, cnt);
   AVC_LAUNCH_CHECK(ctx, "grid_bounds_kernel");
   grid_count_kernel<<<(m + 255) / 256, 256, 0, st>>>(ref, m, G, cnt);
   AVC_LAUNCH_CHECK(ctx, "grid_count_kernel");

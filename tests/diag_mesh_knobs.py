@@ -37,7 +37,7 @@ out = {}
 for name, vol in vols.items():
     r = {}
     ref = None
-    for mode in ('voxel', 'triangle', 'triangle+scalar'):
+    for mode in ('triangle',):
         os.environ['AVC_MC_FACES'] = mode.split('+')[0]
         if mode.endswith('scalar'):
             os.environ['AVC_MC_SCALAR'] = '1'
@@ -49,12 +49,17 @@ for name, vol in vols.items():
             ref = [x.clone() for x in m]
         else:
             r['identical'] = all(torch.equal(a, b) for a, b in zip(ref, m))
+    ref = ref or [x.clone() for x in m]
     os.environ.pop('AVC_MC_SCALAR', None); os.environ.pop('AVC_MC_FACES', None)
     v, f, n = ref
     r['verts'] = int(v.shape[0])
-    for kb in ('256', '128', '64'):
+    for kb in ('256',):
         os.environ['AVC_KNN_BLOCK'] = kb
         r['skin_ms_b' + kb] = t(lambda: eng.skin_mesh(v, n, cv, sw, jm))
     os.environ.pop('AVC_KNN_BLOCK')
+    for rm in ('2', '3', '4', '5', '6', '8'):
+        os.environ['AVC_KNN_RMAX'] = rm
+        r['skin_ms_rmax' + rm] = t(lambda: eng.skin_mesh(v, n, cv, sw, jm), 3)
+    os.environ.pop('AVC_KNN_RMAX')
     out[name] = r
 print(json.dumps(out))

@@ -461,8 +461,15 @@ def test_near_flag_and_grid_knn_far_queries(eng, scene):
     bmin, bmax = fr['cano_bounds']
     q = (rs.uniform(0, 1, (20000, 3)) * (bmax - bmin) * 1.6 + bmin - 0.3 * (bmax - bmin)).astype(np.float32)     # many far outside the body
     rd, ri = fo.knn_points(torch.from_numpy(q), torch.from_numpy(fr['cano_smpl_v']), 4)
-    d2, idx = eng.knn(q, fr['cano_smpl_v'], 4)
-    assert np.array_equal(idx.cpu().numpy(), ri.numpy()) and np.array_equal(d2.cpu().numpy(), rd.numpy())
+    import os
+    for rmax in (None, '1', '3', '12'):                  # shells walked before the brute-force fallback: the result must not depend on it
+        if rmax is not None:
+            os.environ['AVC_KNN_RMAX'] = rmax
+        try:
+            d2, idx = eng.knn(q, fr['cano_smpl_v'], 4)
+        finally:
+            os.environ.pop('AVC_KNN_RMAX', None)
+        assert np.array_equal(idx.cpu().numpy(), ri.numpy()) and np.array_equal(d2.cpu().numpy(), rd.numpy())
     for radius in (0.1, 0.08, 0.03):
         flag = eng.near_flag(q, fr['cano_smpl_v'], radius).cpu().numpy()
         assert np.array_equal(flag, (rd[:, 0] < radius ** 2).numpy())            # torch semantics: float32(radius ** 2)
