@@ -1,23 +1,24 @@
-// EXPERIMENTAL cta_group::2 variant of field_tc.cu (AVC_IMPL_TC2): two CTAs of a cluster (= two SMs of a TPC) share every MMA.
-// The leader CTA issues tcgen05.mma.cta_group::2 with M = 256 (128 points per CTA); each CTA streams only HALF of every weight
-// slab (N/2 rows), so shared-memory B traffic, L2->SM weight traffic and the number of MMA instructions per SM all halve.
-// Everything else (TMEM in-place activations, N-half schedule, op program) is identical to field_tc.cu.
-// tcgen05 (5th-gen tensor core) implementation of the fused per-point networks for sm_100a.
+// tcgen05 (5th-gen tensor core) implementation of the fused per-point networks for sm_100a -- the product path (AVC_IMPL_TC2, what
+// AVC_IMPL_AUTO resolves to on a B200). field_tc.cu is the single-CTA kernel this one grew out of (AVC_IMPL_TC).
 //
-// One persistent CTA per SM evaluates 128-point tiles through the whole network:
-//   * every fully-connected layer is a chain of tcgen05.mma (M=128 points, N<=256 channels, K=16 per instruction),
-//     fp32 accumulators in TMEM;
-//   * operands are fp16 hi/lo pairs (x = hi + lo to ~2^-22): each product is 3 MMAs (hi*hi + lo*hi + hi*lo), which keeps the
+// Two CTAs of a cluster (= the two SMs of a TPC) evaluate a PAIR of 128-point tiles through the whole network:
+//   * every fully-connected layer is a chain of tcgen05.mma.cta_group::2 (M = 256: 128 points per CTA, N <= 256 channels issued as
+//     N = 128 halves, K = 16 per instruction) issued by the leader CTA, fp32 accumulators in TMEM; each CTA streams only HALF of every
+//     weight slab, so L2->SM weight traffic and MMA instructions per SM halve against the single-CTA kernel;
+//   * operands are fp16 hi/lo pairs (x = hi + lo to ~2^-22): each product is 3 MMAs (hi*hi + hi*lo + lo*hi), which keeps the
 //     field within the reference's 1e-4 tolerance where a single bf16/fp16/tf32 pass cannot (BASELINE.md precision probe);
-//   * activations NEVER leave the SM: the epilogue warps read the fp32 accumulator chunk from TMEM (tcgen05.ld), apply
-//     scale/bias/activation, split into fp16 hi/lo and write it back IN PLACE (tcgen05.st) as the A operand (TS-mode MMA) of the
-//     next layer -- 64 fp32 accumulator columns become exactly 32 hi + 32 lo packed columns. The two 256-column halves of TMEM
-//     ping-pong between "A of layer l" and "D of layer l";
-//   * weights stream from L2 through an 8-stage shared-memory ring filled by the bulk-copy engine (cp.async.bulk, pre-packed by
-//     packer.py in the canonical K-major core-matrix layout, so no tensor map / swizzle is needed);
-//   * the skip-connection inputs (bilinear feature gather / positional encoding) live in shared memory as SS-mode A operands.
-// Roles: warps 0-7 compute/epilogue (warp w owns TMEM lanes 32*(w%4)..+31, i.e. 32 points; warps w and w+4 split the columns),
-//        warp 8 lane 0 issues MMAs, warp 9 lane 0 streams weights.
+//   * activations NEVER leave the SM: the epilogue warps read the fp32 accumulator from TMEM (tcgen05.ld, 16-column pieces, software
+//     pipelined), apply scale/bias/activation, split into fp16 hi / negated lo and write it back IN PLACE (tcgen05.st) as the A operand
+//     (TS-mode MMA) of the next layer -- 32 fp32 accumulator columns become 16 hi + 16 lo packed columns. The two 256-column halves of
+//     TMEM ping-pong between "A of layer l" and "D of layer l";
+//   * weights stream from L2 through a 4-stage shared-memory ring filled by the bulk-copy engine (cp.async.bulk; packer.py stores each
+//     layer as a stream in exactly the order and canonical K-major core-matrix layout the ring consumes: no tensor map, no swizzle);
+//   * the skip-connection inputs (bilinear feature gather / positional encoding) live in shared memory as SS-mode A operands; the next
+//     tile's gather is prefetched into a second buffer during the current tile's accumulator waits;
+//   * the <= 3-output heads (offsets, geometry, colour, recon) are evaluated on the CUDA cores inside the preceding epilogue.
+// Roles (352 threads): warps 0-7 compute/epilogue (warp w owns TMEM lanes 32*(w%4)..+31, i.e. 32 points; warps w and w+4 alternate
+//        column chunks), warps 8-9 alternate as MMA issuers on the leader CTA (the peer's warp 8 relays its ring barriers), warp 10
+//        streams weights. All roles walk one op program built on the host (build_ops). DESIGN.md 4.1 / 4.1b has the measured history.
 //
 // Reference call sites restated: see field_simt.cu (same networks, same order of operations per layer).
 #include "common.cuh"
@@ -29,7 +30,7 @@
 namespace {
 
 constexpr int TILE = 128;                 // points per tile == UMMA M
-constexpr int NT = 352;                   // 8 compute warps + 2 alternating MMA-issuer warps + producer warp
+constexpr int NT = 352;                   // 8 compute warps + 2 alternating MMA-issuer warps + weight-producer warp
 constexpr int N_STAGES = 4;
 constexpr int STAGE_KSTEPS = 4;           // k-steps per ring stage (== two 32-column A chunks)
 constexpr int STAGE_BYTES = STAGE_KSTEPS * 4096;   // per k-step of one N-half, THIS CTA's 64 of the 128 weight rows: hi 2 KB + lo 2 KB
