@@ -39,3 +39,21 @@ def tpose_scene(map_hw=256):
 
 def maxabs(a, b):
     return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)))) if np.size(a) else 0.0
+
+
+def uv_sphere(center, radius, n_lat=24, n_lon=32):
+    """Closed, outward-oriented UV sphere (verts (V,3) f32, faces (F,3) i32)."""
+    th = np.linspace(0, np.pi, n_lat + 1)[1:-1]; ph = np.linspace(0, 2 * np.pi, n_lon, endpoint=False)
+    v = [[0, 0, 1]] + [[np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(t)] for t in th for p in ph] + [[0, 0, -1]]
+    v = np.asarray(v) * radius + np.asarray(center)
+    f = []
+    for j in range(n_lon):
+        f.append([0, 1 + j, 1 + (j + 1) % n_lon])
+    for i in range(n_lat - 2):
+        for j in range(n_lon):
+            a = 1 + i * n_lon + j; b = 1 + i * n_lon + (j + 1) % n_lon; c = a + n_lon; d = b + n_lon
+            f += [[a, c, b], [b, c, d]]
+    last = len(v) - 1; base = 1 + (n_lat - 2) * n_lon
+    for j in range(n_lon):
+        f.append([last, base + (j + 1) % n_lon, base + j])
+    return v.astype(np.float32), np.asarray(f, np.int32)

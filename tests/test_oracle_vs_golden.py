@@ -159,3 +159,36 @@ def test_nerf_render_vertex_colours(scene):
     assert maxabs(o['raw'], g['raw']) < 2e-5
     assert maxabs(o['rgb_map'], g['rgb_map']) < 2e-5 and maxabs(o['acc_map'], g['acc_map']) < 2e-5 and maxabs(o['depth_map'], g['depth_map']) < 2e-5
     assert g['acc_map'].max() > 0.9 and (g['acc_map'] > 0.05).mean() > 0.05                           # the compositing is exercised
+
+
+def test_contains_points_oracle_on_analytic_shapes():
+    """trimesh.contains (avatarcap_dataset.py:120-123) is a third-party routine that is not installed: the ray-parity restatement is
+    pinned by shapes whose inside is known in closed form -- spheres (any orientation of the faces), a box with grid points exactly on
+    its faces' projections, nested and disjoint components."""
+    from helpers import uv_sphere
+    from oracle import field_oracle as fo
+    bounds = np.array([[-0.9, -1.0, -0.35], [0.95, 0.9, 0.3]], np.float32)
+    res = (30, 34, 18)
+    pts = fo.generate_volume_points(bounds, res)
+    c1, r1, c2, r2 = np.array([0.1, -0.2, 0.0]), 0.27, np.array([-0.45, 0.5, 0.05]), 0.2
+    v1, f1 = uv_sphere(c1, r1); v2, f2 = uv_sphere(c2, r2, 16, 20)
+    verts = np.concatenate([v1, v2], 0); faces = np.concatenate([f1, f2[:, ::-1] + len(v1)], 0)     # second sphere wound the other way
+    ins = mo.contains_points(verts, faces, pts)
+    d1 = np.linalg.norm(pts - c1, axis=1); d2 = np.linalg.norm(pts - c2, axis=1)
+    assert ins[(d1 < 0.93 * r1) | (d2 < 0.9 * r2)].all() and not ins[(d1 > 1.01 * r1) & (d2 > 1.01 * r2)].any() and ins.sum() > 50
+    # a hollow shell: points inside the inner sphere are outside the solid (two crossings)
+    vi, fi = uv_sphere(c1, 0.12)
+    shell = mo.contains_points(np.concatenate([v1, vi], 0), np.concatenate([f1, fi + len(v1)], 0), pts)
+    assert not shell[d1 < 0.1].any() and shell[(d1 > 0.14) & (d1 < 0.24)].all()
+    # axis-aligned box whose faces pass exactly through grid columns: every column is counted once (top-left rule), half-open in x, y
+    gx = np.unique(pts[:, 0]); gy = np.unique(pts[:, 1])
+    x0, x1, y0, y1, z0, z1 = gx[5], gx[12], gy[7], gy[20], -0.2, 0.17
+    bv = np.array([[x, y, z] for x in (x0, x1) for y in (y0, y1) for z in (z0, z1)], np.float64)
+    bf = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4], [1, 5, 7], [1, 7, 3]])
+    box = mo.contains_points(bv, bf, pts)
+    strictly = (pts[:, 0] > x0) & (pts[:, 0] < x1) & (pts[:, 1] > y0) & (pts[:, 1] < y1) & (pts[:, 2] > z0) & (pts[:, 2] < z1)
+    closed = (pts[:, 0] >= x0) & (pts[:, 0] <= x1) & (pts[:, 1] >= y0) & (pts[:, 1] <= y1) & (pts[:, 2] > z0) & (pts[:, 2] < z1)
+    assert box[strictly].all() and not box[~closed].any()
+    on_edge = closed & ~strictly
+    cols = box[on_edge]
+    assert 0 < cols.sum() < cols.size                     # boundary columns belong to exactly one side, not to both or neither
