@@ -299,6 +299,16 @@ def test_mesh_slabs_equal_whole(eng, res):
 
 
 # --------------------------------------------------------------------------------------------- BASELINE configs
+_ORACLE_CACHE = {}
+
+
+def _cached(key, fn):
+    """the CPU oracle is by far the slowest part of these tests: evaluate it once per configuration, not once per implementation"""
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = fn()
+    return _ORACLE_CACHE[key]
+
+
 @pytest.mark.parametrize('impl', IMPLS)
 def test_config1_dense_64(eng, impl):
     """BASELINE config 1: T-pose body, 64^3 dense grid, occupancy vs the CPU oracle (restated reference)."""
@@ -310,7 +320,7 @@ def test_config1_dense_64(eng, impl):
     fr = s['frame']
     pts = eng.make_grid(fr['cano_bounds'], (64, 64, 64))
     o = eng.eval_occupancy(pts, fr['cano_smpl_center'], impl=impl)
-    ref = fo.occupancy_query(s['avatar_sd'], pts.cpu().numpy(), s['pose_map'], fr['cano_smpl_center'])
+    ref = _cached('config1', lambda: fo.occupancy_query(s['avatar_sd'], pts.cpu().numpy(), s['pose_map'], fr['cano_smpl_center']))
     err = maxabs(o['occ'].cpu().numpy(), ref['cano_pts_ov'][:, 0])
     print('config1 %s: occ max-abs err %.3g (range %.3g..%.3g), off err %.3g' % (
         impl, err, ref['cano_pts_ov'].min(), ref['cano_pts_ov'].max(), maxabs(o['off'].cpu().numpy(), ref['nonrigid_offset'])))
@@ -326,7 +336,7 @@ def test_config1_dense_64(eng, impl):
     from oracle import mesh_oracle as mo
     vol_g = o['occ'].reshape(64, 64, 64)
     v, f, n = eng.extract_mesh(vol_g, fr['cano_bounds'], 0.0)
-    rv, rf, rn = mo.recon_mesh(ref['cano_pts_ov'][:, 0].reshape(64, 64, 64), (64, 64, 64), fr['cano_bounds'], 0.0)
+    rv, rf, rn = _cached('config1_mesh', lambda: mo.recon_mesh(ref['cano_pts_ov'][:, 0].reshape(64, 64, 64), (64, 64, 64), fr['cano_bounds'], 0.0))
     assert abs(v.shape[0] - rv.shape[0]) <= 1e-3 * rv.shape[0] + 1
     assert mo.chamfer(v.cpu().numpy(), rv) < 1e-3
 
@@ -350,7 +360,7 @@ def test_config2_dense_256_properties(eng, impl):
     sel_t = torch.from_numpy(sel).to(eng.device)
     sub = eng.eval_occupancy(pts[sel_t], fr['cano_smpl_center'], impl=impl)
     assert maxabs(sub['occ'].cpu().numpy(), o['occ'][sel_t].cpu().numpy()) < 2e-6
-    ref = fo.occupancy_query(s['avatar_sd'], pts[sel_t].cpu().numpy(), s['pose_map'], fr['cano_smpl_center'], with_texture=True)
+    ref = _cached('config2', lambda: fo.occupancy_query(s['avatar_sd'], pts[sel_t].cpu().numpy(), s['pose_map'], fr['cano_smpl_center'], with_texture=True))
     assert maxabs(o['occ'][sel_t].cpu().numpy(), ref['cano_pts_ov'][:, 0]) < 1e-4
     assert maxabs(o['rgb'][sel_t].cpu().numpy(), ref['rgb']) < 1e-5
     assert maxabs(o['alpha'][sel_t].cpu().numpy(), ref['alpha'][:, 0]) < 1e-4 * max(1.0, float(np.abs(ref['alpha']).max()))
