@@ -113,3 +113,18 @@ def test_patch_fits_the_real_reference(ref_env):
     finally:
         patch.uninstall()
     assert all(getattr(o, n) is f for (o, n), f in before.items())
+
+
+def test_projection_matrices_equal_the_reference(ref_env):
+    """render.py / the oracle restate utils/renderer.py:296-323; compare with the reference's own functions"""
+    import utils.renderer as rr
+    from avatarcap_b200 import render
+    from oracle import raster_oracle as ro
+    for mod in (render, ro):
+        assert np.array_equal(mod.gl_orthographic_projection_matrix(), rr.gl_orthographic_projection_matrix())
+        assert np.array_equal(mod.gl_orthographic_projection_matrix(-50.0, -0.5), rr.gl_orthographic_projection_matrix(-50.0, -0.5))
+        for gl_space in (False, True):
+            a = mod.gl_perspective_projection_matrix(551.3, 548.9, 255.2, 260.7, 512, 480, gl_space=gl_space)
+            b = rr.gl_perspective_projection_matrix(551.3, 548.9, 255.2, 260.7, 512, 480, gl_space=gl_space)
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+        assert np.array_equal(mod.gl_perspective_projection_matrix(500, 500, 256, 256, 512, 512, 50.0, 0.2), rr.gl_perspective_projection_matrix(500, 500, 256, 256, 512, 512, 50.0, 0.2))
