@@ -217,3 +217,38 @@ def test_frames_round_robin_partition():
     import pytest
     with pytest.raises(ValueError):
         pipeline.frames_for_rank(4, 2, 2)
+
+
+def test_knn_shell_walk_covers_every_cell_exactly_once():
+    """Model of the cell traversal of lbs.cu `knn_grid` (3x3x3 cube as z-runs, then shells r >= 2 as side-face runs + the two end cells of
+    the interior rows): after the shells 0..R every cell of the clamped Chebyshev ball of radius R has been visited exactly once, for
+    any grid shape and query cell -- the exactness argument of the search rests on that."""
+    def walk(dims, q, R):
+        dx, dy, dz = dims; cx, cy, cz = q
+        seen = []
+        def run(i, j, k0, k1):
+            seen.extend((i, j, k) for k in range(k0, k1 + 1))
+        for i in range(max(cx - 1, 0), min(cx + 1, dx - 1) + 1):
+            for j in range(max(cy - 1, 0), min(cy + 1, dy - 1) + 1):
+                run(i, j, max(cz - 1, 0), min(cz + 1, dz - 1))
+        for r in range(2, R + 1):
+            for i in range(max(cx - r, 0), min(cx + r, dx - 1) + 1):
+                for j in range(max(cy - r, 0), min(cy + r, dy - 1) + 1):
+                    if abs(i - cx) == r or abs(j - cy) == r:
+                        run(i, j, max(cz - r, 0), min(cz + r, dz - 1))
+                    else:
+                        if cz - r >= 0:
+                            run(i, j, cz - r, cz - r)
+                        if cz + r <= dz - 1:
+                            run(i, j, cz + r, cz + r)
+        return seen
+    rs = np.random.RandomState(0)
+    for _ in range(300):
+        dims = tuple(int(x) for x in rs.randint(1, 9, 3))
+        q = tuple(int(rs.randint(0, d)) for d in dims)
+        R = int(rs.randint(1, 9))
+        seen = walk(dims, q, R)
+        ball = {(i, j, k) for i in range(dims[0]) for j in range(dims[1]) for k in range(dims[2])
+                if max(abs(i - q[0]), abs(j - q[1]), abs(k - q[2])) <= R}
+        assert len(seen) == len(set(seen)), (dims, q, R)
+        assert set(seen) == ball, (dims, q, R)
