@@ -216,5 +216,9 @@ def test_marching_cubes_ambiguous_cells_are_rare():
     # and the triangulation the repo uses is watertight there too (consistent face rule): every edge of the mesh is shared by two faces
     v, f = mo.marching_cubes(vol, 0.0)
     e = np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0), axis=1)
-    _, counts = np.unique(e, axis=0, return_counts=True)
-    assert (counts == 2).all()
+    u, counts = np.unique(e, axis=0, return_counts=True)
+    assert set(np.unique(counts)) <= {1, 2}
+    # open edges only where the body itself leaves the volume (the head touches the +y bound): both end points on a boundary plane
+    open_v = v[u[counts == 1].reshape(-1)]
+    on_bound = ((open_v == 0) | (open_v == np.array(res, np.float32) - 1)).any(axis=1)
+    assert on_bound.all() and (counts == 1).sum() < 50
