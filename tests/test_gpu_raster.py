@@ -160,7 +160,7 @@ def test_full_frame_with_fusion_stage(eng):
     # visible vertices got the image normal rotated back: mv^-1 * (0, 0, +1) = world -z ... i.e. canonical normals of unit length
     ln = fin[fin.norm(dim=-1) > 0].norm(dim=-1)
     assert 0.9 < float(ln.median()) < 1.1 and float(ln.max()) < 1.2     # unit normals (pixels between a visible and a hidden vertex are shorter)
-    ie = encoders.ImageFeatureEncoder(synth.hgfilter_state_dict(), device=eng.device, use_graph=False)
+    ie = encoders.ImageFeatureEncoder(synth.hgfilter_state_dict(), device=eng.device, use_graph=False, benchmark=False)   # no cuDNN autotune: one call only
     fmap = ie(torch.cat([out['front_normal'], out['back_normal']], 1))                        # arch_recon.py:51-52
     assert tuple(fmap.shape) == (1, 32, img // 2, img // 2)
     rec = pipeline.recon_frame(eng, frame_dev, fmap, res, iso=0.5)
