@@ -12,6 +12,9 @@ OK, EINVAL, ECUDA, ESTATE, ECAPACITY, EFORMAT, EVALUE = 0, -1, -2, -3, -4, -5, -
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC2 = 0, 1, 2, 3
 IF_SDF, IF_OCCUPANCY = 0, 1
 MAP_POSE, MAP_IMAGE = 0, 1
+KIND_AVATAR, KIND_RECON = 0, 1
+WEIGHT_SLOTS = 4
+ABI_VERSION = 5
 RASTER_CULL_BACK, RASTER_FLIP_X = 1, 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -31,6 +34,8 @@ SIGNATURES = {
     'avc_debug_set_trace': (_i, [_vp, _vp, _i]),
     'avc_load_avatar_weights': (_i, [_vp, _vp, C.c_size_t]),
     'avc_load_recon_weights': (_i, [_vp, _vp, C.c_size_t]),
+    'avc_load_weights_slot': (_i, [_vp, _i, _i, _vp, C.c_size_t]),
+    'avc_select_weights': (_i, [_vp, _i, _i]),
     'avc_set_feature_map': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     'avc_set_feature_map_hwc': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     'avc_eval_occupancy': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _vp, _vp, _vp, _i, _i, _vp]),

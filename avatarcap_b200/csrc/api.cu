@@ -30,7 +30,7 @@ int avc_ensure_scratch(avc_ctx* ctx, size_t bytes) {
   return AVC_OK;
 }
 
-extern "C" int avc_abi_version(void) { return 4; }
+extern "C" int avc_abi_version(void) { return AVC_ABI_VERSION; }
 
 extern "C" int avc_ctx_create(int device, avc_ctx** out) {
   if (!out) return avc_fail(nullptr, AVC_EINVAL, "avc_ctx_create: out is NULL");
@@ -67,8 +67,8 @@ static void free_weights(AvcWeights& w) {
 extern "C" void avc_ctx_destroy(avc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  free_weights(ctx->avatar); free_weights(ctx->recon);
-  for (int i = 0; i < 2; ++i) if (ctx->maps[i].d_hwc) cudaFree(ctx->maps[i].d_hwc);
+  for (int k = 0; k < 2; ++k) for (int s = 0; s < AVC_WEIGHT_SLOTS; ++s) free_weights(ctx->slots[k][s]);
+  for (int i = 0; i < 2; ++i) { if (ctx->maps[i].d_hwc) cudaFree(ctx->maps[i].d_hwc); if (ctx->maps[i].ready) cudaEventDestroy(ctx->maps[i].ready); }
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
   if (ctx->d_grid) cudaFree(ctx->d_grid);
@@ -112,11 +112,33 @@ static int load_weights(avc_ctx* ctx, AvcWeights& w, const void* blob, size_t nb
   return AVC_OK;
 }
 
+extern "C" int avc_select_weights(avc_ctx* ctx, int kind, int slot) {
+  if (!ctx) return AVC_EINVAL;
+  if ((kind != AVC_KIND_AVATAR && kind != AVC_KIND_RECON) || slot < 0 || slot >= AVC_WEIGHT_SLOTS)
+    return avc_fail(ctx, AVC_EINVAL, "avc_select_weights: bad kind %d / slot %d", kind, slot);
+  if (!ctx->slots[kind][slot].loaded) return avc_fail(ctx, AVC_ESTATE, "avc_select_weights: slot %d holds no weights", slot);
+  (kind == AVC_KIND_AVATAR ? ctx->avatar : ctx->recon) = ctx->slots[kind][slot];      // pointer swap: the slot keeps owning the blob
+  ctx->slot_sel[kind] = slot;
+  return AVC_OK;
+}
+
+extern "C" int avc_load_weights_slot(avc_ctx* ctx, int kind, int slot, const void* blob, size_t nbytes) {
+  if (!ctx) return AVC_EINVAL;
+  if ((kind != AVC_KIND_AVATAR && kind != AVC_KIND_RECON) || slot < 0 || slot >= AVC_WEIGHT_SLOTS)
+    return avc_fail(ctx, AVC_EINVAL, "avc_load_weights_slot: bad kind %d / slot %d", kind, slot);
+  // kernels of earlier calls may still read the blob this slot is about to free
+  AVC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->slots[kind][slot].loaded) AVC_CUDA(ctx, cudaDeviceSynchronize());
+  int rc = load_weights(ctx, ctx->slots[kind][slot], blob, nbytes, (uint32_t)kind, kind == AVC_KIND_AVATAR ? 20 : 4);
+  if (rc) { if (ctx->slot_sel[kind] == slot) (kind == AVC_KIND_AVATAR ? ctx->avatar : ctx->recon) = AvcWeights(); return rc; }
+  return avc_select_weights(ctx, kind, slot);
+}
+
 extern "C" int avc_load_avatar_weights(avc_ctx* ctx, const void* blob, size_t nbytes) {
-  return load_weights(ctx, ctx->avatar, blob, nbytes, AVC_KIND_AVATAR, 20);
+  return avc_load_weights_slot(ctx, AVC_KIND_AVATAR, ctx ? ctx->slot_sel[AVC_KIND_AVATAR] : 0, blob, nbytes);
 }
 extern "C" int avc_load_recon_weights(avc_ctx* ctx, const void* blob, size_t nbytes) {
-  return load_weights(ctx, ctx->recon, blob, nbytes, AVC_KIND_RECON, 4);
+  return avc_load_weights_slot(ctx, AVC_KIND_RECON, ctx ? ctx->slot_sel[AVC_KIND_RECON] : 0, blob, nbytes);
 }
 
 // (C,H,W) -> (H,W,C): one bilinear tap becomes one contiguous C*4-byte read
@@ -148,13 +170,16 @@ static int set_feature_map(avc_ctx* ctx, int which, const float* src, int C, int
     m.cap = need;
   }
   m.C = C; m.H = H; m.W = W;
+  if (!m.ready) AVC_CUDA(ctx, cudaEventCreateWithFlags(&m.ready, cudaEventDisableTiming));
   if (hwc) {
     AVC_CUDA(ctx, cudaMemcpyAsync(m.d_hwc, src, need, cudaMemcpyDeviceToDevice, st));
-    return AVC_OK;
+  } else {
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32), block(32, 8);
+    chw_to_hwc_kernel<<<grid, block, 0, st>>>(src, m.d_hwc, C, H * W);
+    AVC_LAUNCH_CHECK(ctx, "chw_to_hwc_kernel");
   }
-  dim3 grid((H * W + 31) / 32, (C + 31) / 32), block(32, 8);
-  chw_to_hwc_kernel<<<grid, block, 0, st>>>(src, m.d_hwc, C, H * W);
-  AVC_LAUNCH_CHECK(ctx, "chw_to_hwc_kernel");
+  // the host-buffer entry points run on internal streams: they order themselves after this copy through the event
+  AVC_CUDA(ctx, cudaEventRecord(m.ready, st));
   return AVC_OK;
 }
 
@@ -173,12 +198,12 @@ static int pick_impl(avc_ctx* ctx, int* impl_io, bool* use_tc) {
   if (impl == AVC_IMPL_SIMT) { *use_tc = false; return AVC_OK; }
   if (impl == AVC_IMPL_AUTO) {
     *use_tc = avc_tc_available(ctx) != 0;
-    *impl_io = *use_tc ? (ctx->sm_count >= 2 ? AVC_IMPL_TC2 : AVC_IMPL_TC) : AVC_IMPL_SIMT;
+    *impl_io = *use_tc ? AVC_IMPL_TC2 : AVC_IMPL_SIMT;
     return AVC_OK;
   }
   if (impl == AVC_IMPL_TC || impl == AVC_IMPL_TC2) {
     if (!avc_tc_available(ctx)) return avc_fail(ctx, AVC_ESTATE, "tensor-core path requested but not available (needs sm_100 and a library built with tcgen05)");
-    *use_tc = true; return AVC_OK;
+    *use_tc = true; *impl_io = AVC_IMPL_TC2; return AVC_OK;      // AVC_IMPL_TC is kept in the ABI as an alias of the paired kernel
   }
   return avc_fail(ctx, AVC_EINVAL, "bad impl %d", impl);
 }
@@ -195,8 +220,7 @@ static int eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float ce
   if (rc) return rc;
   const float zero[3] = {0, 0, 0};
   const float* c = center ? center : zero;
-  if (use_tc && impl == AVC_IMPL_TC2) return avc_tc2_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st);
-  return use_tc ? avc_tc_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st)
+  return use_tc ? avc_tc2_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st)
                 : avc_simt_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st);
 }
 
@@ -223,8 +247,7 @@ extern "C" int avc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const f
   if (!ctx->maps[AVC_MAP_IMAGE].d_hwc) return avc_fail(ctx, AVC_ESTATE, "image feature map not set");
   bool use_tc; int rc = pick_impl(ctx, &impl, &use_tc);
   if (rc) return rc;
-  if (use_tc && impl == AVC_IMPL_TC2) return avc_tc2_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream);
-  return use_tc ? avc_tc_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream)
+  return use_tc ? avc_tc2_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream)
                 : avc_simt_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream);
 }
 
@@ -269,6 +292,8 @@ static int eval_host(avc_ctx* ctx, bool recon, const float* pts, int64_t n, cons
   for (int s = 0; s < 2; ++s) { cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming); }
   const int64_t n_chunks = (n + chunk - 1) / chunk;
   int status = AVC_OK;
+  // the feature map was (maybe) written on the caller's stream by avc_set_feature_map: the compute stream must see it complete
+  if (cudaEvent_t ready = ctx->maps[recon ? AVC_MAP_IMAGE : AVC_MAP_POSE].ready) cudaStreamWaitEvent(ctx->s_compute, ready, 0);
   // AVC_HOST_TRACE=1: per-chunk timeline (ms from the first H2D) of copy-in, kernel and copy-out, printed to stderr
   const bool trace = getenv("AVC_HOST_TRACE") != nullptr && n_chunks <= 64;
   cudaEvent_t tev[64][5];

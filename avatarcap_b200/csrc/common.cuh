@@ -11,6 +11,7 @@
 #define AVC_MAGIC 0x57435641u /* 'AVCW' */
 #define AVC_BLOB_VERSION 3u
 #define AVC_MAX_LAYERS 24
+#define AVC_WEIGHT_SLOTS 4
 
 // Fixed layer order inside a blob (packer.py writes them in this order).
 // avatar: 0..6 warp conv1..7 (BN folded, softplus) | 7 warp out (256->3) | 8..14 shared fc0..6 | 15,16 geo | 17..19 clr
@@ -49,6 +50,7 @@ struct AvcMap {
   float* d_hwc = nullptr;   // (H,W,C)
   size_t cap = 0;
   int C = 0, H = 0, W = 0;
+  cudaEvent_t ready = nullptr;   // recorded on the caller's stream after the copy / transpose into d_hwc (host entries wait on it)
 };
 
 struct avc_ctx {
@@ -56,7 +58,12 @@ struct avc_ctx {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   std::string err;
+  // `avatar` / `recon` are the ACTIVE weights (a view: the device blobs are owned by the slots below). avc_select_weights()
+  // switches between pre-uploaded blobs with a pointer swap -- the reference's test loop alternates two GeoTexAvatar
+  // instances every frame (main.py:307-315).
   AvcWeights avatar, recon;
+  AvcWeights slots[2][AVC_WEIGHT_SLOTS];
+  int slot_sel[2] = {0, 0};
   AvcMap maps[2];
   int64_t launches = 0;
   // scratch owned by the context (marching cubes scans, host staging)
@@ -94,11 +101,8 @@ int avc_ensure_scratch(avc_ctx* ctx, size_t bytes);
 int avc_simt_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
                          float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
 int avc_simt_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
-int avc_tc_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
-                       float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
-int avc_tc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
 int avc_tc_available(const avc_ctx* ctx);
-// experimental cta_group::2 variant (field_tc2.cu)
+// tcgen05 kernel on CTA pairs (field_tc2.cu)
 int avc_tc2_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
                         float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
 int avc_tc2_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);

@@ -1,5 +1,5 @@
 // tcgen05 (5th-gen tensor core) implementation of the fused per-point networks for sm_100a -- the product path (AVC_IMPL_TC2, what
-// AVC_IMPL_AUTO resolves to on a B200). field_tc.cu is the single-CTA kernel this one grew out of (AVC_IMPL_TC).
+// AVC_IMPL_AUTO resolves to on a B200; the single-CTA kernel of round 1 it grew out of is gone, AVC_IMPL_TC is an alias).
 //
 // Two CTAs of a cluster (= the two SMs of a TPC) evaluate a PAIR of 128-point tiles through the whole network:
 //   * every fully-connected layer is a chain of tcgen05.mma.cta_group::2 (M = 256: 128 points per CTA, N <= 256 channels issued as
@@ -22,8 +22,6 @@
 //
 // Reference call sites restated: see field_simt.cu (same networks, same order of operations per layer).
 #include "common.cuh"
-
-#ifndef AVC_NO_TC
 
 #include <cuda_fp16.h>
 
@@ -993,6 +991,7 @@ int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, c
 
 }  // namespace
 
+int avc_tc_available(const avc_ctx* ctx) { return ctx && ctx->cc_major == 10 ? 1 : 0; }
 
 int avc_tc2_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off, float* out_rgb,
                        float* out_alpha, int if_type, int mode, cudaStream_t st) {
@@ -1005,5 +1004,3 @@ int avc_tc2_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float ce
   return launch_tc2(ctx, ctx->recon, AVC_KIND_RECON, &ctx->maps[AVC_MAP_IMAGE], pts, n, center, out_ov, nullptr, nullptr, nullptr, AVC_IF_SDF,
                    AVC_MODE_QUERY, st);
 }
-
-#endif  // AVC_NO_TC

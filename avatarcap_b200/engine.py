@@ -83,13 +83,28 @@ class Engine:
         self.lib.avc_reset_launch_count(self._h)
 
     # ------------------------------------------------------------------ weights / feature maps
-    def load_avatar(self, state_dict) -> None:
+    def load_avatar(self, state_dict, slot: Optional[int] = None) -> None:
+        """Pack + upload the per-point avatar layers. `slot` (0..WEIGHT_SLOTS-1) keeps several networks resident: the
+        reference's test loop alternates `network` / `network_finetuned` every frame (main.py:307-315) and
+        select_avatar() then switches between them with a pointer swap. None = the active slot."""
         blob = packer.pack_avatar(state_dict)
-        self._check(self.lib.avc_load_avatar_weights(self._h, blob, len(blob)))
+        if slot is None:
+            self._check(self.lib.avc_load_avatar_weights(self._h, blob, len(blob)))
+        else:
+            self._check(self.lib.avc_load_weights_slot(self._h, _lib.KIND_AVATAR, int(slot), blob, len(blob)))
 
-    def load_recon(self, state_dict) -> None:
+    def load_recon(self, state_dict, slot: Optional[int] = None) -> None:
         blob = packer.pack_recon(state_dict)
-        self._check(self.lib.avc_load_recon_weights(self._h, blob, len(blob)))
+        if slot is None:
+            self._check(self.lib.avc_load_recon_weights(self._h, blob, len(blob)))
+        else:
+            self._check(self.lib.avc_load_weights_slot(self._h, _lib.KIND_RECON, int(slot), blob, len(blob)))
+
+    def select_avatar(self, slot: int) -> None:
+        self._check(self.lib.avc_select_weights(self._h, _lib.KIND_AVATAR, int(slot)))
+
+    def select_recon(self, slot: int) -> None:
+        self._check(self.lib.avc_select_weights(self._h, _lib.KIND_RECON, int(slot)))
 
     def set_feature_map(self, which: int, fmap) -> None:
         """(1,C,H,W) or (C,H,W). A channels_last (1,C,H,W) device tensor -- what encoders.py produces -- already has the

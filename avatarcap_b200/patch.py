@@ -4,8 +4,9 @@
     avc_patch.install()            # before main.run_avatarcap(...); `python main.py -c cfg -m test` is unchanged
 
 `install()` re-binds the reference's hot-path call sites to the CUDA library. The replacements are active only while
-autograd is disabled (`torch.no_grad()` / inference), because the training loop (main.py:97-116) differentiates
-through the same modules; with grad enabled every patched method falls through to the original PyTorch code.
+autograd is disabled (`torch.no_grad()` / inference) AND the module is in eval mode: the training loop (main.py:97-116)
+differentiates through the same modules, and finetune_tex (main.py:174-231) queries a train-mode network under no_grad
+(batch-statistics BatchNorm). In both cases every patched method falls through to the original PyTorch code.
 
     network.arch_avatar.OccupancyNet.query      (arch_avatar.py:356)
     network.arch_avatar.WarpingField.query      (arch_avatar.py:113)
@@ -42,25 +43,134 @@ def _engine() -> Engine:
     return _state.get('engine') or default_engine()
 
 
+def _version(module) -> int:
+    return sum(int(p._version) for p in module.parameters()) + sum(int(b._version) for b in module.buffers())
+
+
+class _SlotCache:
+    """Per-module cache of the packed weights in the library's resident slots (avc_load_weights_slot / avc_select_weights):
+    main.py's test loop alternates `network` and `network_finetuned` every frame (main.py:307-315), which with a single slot
+    meant a re-pack + cudaFree + cudaMalloc + synchronous upload twice per frame. Entries are keyed by id(module) and hold a
+    weakref, so a recycled id is never mistaken for the module that owned it; least-recently-used eviction."""
+
+    def __init__(self, kind: str):
+        self.kind = kind
+        self.entries: Dict[int, list] = {}     # id -> [weakref, version, slot, last_use]
+        self.clock = 0
+        self.active = None
+
+    def use(self, net) -> None:
+        import weakref
+        from . import _lib
+        e = _engine()
+        self.clock += 1
+        ent = self.entries.get(id(net))
+        ver = _version(net)
+        if ent is not None and ent[0]() is net and ent[1] == ver:
+            ent[3] = self.clock
+            if self.active != ent[2]:
+                (e.select_avatar if self.kind == 'avatar' else e.select_recon)(ent[2]); self.active = ent[2]
+            return
+        for k in [k for k, v in self.entries.items() if v[0]() is None]:          # dead modules free their slots
+            del self.entries[k]
+        if ent is not None and ent[0]() is net:
+            slot = ent[2]                                                          # same module, new parameters: reload in place
+        else:
+            used = {v[2] for v in self.entries.values()}
+            free = [s for s in range(_lib.WEIGHT_SLOTS) if s not in used]
+            if free:
+                slot = free[0]
+            else:
+                victim = min(self.entries, key=lambda k: self.entries[k][3])
+                slot = self.entries.pop(victim)[2]
+        (e.load_avatar if self.kind == 'avatar' else e.load_recon)(net.state_dict(), slot)
+        self.entries[id(net)] = [weakref.ref(net), ver, slot, self.clock]
+        self.active = slot
+        if self.kind == 'avatar':
+            # WarpingField / DoubleTNet have no back-reference to their GeoTexAvatar: remember whose they are so that a direct
+            # no_grad call on a sub-module evaluates with ITS network's weights (or falls through when it belongs to none)
+            owners = _state.setdefault('owners', {})
+            for k in [k for k, v in owners.items() if v() is None or v() is net]:
+                del owners[k]
+            for sub in (getattr(net, 'warping_field', None), getattr(net, 'cano_template', None)):
+                if sub is not None:
+                    owners[id(sub)] = weakref.ref(net)
+                    _state.setdefault('owner_subs', {})[id(sub)] = weakref.ref(sub)
+
+
+def _cache(kind: str) -> _SlotCache:
+    key = 'cache_' + kind
+    if key not in _state:
+        _state[key] = _SlotCache(kind)
+    return _state[key]
+
+
 def _avatar_loaded(net) -> None:
-    """(Re)pack the avatar weights when the module's parameters changed (main.py loads two checkpoints, :304-315)."""
-    key = (id(net), sum(int(p._version) for p in net.parameters()))
-    if _state.get('avatar_key') != key:
-        _engine().load_avatar(net.state_dict()); _state['avatar_key'] = key
+    """Make `net`'s packed weights the active avatar blob ((re)packing only when its parameters changed)."""
+    _cache('avatar').use(net)
 
 
 def _recon_loaded(net) -> None:
-    key = (id(net), sum(int(p._version) for p in net.parameters()))
-    if _state.get('recon_key') != key:
-        _engine().load_recon(net.state_dict()); _state['recon_key'] = key
+    _cache('recon').use(net)
+
+
+def _owner_of(sub):
+    """The GeoTexAvatar a WarpingField / DoubleTNet instance was packed with, or None."""
+    ref = _state.get('owners', {}).get(id(sub))
+    sref = _state.get('owner_subs', {}).get(id(sub))
+    if ref is None or sref is None or sref() is not sub:
+        return None
+    return ref()
+
+
+def _mode_dependent(module) -> bool:
+    """True when train / eval mode changes the module's forward: BatchNorm with running statistics (recognised by its
+    `running_mean` buffer) or dropout. GroupNorm and weight-norm are mode-free: main.py never puts `recon_net` into eval mode
+    (main.py:300) and its GroupNorm HGFilter + weight-normed decoder evaluate identically either way."""
+    import weakref
+    cache = _state.setdefault('mode_dep', {})
+    ent = cache.get(id(module))
+    if ent is None or ent[0]() is not module:
+        dep = any(n.rsplit('.', 1)[-1] == 'running_mean' for n, _ in module.named_buffers()) or \
+            any(isinstance(m, torch.nn.modules.dropout._DropoutNd) for m in module.modules())
+        ent = (weakref.ref(module), dep)
+        cache[id(module)] = ent
+    return ent[1]
+
+
+def _inference(*modules) -> bool:
+    """The replacements fold BatchNorm running statistics (eval mode) and have no autograd: they are only valid when grad is
+    off AND no module involved is a train-mode module whose forward depends on the mode. finetune_tex (main.py:174-231)
+    queries a train-mode `network_init` under torch.no_grad() -- batch-statistics BatchNorm -- and must keep the reference's
+    PyTorch path."""
+    if torch.is_grad_enabled():
+        return False
+    return all(not (m.training and _mode_dependent(m)) for m in modules if m is not None)
 
 
 def _encoder(slot: str, module, cls):
-    """CUDA-graph encoder rebuilt when the PyTorch module's parameters change (same keying as the weight packers)."""
-    key = (id(module), sum(int(p._version) for p in module.parameters()))
-    if _state.get(slot + '_key') != key:
-        _state[slot] = cls(module.state_dict(), device=_engine().device); _state[slot + '_key'] = key
-    return _state[slot]
+    """CUDA-graph encoder per PyTorch module (dict keyed by id + weakref, rebuilt when the parameters change): two networks
+    alternating per frame no longer rebuild + re-capture each other's encoder."""
+    import weakref
+    cache = _state.setdefault('enc_' + slot, {})
+    ent = cache.get(id(module))
+    ver = _version(module)
+    if ent is None or ent[0]() is not module or ent[1] != ver:
+        for k in [k for k, v in cache.items() if v[0]() is None]:
+            del cache[k]
+        ent = [weakref.ref(module), ver, cls(module.state_dict(), device=_engine().device)]
+        cache[id(module)] = ent
+    return ent[2]
+
+
+def _weight_volume(cwv):
+    """(X,Y,Z,24) copy of CanoBlendWeightVolume.base_weight_volume, cached per tensor version (the reference's
+    NerfRenderer.render calls forward once per 2048-ray chunk -- ~100 full-volume permute copies per frame otherwise)."""
+    t = cwv.base_weight_volume
+    key = (t.data_ptr(), int(t._version), tuple(t.shape))
+    if _state.get('wv_key') != key:
+        _state['wv'] = t[0].permute(1, 2, 3, 0).contiguous(); _state['wv_key'] = key
+    return _state['wv']
 
 
 def _rebind_importers(name: str, original, replacement) -> None:
@@ -98,7 +208,7 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
 
     o_query = keep(arch_avatar.OccupancyNet, 'query')
     def query(self, batch):
-        if torch.is_grad_enabled():
+        if not _inference(self.net):
             return o_query(self, batch)
         _avatar_loaded(self.net)
         return api.occupancy_query(_engine(), batch, self.net.warping_field.pose_feat_map, impl=impl)
@@ -106,25 +216,29 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
 
     o_wq = keep(arch_avatar.WarpingField, 'query')
     def wquery(self, pts, batch):
-        if torch.is_grad_enabled() or _state.get('avatar_key') is None:
+        owner = _owner_of(self)
+        if owner is None or not _inference(self, owner):
             return o_wq(self, pts, batch)
+        _avatar_loaded(owner)
         return api.warping_field_query(_engine(), pts, batch, self.pose_feat_map, impl=impl)
     arch_avatar.WarpingField.query = wquery
 
     o_tf = keep(arch_avatar.DoubleTNet, 'forward')
     def tforward(self, pts):
-        if torch.is_grad_enabled() or _state.get('avatar_key') is None:
+        owner = _owner_of(self)
+        if owner is None or not _inference(self, owner):
             return o_tf(self, pts)
+        _avatar_loaded(owner)
         return api.template_forward(_engine(), pts, impl=impl)
     arch_avatar.DoubleTNet.forward = tforward
 
     o_gf = keep(arch_avatar.GeoTexAvatar, 'forward')
     def gforward(self, wpts, viewdirs, dists, batch, pts_space='posed'):
-        if torch.is_grad_enabled():
+        if not _inference(self):
             return o_gf(self, wpts, viewdirs, dists, batch, pts_space)
         _avatar_loaded(self)
         su = smpl_util_mod.smpl_util
-        wv = self.cano_weight_volume.base_weight_volume[0].permute(1, 2, 3, 0).contiguous()      # (X,Y,Z,24)
+        wv = _weight_volume(self.cano_weight_volume) if pts_space == 'posed' else None            # (X,Y,Z,24), only the posed warp reads it
         return api.geotex_forward(_engine(), wpts, dists, batch, self.warping_field.pose_feat_map, su.smpl_skinning_weights,
                                   su.cano_smpl_vertices, wv, pts_space, impl=impl)
     arch_avatar.GeoTexAvatar.forward = gforward
@@ -132,7 +246,7 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
     if encoders:
         o_pc = keep(arch_avatar.WarpingField, 'precompute_conv')
         def precompute_conv(self, batch):
-            if torch.is_grad_enabled() or not batch['smpl_pos_map'].is_cuda:
+            if not _inference(self) or not batch['smpl_pos_map'].is_cuda:
                 return o_pc(self, batch)
             # clone: the graph owns its output buffer and the reference keeps pose_feat_map across calls (arch_avatar.py:111)
             self.pose_feat_map = _encoder('unet', self.unet, enc_mod.PoseFeatureEncoder)(batch['smpl_pos_map']).clone(memory_format=torch.preserve_format)
@@ -140,13 +254,15 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
 
         o_gfm = keep(arch_recon.ReconNetwork, 'get_feat_maps')
         def get_feat_maps(self, image):
-            if torch.is_grad_enabled() or not image.is_cuda:
+            if not _inference(self) or not image.is_cuda:
                 return o_gfm(self, image)
             return [_encoder('hg', self.image_encoder, enc_mod.ImageFeatureEncoder)(image)]      # list like HGFilter's `outputs`
         arch_recon.ReconNetwork.get_feat_maps = get_feat_maps
 
     o_inf = keep(arch_recon.ReconNetwork, 'infer')
     def infer(self, items):
+        if self.training and _mode_dependent(self):         # see _inference; the stock ReconNetwork is mode-free
+            return o_inf(self, items)
         with torch.no_grad():
             _recon_loaded(self)
             imgs = torch.cat([items['front_normal'], items['back_normal']], dim=1)            # arch_recon.py:51

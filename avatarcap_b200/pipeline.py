@@ -69,10 +69,11 @@ def recon_frame(engine: Engine, frame: Dict, img_feat_map, vol_res, flag: Option
 
 
 def fused_normal_maps(engine: Engine, avatar: Dict[str, torch.Tensor], frame: Dict, normal_map, cam: Dict, w2c, img: int = 512,
-                      integrate_manner: str = 'cover', neck_xy=None, iter_num: int = 100):
+                      integrate_manner: str = 'cover', neck_xy=None, iter_num: int = 100, merge_fn=None):
     """Step 2 of run_avatarcap (main.py:369, 400-428) on the device: the avatar's canonical front / back normal maps
     (render_cano_mesh), the image-observed normals brought to the canonical space (canonicalize_normal_map) and their fusion
-    ('cover' :421, or 'merge' :416-420 -- the Adam rotation-grid optimiser, PyTorch autograd as in the reference).
+    ('cover' :421, or 'merge' :416-420 -- the Adam rotation-grid optimiser is NOT part of this package: pass the reference's own
+    normal_fusion.merge_normal_images as `merge_fn(src_img, tar_img, iter_num, neck_xy) -> np.ndarray`).
     `avatar` is avatar_frame()'s result; cam = {'fx','fy','cx','cy'}; w2c the (4,4) world->camera matrix (items['w2c_RT']).
     -> {'front_normal': (1,3,S,S), 'back_normal': (1,3,S,S)} ready for ReconNetwork.get_feat_maps (arch_recon.py:41-52)."""
     from . import render
@@ -86,9 +87,9 @@ def fused_normal_maps(engine: Engine, avatar: Dict[str, torch.Tensor], frame: Di
     if integrate_manner == 'cover':
         front = render.merge_normal_images_cover(front_avatar.clone(), front_img)
     elif integrate_manner == 'merge':
-        if neck_xy is None:
-            raise ValueError('merge needs neck_xy')
-        front = torch.from_numpy(render.merge_normal_images(front_avatar, front_img, iter_num, neck_xy, device=engine.device)).to(engine.device)
+        if neck_xy is None or merge_fn is None:
+            raise ValueError("integrate_manner='merge' needs neck_xy and merge_fn (the reference's normal_fusion.merge_normal_images)")
+        front = torch.as_tensor(merge_fn(front_avatar.cpu().numpy(), front_img.cpu().numpy(), iter_num, neck_xy)).to(engine.device, torch.float32)
     else:
         raise ValueError('Invalid integration manner!')                                                      # main.py:423
     # "suppose that the performer is facing the camera": the back keeps the avatar normal (main.py:425-426)

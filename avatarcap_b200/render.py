@@ -8,13 +8,13 @@ library (csrc/raster.cu) on meshes that are already in HBM; the reference round-
     gl_orthographic_projection_matrix / gl_perspective_projection_..   same names          utils/renderer.py:296-323
     render_cano_mesh(renderer, vertices, normals, faces, center)       render_cano_mesh    utils/visualize_util.py:11-52
     canonicalize_normal_map(pos_renderer, attri_renderer, ...)         canonicalize_normal_map   normal_fusion.py:12-66
-    merge_normal_images(src, tar, iter_num, neck_xy)                   merge_normal_images       normal_fusion.py:91-155
     merge_normal_images_cover(src, tar)                                merge_normal_images_cover normal_fusion.py:158-167
 
 `*_device` variants keep everything on the GPU (torch tensors in, torch tensors out) for pipeline.py.
 The phong shaders (renderer.py:54-292) only draw the JPEG previews main.py writes next to the meshes: out of scope.
-merge_normal_images is an Adam loop over a 64x64 rotation grid: it stays a PyTorch autograd program like the reference's
-(no kernel of ours on that path), run on the engine's device.
+normal_fusion.merge_normal_images (normal_fusion.py:91-155, the 100-step Adam registration on a 64x64 rotation grid) is an
+optimiser, not a kernel of the replaced path, and SURVEY.md section 2 marks it out of scope: `patch.install()` leaves the
+reference's own function in place and pipeline.fused_normal_maps takes it as a callable.
 """
 from __future__ import annotations
 
@@ -183,89 +183,6 @@ def canonicalize_normal_map(pos_renderer: Renderer, attri_renderer: Renderer, ca
 
 
 # ------------------------------------------------------------------------------------------------------------ fusion
-def axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
-    """pytorch3d.transforms.axis_angle_to_matrix (pytorch3d==0.6.0, requirements.txt:6; not vendored): axis-angle -> unit
-    quaternion (sin(x/2)/x by its Taylor series below 1e-6 rad) -> rotation matrix."""
-    angles = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
-    half_angles = angles * 0.5
-    small = angles.abs() < 1e-6
-    sin_half_over_angle = torch.where(small, 0.5 - (angles * angles) / 48, torch.sin(half_angles) / torch.where(small, torch.ones_like(angles), angles))
-    q = torch.cat([torch.cos(half_angles), axis_angle * sin_half_over_angle], dim=-1)
-    r, i, j, k = torch.unbind(q, -1)
-    two_s = 2.0 / (q * q).sum(-1)
-    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
-                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
-                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
-    return o.reshape(q.shape[:-1] + (3, 3))
-
-
-def _neighbor_images(img: torch.Tensor, win_size: int = 3):
-    """get_neighbor_images (normal_fusion.py:69-82): the 8 one-texel shifts by nearest sampling with zero padding."""
-    H, W, _ = img.shape
-    half = win_size // 2
-    out = []
-    for i in range(-half, half + 1):
-        for j in range(-half, half + 1):
-            if i == 0 and j == 0:
-                continue
-            theta = torch.tensor([[1, 0, j / (H / 2)], [0, 1, i / (W / 2)]], dtype=torch.float32, device=img.device)
-            grid = F.affine_grid(theta.unsqueeze(0), torch.Size((1, 1, H, W)), align_corners=True)
-            a = F.grid_sample(input=img.permute((2, 0, 1)).unsqueeze(0), grid=grid, mode='nearest', align_corners=True)
-            out.append(a.squeeze(0).permute((1, 2, 0)))
-    return out
-
-
-def _resize_img(src: torch.Tensor, tar_shape) -> torch.Tensor:
-    """resize_img (normal_fusion.py:85-90): bilinear, border, align_corners."""
-    theta = torch.tensor([[1, 0, 0], [0, 1, 0]], dtype=torch.float32, device=src.device)
-    grid = F.affine_grid(theta.unsqueeze(0), torch.Size((1, 1, tar_shape[0], tar_shape[1])), align_corners=True)
-    return F.grid_sample(src.permute((2, 0, 1)).unsqueeze(0), grid, 'bilinear', 'border', True).squeeze(0).permute((1, 2, 0))
-
-
-def merge_normal_images(src_img, tar_img, iter_num: int, neck_xy, device: Optional[torch.device] = None) -> np.ndarray:
-    """normal_fusion.merge_normal_images (:91-155): rotation-grid registration of the avatar normals (src) to the image-observed
-    normals (tar), then a distance-transform blend; the face rectangle keeps the avatar normals. Autograd + Adam as in the
-    reference (this is an optimiser, not a kernel of the replaced path); cv2 erode / distanceTransform on the host, as there."""
-    import cv2 as cv
-    dev = torch.device(device) if device is not None else (torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu'))
-    with torch.enable_grad():
-        as_t = lambda x: (x.detach() if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(dev, torch.float32)   # noqa: E731
-        src_img = as_t(src_img)
-        tar_img = as_t(tar_img)
-        src_mask = torch.linalg.norm(src_img, dim=-1) > 0.
-        tar_mask = torch.linalg.norm(tar_img, dim=-1) > 0.
-        kernel = cv.getStructuringElement(cv.MORPH_RECT, (3, 3))
-        tar_mask = cv.erode(tar_mask.cpu().numpy().astype(np.uint8), kernel, iterations=3)
-        dt_tar_mask = torch.from_numpy(cv.distanceTransform(tar_mask, cv.DIST_L1, 3)).to(dev)
-        tar_mask = torch.from_numpy(tar_mask > 0).to(dev)
-        valid_mask = torch.logical_and(src_mask, tar_mask)
-        src_img = src_img.clone().requires_grad_()
-        init_src_img = src_img.detach().clone()
-        rot_aa_img = torch.zeros((64, 64, 3), dtype=torch.float32, device=dev, requires_grad=True)
-        optm_rot = torch.optim.Adam([rot_aa_img], lr=1e-2)
-        optm_normal = torch.optim.Adam([src_img], lr=1e-1)
-        smooth_lambda = 1.
-        for iter_idx in range(iter_num):
-            rot_mat_img = axis_angle_to_matrix(_resize_img(rot_aa_img, (512, 512)))
-            data_loss = torch.square(torch.einsum('ijab,ijb->ija', rot_mat_img, src_img) - tar_img)[valid_mask].mean()
-            smooth_loss = 0.
-            for nb in _neighbor_images(rot_aa_img):
-                smooth_loss = smooth_loss + torch.square(nb - rot_aa_img).mean()
-            total_loss = data_loss + smooth_lambda * smooth_loss
-            opt = optm_rot if iter_idx < iter_num / 2 else optm_normal
-            opt.zero_grad()
-            total_loss.backward()
-            opt.step()
-        with torch.no_grad():
-            dt = dt_tar_mask[..., None] / 5.
-            w0 = torch.ones_like(dt)
-            w0[dt > 1.] = 0.
-            out = (src_img * dt + init_src_img * w0) / (dt + w0)
-            r = [neck_xy[1] - 90, neck_xy[0] - 35, neck_xy[1], neck_xy[0] + 35]
-            out[r[0]: r[2], r[1]: r[3]] = init_src_img[r[0]: r[2], r[1]: r[3]]
-        return out.detach().cpu().numpy()
-
-
 def merge_normal_images_cover(src_img, tar_img):
     """normal_fusion.py:158-167: cover the avatar normal with the image-observed one where that is valid (in place, like the
     reference; works on numpy arrays and on torch tensors)."""

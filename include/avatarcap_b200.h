@@ -27,6 +27,8 @@
 extern "C" {
 #endif
 
+#define AVC_ABI_VERSION   5    /* what avc_abi_version() of a matching library returns */
+
 #define AVC_OK            0
 #define AVC_EINVAL       -1   /* bad argument (NULL pointer, bad shape, bad flag)              */
 #define AVC_ECUDA        -2   /* a CUDA runtime call or kernel launch failed                   */
@@ -40,8 +42,9 @@ typedef struct avc_ctx avc_ctx;
 /* which implementation of the field evaluation to run */
 #define AVC_IMPL_AUTO   0     /* tensor-core kernel when available, else SIMT                  */
 #define AVC_IMPL_SIMT   1     /* fp32 CUDA-core kernel (bit-near the reference's fp32 math)    */
-#define AVC_IMPL_TC     2     /* tcgen05 kernel, fp16 hi/lo split operands, fp32 accumulate     */
-#define AVC_IMPL_TC2    3     /* the same kernel on CTA pairs (cta_group::2, M = 256 per MMA): what AUTO resolves to on sm_100 */
+#define AVC_IMPL_TC     2     /* alias of AVC_IMPL_TC2 (the single-CTA kernel of ABI <= 4 is gone) */
+#define AVC_IMPL_TC2    3     /* tcgen05 kernel on CTA pairs (cta_group::2, M = 256 per MMA), fp16 hi/lo split operands, fp32
+                                 accumulate: what AUTO resolves to on sm_100 */
 
 /* implicit-field type, config.py:12-22 */
 #define AVC_IF_SDF        0
@@ -78,10 +81,20 @@ int avc_debug_set_trace(avc_ctx* ctx, void* dev_buf /*[dev]|NULL*/, int flags /*
 /* ---------------------------------------------------------------------------------------------- */
 int avc_load_avatar_weights(avc_ctx* ctx, const void* blob /*[host]*/, size_t nbytes);
 int avc_load_recon_weights(avc_ctx* ctx, const void* blob /*[host]*/, size_t nbytes);
+/* The reference's test loop alternates two GeoTexAvatar instances every frame (`network` for the geometry, `network_finetuned`
+ * for the colours, main.py:307-315): AVC_WEIGHT_SLOTS blobs per kind stay resident and avc_select_weights switches the active
+ * one with a pointer swap. kind: 0 = avatar, 1 = recon. avc_load_*_weights above (re)load the ACTIVE slot. Loading into an
+ * occupied slot synchronises the device first (kernels in flight may still read the old blob).                          */
+#define AVC_WEIGHT_SLOTS 4
+int avc_load_weights_slot(avc_ctx* ctx, int kind, int slot, const void* blob /*[host]*/, size_t nbytes);
+int avc_select_weights(avc_ctx* ctx, int kind, int slot);
 
 /* per-frame encoder output (stays in PyTorch; WarpingField.precompute_conv arch_avatar.py:109-111,
  * ReconNetwork.get_feat_maps arch_recon.py:41-43). `chw` is a [dev] (C,H,W) float32 tensor; the library
  * transposes it into an owned (H,W,C) copy so that one bilinear tap is one contiguous read.            */
+/* Stream rule: the copy is enqueued on `stream`. Device-pointer entry points called on the SAME stream are ordered after it by
+ * the stream; the *_host entry points (internal streams) wait for an event recorded behind the copy. A device-pointer entry
+ * point called on a DIFFERENT stream must be ordered by the caller.                                                     */
 int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw /*[dev]*/, int C, int H, int W, void* stream);
 /* same, for an encoder that already produced the (H,W,C) order (a channels_last torch tensor, avatarcap_b200/encoders.py):
  * plain device copy into the owned buffer, no transpose.                                                          */

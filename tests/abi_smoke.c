@@ -15,7 +15,7 @@
 
 int main(void) {
   avc_ctx* ctx = NULL;
-  if (avc_abi_version() != 4) { fprintf(stderr, "abi_smoke: ABI version %d\n", avc_abi_version()); return 1; }
+  if (avc_abi_version() != AVC_ABI_VERSION) { fprintf(stderr, "abi_smoke: ABI version %d\n", avc_abi_version()); return 1; }
   if (avc_ctx_create(0, &ctx) != AVC_OK) { fprintf(stderr, "abi_smoke: no context: %s\n", avc_last_error(NULL)); return 2; }
 
   /* grid of generate_volume_points: last point == bmax */

@@ -121,7 +121,7 @@ def test_abi_header_matches_binding():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.avc_abi_version() == 4
+    assert lib.avc_abi_version() == 5
 
 
 def test_header_is_plain_c99_and_the_c_client_compiles():

@@ -12,7 +12,7 @@ from avatarcap_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = ['simt', 'tc', 'tc2']
+IMPLS = ['simt', 'tc2']
 
 
 @pytest.fixture(scope='module')

@@ -120,14 +120,6 @@ def test_fusion_on_device_vs_reference_golden(eng, g):
     fi, _ = render.render_cano_mesh_device(eng, g['v'], g['vn'], g['f'], g['center'], img)
     cover = render.merge_normal_images_cover(front.clone(), fi)
     assert np.abs(cover.cpu().numpy()[::4, ::4] - g['cover_sub']).max() < 2e-5
-    merged = render.merge_normal_images(front, fi, iter_num=int(g['merge_iters']), neck_xy=tuple(int(x) for x in g['neck_xy']), device=eng.device)
-    d = np.abs(merged[::4, ::4] - g['merged_sub'])
-    err = float(d.max())
-    print('merge_normal_images on the device vs the reference (CPU): max-abs %.3g, 99.9th percentile %.3g' % (err, float(np.quantile(d, 0.999))))
-    # 20 Adam steps on another device: reduction order differs, and Adam's normalised step can amplify that at isolated pixels whose
-    # gradient is close to zero -- tight on the bulk, looser on the maximum
-    assert float(np.quantile(d, 0.999)) < 5e-3 and err < 5e-2
-    assert np.abs(merged[::4, ::4] - g['cover_sub']).max() > 0.1          # the optimiser did move the normals
 
 
 def test_full_frame_with_fusion_stage(eng):

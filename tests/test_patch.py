@@ -30,7 +30,7 @@ def test_install_rebinds_and_uninstall_restores(frame):
         assert all(getattr(c, n) is not f for (c, n), f in orig.items())
         assert mods['utils.recon_util'].recon_mesh is not orig_rm
         # with autograd enabled every patched method falls through to the reference's own code (training, main.py:97-116)
-        net = aa.GeoTexAvatar(frame)
+        net = aa.GeoTexAvatar(frame).eval()                 # main.py:297
         with torch.enable_grad():
             with pytest.raises(fr.Fallthrough):
                 aa.OccupancyNet(net).query({})
@@ -41,6 +41,24 @@ def test_install_rebinds_and_uninstall_restores(frame):
         # host tensors never reach the CUDA encoders
         with torch.no_grad(), pytest.raises(fr.Fallthrough):
             net.warping_field.precompute_conv({'smpl_pos_map': torch.zeros(1, 6, 256, 256)})
+        # a TRAIN-mode network under no_grad (finetune_tex's network_init, main.py:186-188, 226-231) evaluates BatchNorm with batch
+        # statistics in the reference: the eval-mode-folding replacements must fall through
+        net_init = aa.GeoTexAvatar(frame)                   # never .eval()'d, like the reference
+        assert net_init.training and patch._mode_dependent(net_init)
+        with torch.no_grad():
+            with pytest.raises(fr.Fallthrough):
+                aa.OccupancyNet(net_init).query({})
+            with pytest.raises(fr.Fallthrough):
+                net_init(None, None, None, {}, 'cano')
+            with pytest.raises(fr.Fallthrough):
+                net_init.warping_field.query(None, {})
+            with pytest.raises(fr.Fallthrough):
+                net_init.cano_template(None)
+            # a sub-module that belongs to no packed network never evaluates with somebody else's weights
+            with pytest.raises(fr.Fallthrough):
+                net.eval().cano_template(None)
+        # the stock ReconNetwork (GroupNorm + weight-norm) is mode-free: main.py never calls recon_net.eval() (main.py:300)
+        assert not patch._mode_dependent(ar.ReconNetwork())
         # render stage: phong previews stay on the (fake) GL renderer and the GL-renderer call paths fall through
         R = mods['utils.renderer'].Renderer
         gl = R(512, 512, shader_name='phong_geometry', bg_color=(1, 1, 1), window_name='Phong')
@@ -96,7 +114,7 @@ def test_patched_call_sites_run_on_the_library(frame):
     aa = mods['network.arch_avatar']; ar = mods['network.arch_recon']; su = mods['utils.smpl_util'].smpl_util
     patch.install(engine=eng, modules=mods)
     try:
-        net = aa.GeoTexAvatar(frame).to(dev); occ_net = aa.OccupancyNet(net)
+        net = aa.GeoTexAvatar(frame).to(dev).eval(); occ_net = aa.OccupancyNet(net)          # main.py:296-298
         pts = torch.from_numpy(synth.volume_points(frame['cano_bounds'], (40, 40, 24)))[None].to(dev)
         batch = {'cano_pts': pts, 'smpl_pos_map': torch.from_numpy(synth.smpl_pos_map()).to(dev),
                  'cano_smpl_center': torch.from_numpy(frame['cano_smpl_center'])[None].to(dev),
@@ -127,6 +145,29 @@ def test_patched_call_sites_run_on_the_library(frame):
             items = {'cano_pts': pts, 'front_normal': nm[:, :3], 'back_normal': nm[:, 3:], 'cano_smpl_center': batch['cano_smpl_center']}
             ov = rn.infer(items)
             assert tuple(ov.shape) == (1, pts.shape[1]) and 0.0 <= float(ov.min()) and float(ov.max()) <= 1.0 and float(ov.std()) > 1e-3
+            # two networks alternating per frame (main.py:307-315): each keeps its own resident weight slot, switching is a
+            # pointer swap (no re-pack), and a sub-module call evaluates with ITS owner's weights
+            net2 = aa.GeoTexAvatar(frame).to(dev).eval()
+            with torch.no_grad():
+                for p_ in net2.cano_template.parameters():
+                    p_.mul_(1.01)
+            net2.warping_field.pose_feat_map = fmap
+            out2 = aa.OccupancyNet(net2).query(batch)
+            assert float((out2['cano_pts_ov'] - out['cano_pts_ov']).abs().max()) > 1e-4
+            cache = patch._cache('avatar')
+            assert len(cache.entries) == 2 and cache.entries[id(net)][2] != cache.entries[id(net2)][2]
+            import avatarcap_b200.packer as packer_mod
+            calls = []
+            orig_pack = packer_mod.pack_avatar
+            packer_mod.pack_avatar = lambda sd: (calls.append(1), orig_pack(sd))[1]
+            try:
+                again = occ_net.query(batch); again2 = aa.OccupancyNet(net2).query(batch)
+                r1, _, o1 = net.cano_template(pts + off); r2, _, o2 = net2.cano_template(pts + off)
+            finally:
+                packer_mod.pack_avatar = orig_pack
+            assert not calls                                                           # cached blobs: nothing was re-packed
+            assert torch.equal(again['cano_pts_ov'], out['cano_pts_ov']) and torch.equal(again2['cano_pts_ov'], out2['cano_pts_ov'])
+            assert torch.equal(r1, rgb) and not torch.equal(o1, o2)
             # mesh + skinning call sites
             vol = out['cano_pts_ov'].reshape(40, 40, 24)
             v, f, n = mods['utils.recon_util'].recon_mesh(vol, (40, 40, 24), frame['cano_bounds'], 0.0)

@@ -150,7 +150,7 @@ def test_ply_writer_bytes_equal_reference(tmp_path):
 
 
 def test_fusion_mirror_vs_reference_golden(g):
-    """merge_normal_images / merge_normal_images_cover (torch port, run on the CPU here) against the reference's own output"""
+    """merge_normal_images_cover against the reference's own output (the Adam-based merge_normal_images stays the reference's)"""
     from avatarcap_b200 import render
     img = int(g['img'])
     front, _ = ro.render_cano_mesh(g['v'], g['n'], g['f'], g['center'], img)
@@ -158,23 +158,6 @@ def test_fusion_mirror_vs_reference_golden(g):
     cover = render.merge_normal_images_cover(front.copy(), fi)
     assert np.abs(cover[::4, ::4] - g['cover_sub']).max() < 2e-5   # the golden's per-vertex normals came from torch (reference), these from numpy
     assert np.array_equal(cover, ro.merge_normal_images_cover(front, fi))
-    merged = render.merge_normal_images(front.copy(), fi, iter_num=int(g['merge_iters']), neck_xy=tuple(int(x) for x in g['neck_xy']), device='cpu')
-    err = np.abs(merged[::4, ::4] - g['merged_sub'])
-    assert err.max() < 2e-3, err.max()
-    assert np.abs(merged[::4, ::4] - g['cover_sub']).max() > 0.1          # the optimiser did move the normals
-
-
-def test_axis_angle_to_matrix_properties():
-    import torch
-    from avatarcap_b200 import render
-    aa = torch.tensor([[0., 0., 0.], [1e-8, 0., 0.], [0., math_pi() / 2, 0.], [0.3, -0.2, 0.9]], dtype=torch.float64)
-    R = render.axis_angle_to_matrix(aa)
-    assert torch.allclose(R @ R.transpose(-1, -2), torch.eye(3, dtype=torch.float64).expand(4, 3, 3), atol=1e-12)
-    assert torch.allclose(R[0], torch.eye(3, dtype=torch.float64)) and torch.allclose(R[2] @ torch.tensor([1., 0., 0.], dtype=torch.float64),
-                                                                                      torch.tensor([0., 0., -1.], dtype=torch.float64), atol=1e-12)
-    # Rodrigues: R v = v cos t + (k x v) sin t + k (k.v)(1 - cos t)
-    t = aa[3].norm(); k = aa[3] / t; v = torch.tensor([0.2, 0.5, -0.7], dtype=torch.float64)
-    assert torch.allclose(R[3] @ v, v * torch.cos(t) + torch.linalg.cross(k, v) * torch.sin(t) + k * (k @ v) * (1 - torch.cos(t)), atol=1e-12)
 
 
 def math_pi():
