@@ -48,6 +48,7 @@ SIGNATURES = {
     'avc_scatter_fill': (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     'avc_mc_count': (_i, [_vp, _vp, C.POINTER(_i), _f, _i, _i, C.POINTER(_i64), C.POINTER(_i64), _vp]),
     'avc_mc_emit': (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_f), _f, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i64, _vp]),
+    'avc_mc_extract': (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_f), _f, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     'avc_mc_emit_counted': (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_f), _f, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i64, _vp]),
     'avc_knn': (_i, [_vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     'avc_near_flag': (_i, [_vp, _vp, _i64, _vp, _i, C.c_double, _vp, _vp]),

@@ -74,19 +74,19 @@ __device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const
 
 // the same for a thread's MC_VPT = 4 consecutive voxels when they are one aligned float4 of a single z-row (d.vec4): 4 rows x
 // (float4 + the next element) instead of up to 8 scalar loads per voxel
-struct Vox4 { int cut[MC_VPT]; int ccase[MC_VPT]; bool in_scan, owned; };
+struct Vox4 { int cut[MC_VPT]; int ccase[MC_VPT]; bool in_scan, owned; int own_mask; /* bit q: voxel q lies in an owned plane */ };
 __device__ __forceinline__ void load_row5(const float* __restrict__ p, bool more, float iso, bool b[5]) {
   const float4 v = __ldg(reinterpret_cast<const float4*>(p));
   b[0] = v.x > iso; b[1] = v.y > iso; b[2] = v.z > iso; b[3] = v.w > iso;
   b[4] = more ? (__ldg(p + 4) > iso) : false;
 }
 __device__ __forceinline__ void classify4(const float* __restrict__ vol, const McDims& d, int64_t v0, const Vox3& c, Vox4& r) {
-  r.in_scan = false; r.owned = false;
+  r.in_scan = false; r.owned = false; r.own_mask = 0;
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) { r.cut[q] = 0; r.ccase[q] = -1; }
   if (v0 >= d.nvox) return;
   if (c.i < d.lo || c.i >= d.scan_end) return;
-  r.in_scan = true; r.owned = c.i < d.hi_excl;
+  r.in_scan = true; r.owned = c.i < d.hi_excl; r.own_mask = r.owned ? 15 : 0;
   const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
   const bool hx = c.i + 1 < d.rx, hy = c.j + 1 < d.ry, hz3 = c.k + 4 < d.rz;       // voxels q < 3 always have a +z neighbour in the row
   bool A[5], B[5], C[5], E[5];
@@ -110,14 +110,14 @@ __device__ __forceinline__ void classify4(const float* __restrict__ vol, const M
 __device__ __forceinline__ void classify_thread(const float* __restrict__ vol, const McDims& d, int64_t v0, Vox4& r) {
   Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
   if (d.vec4) { classify4(vol, d, v0, c, r); return; }
-  r.in_scan = false; r.owned = false;
+  r.in_scan = false; r.owned = false; r.own_mask = 0;
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
     const VoxInfo x = classify(vol, d, v0 + q, c);
     vox_next(d, c);
     // per-voxel flags folded into the values: cut counts only inside the scan range, the case only for owned cells
     r.cut[q] = x.in_scan ? x.cut : 0; r.ccase[q] = x.owned ? x.ccase : -1;
-    r.in_scan = r.in_scan || x.in_scan; r.owned = r.owned || x.owned;
+    r.in_scan = r.in_scan || x.in_scan; r.owned = r.owned || x.owned; r.own_mask |= x.owned ? (1 << q) : 0;
   }
 }
 
@@ -127,143 +127,136 @@ __device__ __forceinline__ void stage_ntri(unsigned char* s_ntri) {
   __syncthreads();
 }
 
-// block-wide exclusive scan of one int per thread; returns the exclusive prefix, *total = block sum
-__device__ __forceinline__ int block_excl_scan(int val, int* total) {
-  __shared__ int warp_sums[MC_NT / 32];
+// block-wide exclusive scan of one 64-bit word per thread (packed counters); returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long val, unsigned long long* total) {
+  __shared__ unsigned long long warp_sums[MC_NT / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = val;
+  unsigned long long inc = val;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
   __syncthreads();   // protect warp_sums reuse across calls
   if (lane == 31) warp_sums[wid] = inc;
   __syncthreads();
-  int wprefix = 0, tot = 0;
+  unsigned long long wprefix = 0, tot = 0;
 #pragma unroll
-  for (int w = 0; w < MC_NT / 32; ++w) { const int s = warp_sums[w]; if (w < wid) wprefix += s; tot += s; }
+  for (int w = 0; w < MC_NT / 32; ++w) { const unsigned long long s = warp_sums[w]; if (w < wid) wprefix += s; tot += s; }
   *total = tot;
   return wprefix + inc - val;
 }
 
-// pass A: per-block totals {vertices in scan range, owned vertices, triangles}
-__global__ void __launch_bounds__(MC_NT) mc_count_kernel(const float* __restrict__ vol, McDims d, int* __restrict__ blk) {
-  __shared__ unsigned char s_ntri[256];
-  stage_ntri(s_ntri);
-  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  int nv = 0, nvo = 0, nt = 0;
-  if (d.vec4) {
-    Vox4 r; classify4(vol, d, v0, vox_of(d, v0 < d.nvox ? v0 : 0), r);
-#pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) {
-      const int n = __popc(r.cut[q]);
-      nv += n;                                         // cut is 0 outside the scan range
-      if (r.owned) { nvo += n; if (r.ccase[q] >= 0) nt += s_ntri[r.ccase[q]]; }
-    }
-  } else {
-    Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
-#pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) {
-      const VoxInfo r = classify(vol, d, v0 + q, c);
-      vox_next(d, c);
-      const int n = __popc(r.cut);
-      if (r.in_scan) nv += n;
-      if (r.owned) { nvo += n; if (r.ccase >= 0) nt += s_ntri[r.ccase]; }
-    }
-  }
-  // the three counts fit one word each only loosely (nt <= 20, nv <= 12 per thread): reduce them packed, 10 bits apart would overflow
-  // at 256 threads, so use two warp-shuffle reductions on a 64-bit word (21 bits per field)
-  unsigned long long w = (unsigned long long)nv | ((unsigned long long)nvo << 21) | ((unsigned long long)nt << 42);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-  __shared__ unsigned long long s_w[MC_NT / 32];
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = w;
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass chained scan across blocks (decoupled look-back). One 64-bit state word per block: bits 63..62 = flag
+// (0 empty, 1 = the block's own aggregate, 2 = inclusive prefix of everything up to and including the block), bits 61..0 = payload
+// (for marching cubes two 31-bit counters: vertices << 31 | triangles). Blocks take their logical index from an atomic ticket,
+// so every predecessor of a running block has itself started -- the spin below always makes progress. Replaces the
+// count kernel + single-CTA scan kernel + second classification pass of round 1 (3 launches, the volume read twice).
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
+struct LookbackState { unsigned long long* state; unsigned int* ticket; };
+
+__device__ __forceinline__ int lookback_ticket(const LookbackState& L) {
+  __shared__ int s_bid;
+  if (threadIdx.x == 0) s_bid = (int)atomicAdd(L.ticket, 1u);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long t = 0;
+  return s_bid;
+}
+// called by ALL threads of the block; returns the exclusive prefix (payload sum of the blocks 0..bid-1) to every thread
+__device__ __forceinline__ unsigned long long lookback_prefix(const LookbackState& L, int bid, unsigned long long agg) {
+  __shared__ unsigned long long s_excl;
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    volatile unsigned long long* st = L.state;
+    if (lane == 0) { st[bid] = (bid == 0 ? LB_PREFIX : LB_AGG) | agg; }
+    unsigned long long excl = 0;
+    if (bid > 0) {
+      int base = bid - 1;
+      for (;;) {
+        const int idx = base - lane;
+        unsigned long long w = LB_PREFIX;                  // before block 0: an inclusive prefix of zero
+        if (idx >= 0) {
+          unsigned int spins = 0;
+          while (((w = st[idx]) >> 62) == 0) {
+            if (++spins > (1u << 26)) { printf("avatarcap_b200: look-back scan stalled (block %d waits for %d)\n", bid, idx); __trap(); }
+            __nanosleep(32);
+          }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        const int first = m ? __ffs((int)m) - 1 : 32;        // nearest predecessor whose inclusive prefix is known
+        unsigned long long c = lane <= first ? (w & LB_MASK) : 0ull;
 #pragma unroll
-    for (int i = 0; i < MC_NT / 32; ++i) t += s_w[i];
-    blk[3 * blockIdx.x] = (int)(t & 0x1fffff); blk[3 * blockIdx.x + 1] = (int)((t >> 21) & 0x1fffff); blk[3 * blockIdx.x + 2] = (int)(t >> 42);
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        excl += c;
+        if (m) break;
+        base -= 32;
+      }
+      if (lane == 0) st[bid] = LB_PREFIX | (excl + agg);
+    }
+    if (lane == 0) s_excl = excl;
   }
+  __syncthreads();
+  return s_excl;
 }
 
-// pass B: exclusive scan over blocks (single CTA, 8 consecutive blocks per thread per round); totals -> tot[0..2] (int64)
-constexpr int SCAN_EPT = 8;
-__global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(int* __restrict__ blk, int nblk, int64_t* __restrict__ tot) {
-  __shared__ long long carry[3];
-  __shared__ long long wsum[3][32];
-  if (threadIdx.x < 3) carry[threadIdx.x] = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < nblk; base += 1024 * SCAN_EPT) {
-    const int b0 = base + threadIdx.x * SCAN_EPT;
-    int x[SCAN_EPT][3];
-    long long sum[3] = {0, 0, 0};
-#pragma unroll
-    for (int e = 0; e < SCAN_EPT; ++e)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { x[e][c] = b0 + e < nblk ? blk[3 * (b0 + e) + c] : 0; sum[c] += x[e][c]; }
-    long long inc[3] = {sum[0], sum[1], sum[2]};
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { const long long t = __shfl_up_sync(0xffffffffu, inc[c], o); if (lane >= o) inc[c] += t; }
-    if (lane == 31) { wsum[0][wid] = inc[0]; wsum[1][wid] = inc[1]; wsum[2][wid] = inc[2]; }
-    __syncthreads();
-    long long pre[3], tt[3] = {0, 0, 0};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      // warp `wid` needs the sum of the warp totals below it: one shuffle scan over the 32 totals instead of a 32-step loop
-      long long v = wsum[c][lane], sc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
-      tt[c] = __shfl_sync(0xffffffffu, sc, 31);
-      const long long below = __shfl_sync(0xffffffffu, sc - v, wid);
-      pre[c] = carry[c] + below + inc[c] - sum[c];
-    }
-#pragma unroll
-    for (int e = 0; e < SCAN_EPT; ++e)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { if (b0 + e < nblk) blk[3 * (b0 + e) + c] = (int)pre[c]; pre[c] += x[e][c]; }
-    __syncthreads();
-    if (threadIdx.x < 3) carry[threadIdx.x] += tt[threadIdx.x];
-    __syncthreads();
-  }
-  if (threadIdx.x < 3) tot[threadIdx.x] = carry[threadIdx.x];
-}
-
-// pass C: vbase[v] = exclusive vertex prefix of voxel v (canonical order: voxel linear index, then axis)
-// Also compacts the sign-changing edges: edges[vid] = voxel*4 + axis, so that the vertex kernel runs one thread per vertex, and
-// (tris != NULL) the triangles: tris[t] = voxel << 11 | case << 3 | triangle number, so that the face kernel runs one thread per
-// TRIANGLE instead of re-classifying every voxel with a tenth of the lanes doing the emission.
-__global__ void __launch_bounds__(MC_NT) mc_vbase_kernel(const float* __restrict__ vol, McDims d, const int* __restrict__ blk,
-                                                         int* __restrict__ vbase, long long* __restrict__ edges, long long* __restrict__ tris) {
+// mc counters (device, int64): [0] vertices in the scan range, [1] owned vertices, [2] triangles, [3] reserved
+// Fused pass: classify -> block scan -> look-back -> vbase[v] = exclusive vertex prefix of voxel v (canonical order: voxel linear
+// index, then axis), the compact list of sign-changing EDGES (edges[vid] = voxel*4 + axis: the vertex kernel runs one thread per
+// vertex) and of TRIANGLES (tris[t] = voxel << 11 | case << 3 | triangle number: one thread per triangle). vbase == NULL: count only.
+// Entries beyond the capacities cap_e / cap_t are dropped (the totals stay exact, the caller sees the overflow).
+__global__ void __launch_bounds__(MC_NT) mc_scan_kernel(const float* __restrict__ vol, McDims d, LookbackState L, int nblk, long long* __restrict__ counts,
+                                                        int* __restrict__ vbase, long long* __restrict__ edges, long long* __restrict__ tris,
+                                                        long long cap_e, long long cap_t) {
   __shared__ unsigned char s_ntri[256];
+  const int bid = lookback_ticket(L);
   stage_ntri(s_ntri);
-  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  int c[MC_VPT], cut[MC_VPT], ccase[MC_VPT]; int nv = 0, nt = 0;
+  const int64_t v0 = ((int64_t)bid * MC_NT + threadIdx.x) * MC_VPT;
+  int c[MC_VPT], cut[MC_VPT], ccase[MC_VPT]; int nv = 0, nvo = 0, nt = 0;
   {
     Vox4 r; classify_thread(vol, d, v0, r);
 #pragma unroll
     for (int q = 0; q < MC_VPT; ++q) {
       cut[q] = r.cut[q]; c[q] = __popc(cut[q]); nv += c[q];
+      if ((r.own_mask >> q) & 1) nvo += c[q];
       ccase[q] = r.ccase[q]; if (ccase[q] >= 0) nt += s_ntri[ccase[q]];
     }
   }
-  int tot; int p = blk[3 * blockIdx.x] + block_excl_scan(nv, &tot);
+  // owned-vertex total: an order-independent integer sum
+  {
+    int w = nvo;
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) {
-    if (v0 + q < d.nvox) vbase[v0 + q] = p;
-    int e = p;
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) if ((cut[q] >> ax) & 1) edges[e++] = (long long)(v0 + q) * 4 + ax;
-    p += c[q];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(reinterpret_cast<unsigned long long*>(counts + 1), (unsigned long long)w);
   }
-  if (tris) {
-    int tb = blk[3 * blockIdx.x + 2] + block_excl_scan(nt, &tot);
+  unsigned long long tot;
+  const unsigned long long mine = block_excl_scan64(((unsigned long long)nv << 31) | (unsigned long long)nt, &tot);
+  const unsigned long long pre = lookback_prefix(L, bid, tot) + mine;
+  if (bid == nblk - 1 && threadIdx.x == MC_NT - 1) {
+    const unsigned long long all = pre + (((unsigned long long)nv << 31) | (unsigned long long)nt);
+    counts[0] = (long long)(all >> 31); counts[2] = (long long)(all & 0x7fffffffull);
+  }
+  if (!vbase) return;
+  int p = (int)(pre >> 31);
+  if (d.vec4 && v0 < d.nvox) {
+    *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + c[0], p + c[0] + c[1], p + c[0] + c[1] + c[2]);
+  } else {
+    int pp = p;
+#pragma unroll
+    for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += c[q]; }
+  }
+  if (nv) {
+#pragma unroll
+    for (int q = 0; q < MC_VPT; ++q) {
+      int e = p;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) if ((cut[q] >> ax) & 1) { if (e < cap_e) edges[e] = (long long)(v0 + q) * 4 + ax; ++e; }
+      p += c[q];
+    }
+  }
+  if (nt) {
+    int tb = (int)(pre & 0x7fffffffull);
 #pragma unroll
     for (int q = 0; q < MC_VPT; ++q) {
       if (ccase[q] < 0) continue;
       const int ntri = s_ntri[ccase[q]];
-      for (int tix = 0; tix < ntri; ++tix) tris[tb++] = ((long long)(v0 + q) << 11) | ((long long)ccase[q] << 3) | tix;
+      for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)ccase[q] << 3) | tix;
     }
   }
 }
@@ -285,10 +278,19 @@ __device__ __forceinline__ float vol_at(const float* __restrict__ vol, const McD
 }
 
 // pass D1: one thread per owned vertex (dense warps): position by linear interpolation + Sobel/trilinear normal
+// The counts live on the device (no host round trip between the scan and the emission): a fixed persistent grid strides over
+// min(count, capacity). Thread 0 also publishes the caller-visible record out_counts = {owned vertices, faces, vertices incl. the
+// next slab's first plane, overflow flags (bit 0: vertices, bit 1: faces)}.
 __global__ void __launch_bounds__(128) mc_verts_kernel(const float* __restrict__ vol, McDims d, McEmit e, const long long* __restrict__ edges,
-                                                       int64_t n_owned) {
-  const int64_t vid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (vid >= n_owned) return;
+                                                       const long long* __restrict__ counts, long long cap_v, long long cap_f,
+                                                       long long* __restrict__ out_counts) {
+  const long long n_all = counts[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && out_counts) {
+    out_counts[0] = n_all; out_counts[1] = counts[2]; out_counts[2] = counts[0];
+    out_counts[3] = (n_all > cap_v ? 1 : 0) | (counts[2] > cap_f ? 2 : 0);
+  }
+  const int64_t n_owned = n_all < cap_v ? n_all : cap_v;
+  for (int64_t vid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vid < n_owned; vid += (int64_t)gridDim.x * blockDim.x) {
   const long long key = edges[vid];
   const int64_t v = key >> 2; const int ax = (int)(key & 3);
   const int k = (int)(v % d.rz); const int64_t t = v / d.rz; const int j = (int)(t % d.ry); const int i = (int)(t / d.ry);
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(128) mc_verts_kernel(const float* __restrict__
     g[c] = fminf((float)(e.gres[c] - 1), fmaxf(s, 0.f));
   }
   e.verts[vid * 3 + 0] = p[0]; e.verts[vid * 3 + 1] = p[1]; e.verts[vid * 3 + 2] = p[2];
-  if (!e.normals) return;
+  if (!e.normals) continue;
   // trilinear sample of the Sobel gradient volume: 8 corners, each a 3x3x3 stencil -> a 4x4x4 block of voxels
   const int x0 = (int)floorf(g[0]), y0 = (int)floorf(g[1]), z0 = (int)floorf(g[2]);
   const float fx = g[0] - (float)x0, fy = g[1] - (float)y0, fz = g[2] - (float)z0;
@@ -347,68 +349,17 @@ __global__ void __launch_bounds__(128) mc_verts_kernel(const float* __restrict__
   e.normals[vid * 3 + 0] = -(n[0] / nn);                              // negated (:68)
   e.normals[vid * 3 + 1] = -(n[1] / nn);
   e.normals[vid * 3 + 2] = -(n[2] / nn);
-}
-
-// pass D2: faces of the cell whose lowest corner is each owned voxel
-__global__ void __launch_bounds__(MC_NT) mc_faces_kernel(const float* __restrict__ vol, McDims d, McEmit e, const int* __restrict__ blk,
-                                                         const int* __restrict__ vbase) {
-  __shared__ unsigned char s_ntri[256];
-  __shared__ uint4 s_tri[256];                                      // 16 edge numbers per case
-  s_tri[threadIdx.x] = reinterpret_cast<const uint4*>(g_mc_tri)[threadIdx.x];
-  stage_ntri(s_ntri);
-  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  int ccase[MC_VPT]; int nt = 0;
-  const Vox3 c0 = vox_of(d, v0 < d.nvox ? v0 : 0);
-  Vox3 vc = c0;
-#pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) {
-    const VoxInfo r = classify(vol, d, v0 + q, vc);
-    vox_next(d, vc);
-    ccase[q] = (r.owned ? r.ccase : -1); if (ccase[q] >= 0) nt += s_ntri[ccase[q]];
-  }
-  int tot; int tbase = blk[3 * blockIdx.x + 2] + block_excl_scan(nt, &tot);
-  const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
-  vc = c0;
-#pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) {
-    const int i = vc.i, j = vc.j;
-    vox_next(d, vc);
-    if (ccase[q] < 0) continue;
-    const int64_t v = v0 + q;
-    const int ntri = s_ntri[ccase[q]];
-    const signed char* tri = reinterpret_cast<const signed char*>(&s_tri[ccase[q]]);
-    for (int tix = 0; tix < ntri; ++tix) {
-      int ids[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int ed = tri[3 * tix + c];
-        const int corner = (int)((AVC_MC_EDGE_CORNER_NIBBLES >> (4 * ed)) & 0xF), ax = ed >> 2;
-        const int64_t ov = v + (corner & 1) * sx + ((corner >> 1) & 1) * sy + ((corner >> 2) & 1);
-        // rank of `ax` among the owner's cut edges: recompute the owner's lower-axis cut flags
-        int rank = 0;
-        if (ax > 0) {
-          const bool o0 = ldv(vol, ov) > d.iso;
-          const int oi = i + (corner & 1), oj = j + ((corner >> 1) & 1);
-          if (oi + 1 < d.rx && ((ldv(vol, ov + sx) > d.iso) != o0)) ++rank;
-          if (ax > 1 && oj + 1 < d.ry && ((ldv(vol, ov + sy) > d.iso) != o0)) ++rank;
-        }
-        ids[c] = vbase[ov] + rank;
-      }
-      const int64_t f = (int64_t)tbase + tix;
-      e.faces[f * 3 + 0] = ids[2]; e.faces[f * 3 + 1] = ids[1]; e.faces[f * 3 + 2] = ids[0];   // faces[:, [2,1,0]]  :69
-    }
-    tbase += ntri;
   }
 }
 
 // pass D2': one thread per TRIANGLE (records written by mc_vbase_kernel): dense warps, no second classification of the volume
 __global__ void __launch_bounds__(MC_NT) mc_tris_kernel(const float* __restrict__ vol, McDims d, McEmit e, const long long* __restrict__ tris,
-                                                        const int* __restrict__ vbase, int64_t n_faces) {
+                                                        const int* __restrict__ vbase, const long long* __restrict__ counts, long long cap_f) {
   __shared__ uint4 s_tri[256];                                      // 16 edge numbers per case
   s_tri[threadIdx.x] = reinterpret_cast<const uint4*>(g_mc_tri)[threadIdx.x];
   __syncthreads();
-  const int64_t f = (int64_t)blockIdx.x * MC_NT + threadIdx.x;
-  if (f >= n_faces) return;
+  const int64_t n_faces = counts[2] < cap_f ? counts[2] : cap_f;
+  for (int64_t f = (int64_t)blockIdx.x * MC_NT + threadIdx.x; f < n_faces; f += (int64_t)gridDim.x * MC_NT) {
   const long long key = tris[f];
   const int64_t v = key >> 11; const int cc = (int)((key >> 3) & 255), tix = (int)(key & 7);
   const Vox3 c0 = vox_of(d, v);
@@ -430,6 +381,7 @@ __global__ void __launch_bounds__(MC_NT) mc_tris_kernel(const float* __restrict_
     ids[c] = vbase[ov] + rank;
   }
   e.faces[f * 3 + 0] = ids[2]; e.faces[f * 3 + 1] = ids[1]; e.faces[f * 3 + 2] = ids[0];   // faces[:, [2,1,0]]  recon_util.py:69
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -449,23 +401,25 @@ __global__ void make_grid_kernel(float* __restrict__ out, float bx, float by, fl
   out[idx * 3 + 2] = __fadd_rn(__fmul_rn(lin(k, rz), lz), bz);
 }
 
-__global__ void __launch_bounds__(MC_NT) flag_count_kernel(const uint8_t* __restrict__ flag, int64_t n, int* __restrict__ blk) {
-  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
-  int c = 0;
-#pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) if (v0 + q < n && flag[v0 + q]) ++c;
-  int tot; block_excl_scan(c, &tot);
-  if (threadIdx.x == 0) { blk[3 * blockIdx.x] = tot; blk[3 * blockIdx.x + 1] = 0; blk[3 * blockIdx.x + 2] = 0; }
-}
-
-__global__ void __launch_bounds__(MC_NT) scatter_fill_kernel(const uint8_t* __restrict__ flag, int64_t n, const int* __restrict__ blk,
+// vol[flag] = vals (in order); vol[~flag] = fill (in order)   main.py:357,362-364. One pass: the flag count of each block is
+// chained through the look-back scan, so the flags are read once and there is no separate count / scan launch.
+__global__ void __launch_bounds__(MC_NT) scatter_fill_kernel(const uint8_t* __restrict__ flag, int64_t n, LookbackState L,
                                                              const float* __restrict__ vals, const float* __restrict__ fill,
                                                              float* __restrict__ out) {
-  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * MC_VPT;
+  const int bid = lookback_ticket(L);
+  const int64_t v0 = ((int64_t)bid * MC_NT + threadIdx.x) * MC_VPT;
   int c = 0; bool f[MC_VPT];
+  if (v0 + MC_VPT <= n && (reinterpret_cast<uintptr_t>(flag) & 3) == 0) {
+    const uchar4 f4 = *reinterpret_cast<const uchar4*>(flag + v0);
+    f[0] = f4.x != 0; f[1] = f4.y != 0; f[2] = f4.z != 0; f[3] = f4.w != 0;
+    c = (int)f[0] + (int)f[1] + (int)f[2] + (int)f[3];
+  } else {
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) { f[q] = (v0 + q < n) && flag[v0 + q]; c += f[q]; }
-  int tot; int64_t p = (int64_t)blk[3 * blockIdx.x] + block_excl_scan(c, &tot);
+    for (int q = 0; q < MC_VPT; ++q) { f[q] = (v0 + q < n) && flag[v0 + q]; c += f[q]; }
+  }
+  unsigned long long tot;
+  const unsigned long long mine = block_excl_scan64((unsigned long long)c, &tot);
+  int64_t p = (int64_t)(lookback_prefix(L, bid, tot) + mine);
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
     const int64_t v = v0 + q;
@@ -474,23 +428,29 @@ __global__ void __launch_bounds__(MC_NT) scatter_fill_kernel(const uint8_t* __re
   }
 }
 
-int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi, McDims* d, int* nblk, int** d_blk, int64_t** d_tot,
-             int** d_vbase) {
+// scratch layout of one scan: [0,64) counters (int64 x 4: scan vertices, owned vertices, triangles, -) | [64,128) ticket |
+// [128, 128 + 8*nblk) look-back state words | (256-aligned) vbase, 4 B per voxel
+struct McScratch { long long* counts; LookbackState L; int* vbase; size_t zero_bytes; };
+
+int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi, bool with_vbase, McDims* d, int* nblk, McScratch* S) {
   if (res[0] < 2 || res[1] < 2 || res[2] < 2) return avc_fail(ctx, AVC_EINVAL, "marching cubes needs res >= 2 per axis");
   if (halo_lo < 0 || halo_hi < 0 || halo_lo + halo_hi >= res[0]) return avc_fail(ctx, AVC_EINVAL, "bad halo widths");
   d->rx = res[0]; d->ry = res[1]; d->rz = res[2];
   d->lo = halo_lo; d->hi_excl = res[0] - halo_hi; d->scan_end = halo_hi > 0 ? d->hi_excl + 1 : d->hi_excl;
   d->iso = iso; d->nvox = (int64_t)res[0] * res[1] * res[2]; d->vec4 = 0;
-  if (d->nvox > (int64_t)1 << 40) return avc_fail(ctx, AVC_EINVAL, "volume too large");
+  // vertex / triangle prefixes travel as 31-bit fields of one look-back word: 3 edges and at most 5 triangles per voxel
+  if (d->nvox * 5 >= ((int64_t)1 << 31)) return avc_fail(ctx, AVC_EINVAL, "volume too large for int32 mesh indices (%lld voxels)", (long long)d->nvox);
   *nblk = (int)((d->nvox + MC_VPB - 1) / MC_VPB);
-  const size_t need = (size_t)*nblk * 3 * sizeof(int) + 64 + (size_t)d->nvox * sizeof(int) + 256;
+  size_t off = 128 + (size_t)*nblk * sizeof(unsigned long long); off = (off + 255) & ~(size_t)255;
+  const size_t need = off + (with_vbase ? (size_t)d->nvox * sizeof(int) : 0) + 256;
   int rc = avc_ensure_scratch(ctx, need);
   if (rc) return rc;
   char* base = (char*)ctx->d_scratch;
-  *d_tot = (int64_t*)base;
-  *d_blk = (int*)(base + 64);
-  size_t off = 64 + (size_t)*nblk * 3 * sizeof(int); off = (off + 255) & ~(size_t)255;
-  *d_vbase = (int*)(base + off);
+  S->counts = (long long*)base;
+  S->L.ticket = (unsigned int*)(base + 64);
+  S->L.state = (unsigned long long*)(base + 128);
+  S->vbase = with_vbase ? (int*)(base + off) : nullptr;
+  S->zero_bytes = 128 + (size_t)*nblk * sizeof(unsigned long long);
   return AVC_OK;
 }
 
@@ -515,14 +475,12 @@ extern "C" int avc_scatter_fill(avc_ctx* ctx, const uint8_t* flag, int64_t n_tot
   if (n_total == 0) return AVC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((n_total + MC_VPB - 1) / MC_VPB);
-  int rc = avc_ensure_scratch(ctx, (size_t)nblk * 3 * sizeof(int) + 64);
+  const size_t zero = 128 + (size_t)nblk * sizeof(unsigned long long);
+  int rc = avc_ensure_scratch(ctx, zero);
   if (rc) return rc;
-  int64_t* d_tot = (int64_t*)ctx->d_scratch; int* d_blk = (int*)((char*)ctx->d_scratch + 64);
-  flag_count_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, d_blk);
-  AVC_LAUNCH_CHECK(ctx, "flag_count_kernel");
-  mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(d_blk, nblk, d_tot);
-  AVC_LAUNCH_CHECK(ctx, "mc_scan_blocks_kernel");
-  scatter_fill_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, d_blk, vals, fill, out_vol);
+  AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, zero, st));
+  LookbackState L; L.ticket = (unsigned int*)((char*)ctx->d_scratch + 64); L.state = (unsigned long long*)((char*)ctx->d_scratch + 128);
+  scatter_fill_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, L, vals, fill, out_vol);
   AVC_LAUNCH_CHECK(ctx, "scatter_fill_kernel");
   return AVC_OK;
 }
@@ -532,25 +490,19 @@ static int mc_vec4_ok(const float* vol, const int res[3]) {
   return ((res[2] & 3) == 0 && (reinterpret_cast<uintptr_t>(vol) & 15) == 0 && !getenv("AVC_MC_SCALAR")) ? 1 : 0;
 }
 
-static int mc_run_count(avc_ctx* ctx, const float* vol, const McDims& d, int nblk, int* d_blk, int64_t* d_tot, cudaStream_t st) {
-  mc_count_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk);
-  AVC_LAUNCH_CHECK(ctx, "mc_count_kernel");
-  mc_scan_blocks_kernel<<<1, 1024, 0, st>>>(d_blk, nblk, d_tot);
-  AVC_LAUNCH_CHECK(ctx, "mc_scan_blocks_kernel");
-  AVC_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, d_tot, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  AVC_CUDA(ctx, cudaStreamSynchronize(st));
-  return AVC_OK;
-}
-
 extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], float iso, int x_halo_lo, int x_halo_hi, int64_t* n_verts,
                             int64_t* n_faces, void* stream) {
   if (!ctx || !vol || !res || !n_verts || !n_faces) return avc_fail(ctx, AVC_EINVAL, "avc_mc_count: NULL argument");
-  McDims d; int nblk; int* d_blk; int64_t* d_tot; int* d_vbase;
-  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);
+  cudaStream_t st = (cudaStream_t)stream;
+  McDims d; int nblk; McScratch S;
+  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, false, &d, &nblk, &S);
   if (rc) return rc;
   d.vec4 = mc_vec4_ok(vol, res);
-  rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, (cudaStream_t)stream);
-  if (rc) return rc;
+  AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, S.zero_bytes, st));
+  mc_scan_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, nullptr, nullptr, nullptr, 0, 0);
+  AVC_LAUNCH_CHECK(ctx, "mc_scan_kernel(count)");
+  AVC_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, S.counts, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  AVC_CUDA(ctx, cudaStreamSynchronize(st));
   *n_verts = ctx->h_counts[1]; *n_faces = ctx->h_counts[2];
   auto& L = ctx->mc_last;
   L.vol = vol; L.res[0] = res[0]; L.res[1] = res[1]; L.res[2] = res[2]; L.iso = iso; L.lo = x_halo_lo; L.hi = x_halo_hi;
@@ -559,49 +511,31 @@ extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], fl
   return AVC_OK;
 }
 
-static int mc_emit_impl(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
-                        int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
-                        void* stream, bool trust_last_count) {
-  if (!ctx || !vol || !res || !bounds || !verts || !faces) return avc_fail(ctx, AVC_EINVAL, "avc_mc_emit: NULL argument");
-  if (gres_x < res[0] - x_halo_lo - x_halo_hi || x_origin < -x_halo_lo) return avc_fail(ctx, AVC_EINVAL, "avc_mc_emit: bad slab placement");
-  cudaStream_t st = (cudaStream_t)stream;
-  const auto& L = ctx->mc_last;
-  // the block sums and totals of the preceding avc_mc_count are still in the scratch buffer: skip the second count + scan + host sync
-  const bool reuse = trust_last_count && L.valid && L.vol == vol && L.res[0] == res[0] && L.res[1] == res[1] && L.res[2] == res[2] && L.iso == iso &&
-                     L.lo == x_halo_lo && L.hi == x_halo_hi;
-  int64_t counts[3] = {L.counts[0], L.counts[1], L.counts[2]};
-  McDims d; int nblk; int* d_blk; int64_t* d_tot; int* d_vbase;
-  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, &d, &nblk, &d_blk, &d_tot, &d_vbase);     // same size as for the count: no reallocation
+// Asynchronous core: scan + vertex + triangle kernels on `stream`, bounded by the capacities, no host synchronisation.
+static int mc_extract_async(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
+                            int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
+                            int64_t* d_counts, cudaStream_t st) {
+  if (!ctx || !vol || !res || !bounds || !verts || !faces) return avc_fail(ctx, AVC_EINVAL, "marching cubes: NULL argument");
+  if (cap_v < 0 || cap_f < 0) return avc_fail(ctx, AVC_EINVAL, "marching cubes: negative capacity");
+  if (gres_x < res[0] - x_halo_lo - x_halo_hi || x_origin < -x_halo_lo) return avc_fail(ctx, AVC_EINVAL, "marching cubes: bad slab placement");
+  McDims d; int nblk; McScratch S;
+  int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, true, &d, &nblk, &S);
   if (rc) return rc;
   d.vec4 = mc_vec4_ok(vol, res);
-  if (reuse) {
-    for (int c = 0; c < 3; ++c) ctx->h_counts[c] = counts[c];
-  } else {
-    rc = mc_run_count(ctx, vol, d, nblk, d_blk, d_tot, st);
-    if (rc) return rc;
-  }
-  const int64_t nv = ctx->h_counts[1], nf = ctx->h_counts[2];
-  if (nv > cap_v || nf > cap_f)
-    return avc_fail(ctx, AVC_ECAPACITY, "avc_mc_emit: need %lld vertices / %lld faces, capacity %lld / %lld", (long long)nv, (long long)nf,
-                    (long long)cap_v, (long long)cap_f);
-  if (ctx->h_counts[0] > 0x7fffffffLL || nf > 0x7fffffffLL) return avc_fail(ctx, AVC_EINVAL, "mesh too large for int32 indices");
-  if (nv == 0 && nf == 0) return AVC_OK;
-  // compact edge list (8 B per vertex in the scan range), separate buffer so the scan scratch above stays valid
-  // ... and the compact triangle list (8 B per face) behind it; AVC_MC_FACES=voxel selects the older per-voxel face pass (A/B knob)
-  const char* fmode = getenv("AVC_MC_FACES");
-  const bool per_triangle = !(fmode && strcmp(fmode, "voxel") == 0) && d.nvox < ((int64_t)1 << 52);
-  const size_t n_edges = (size_t)(ctx->h_counts[0] + 1);
-  const size_t need2 = (n_edges + (per_triangle ? (size_t)nf + 1 : 0)) * sizeof(long long);
+  // compact edge list (8 B per owned vertex) and triangle list (8 B per face), sized by the capacities; separate buffer so that the
+  // scan scratch above stays valid
+  const size_t need2 = ((size_t)cap_v + (size_t)cap_f + 2) * sizeof(long long);
   if (need2 > ctx->scratch2_cap) {
-    if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
+    if (ctx->d_scratch2) { AVC_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->d_scratch2); }
     ctx->d_scratch2 = nullptr; ctx->scratch2_cap = 0;
     AVC_CUDA(ctx, cudaMalloc(&ctx->d_scratch2, need2 + (need2 >> 3)));
     ctx->scratch2_cap = need2 + (need2 >> 3);
   }
   long long* d_edges = reinterpret_cast<long long*>(ctx->d_scratch2);
-  long long* d_tris = per_triangle ? d_edges + n_edges : nullptr;
-  mc_vbase_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, d_blk, d_vbase, d_edges, d_tris);
-  AVC_LAUNCH_CHECK(ctx, "mc_vbase_kernel");
+  long long* d_tris = d_edges + cap_v + 1;
+  AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, S.zero_bytes, st));
+  mc_scan_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, S.vbase, d_edges, d_tris, (long long)cap_v, (long long)cap_f);
+  AVC_LAUNCH_CHECK(ctx, "mc_scan_kernel");
   McEmit e;
   const int gres[3] = {gres_x, res[1], res[2]};
   for (int c = 0; c < 3; ++c) {
@@ -609,20 +543,44 @@ static int mc_emit_impl(avc_ctx* ctx, const float* vol, const int res[3], const 
     e.vox[c] = e.len[c] / (float)gres[c];                                   // recon_util.py:60-61
   }
   e.x_origin = x_origin; e.verts = verts; e.normals = normals; e.faces = faces;
-  if (nv > 0) {
-    mc_verts_kernel<<<(unsigned)((nv + 127) / 128), 128, 0, st>>>(vol, d, e, d_edges, nv);
-    AVC_LAUNCH_CHECK(ctx, "mc_verts_kernel");
-  }
-  if (per_triangle) {
-    if (nf > 0) {
-      mc_tris_kernel<<<(unsigned)((nf + MC_NT - 1) / MC_NT), MC_NT, 0, st>>>(vol, d, e, d_tris, d_vbase, nf);
-      AVC_LAUNCH_CHECK(ctx, "mc_tris_kernel");
-    }
-  } else {
-    mc_faces_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, e, d_blk, d_vbase);
-    AVC_LAUNCH_CHECK(ctx, "mc_faces_kernel");
-  }
+  // persistent grids: the work size is only known on the device
+  const int64_t want_v = (cap_v + 127) / 128, want_f = (cap_f + MC_NT - 1) / MC_NT;
+  const int gv = (int)(want_v < (int64_t)ctx->sm_count * 16 ? (want_v > 0 ? want_v : 1) : (int64_t)ctx->sm_count * 16);
+  const int gf = (int)(want_f < (int64_t)ctx->sm_count * 8 ? (want_f > 0 ? want_f : 1) : (int64_t)ctx->sm_count * 8);
+  mc_verts_kernel<<<gv, 128, 0, st>>>(vol, d, e, d_edges, S.counts, (long long)cap_v, (long long)cap_f, (long long*)d_counts);
+  AVC_LAUNCH_CHECK(ctx, "mc_verts_kernel");
+  mc_tris_kernel<<<gf, MC_NT, 0, st>>>(vol, d, e, d_tris, S.vbase, S.counts, (long long)cap_f);
+  AVC_LAUNCH_CHECK(ctx, "mc_tris_kernel");
   return AVC_OK;
+}
+
+extern "C" int avc_mc_extract(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
+                              int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
+                              int64_t* counts, void* stream) {
+  if (ctx && !counts) return avc_fail(ctx, AVC_EINVAL, "avc_mc_extract: counts is NULL");
+  return mc_extract_async(ctx, vol, res, bounds, iso, x_halo_lo, x_halo_hi, x_origin, gres_x, verts, normals, faces, cap_v, cap_f, counts,
+                          (cudaStream_t)stream);
+}
+
+static int mc_emit_impl(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
+                        int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
+                        void* stream, bool trust_last_count) {
+  if (!ctx || !vol || !res || !bounds || !verts || !faces) return avc_fail(ctx, AVC_EINVAL, "avc_mc_emit: NULL argument");
+  const auto& L = ctx->mc_last;
+  // the totals of the preceding avc_mc_count are still known: skip the counting pass and its host synchronisation
+  const bool reuse = trust_last_count && L.valid && L.vol == vol && L.res[0] == res[0] && L.res[1] == res[1] && L.res[2] == res[2] && L.iso == iso &&
+                     L.lo == x_halo_lo && L.hi == x_halo_hi;
+  int64_t nv = L.counts[1], nf = L.counts[2];
+  if (!reuse) {
+    int rc = avc_mc_count(ctx, vol, res, iso, x_halo_lo, x_halo_hi, &nv, &nf, stream);
+    if (rc) return rc;
+  }
+  if (nv > cap_v || nf > cap_f)
+    return avc_fail(ctx, AVC_ECAPACITY, "avc_mc_emit: need %lld vertices / %lld faces, capacity %lld / %lld", (long long)nv, (long long)nf,
+                    (long long)cap_v, (long long)cap_f);
+  if (nv == 0 && nf == 0) return AVC_OK;
+  return mc_extract_async(ctx, vol, res, bounds, iso, x_halo_lo, x_halo_hi, x_origin, gres_x, verts, normals, faces, nv, nf, nullptr,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int avc_mc_emit(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,

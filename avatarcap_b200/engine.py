@@ -37,7 +37,7 @@ class Engine:
         if rc:
             raise AvcError(rc, self.lib.avc_last_error(None).decode())
         self._h = h
-        self._keep: Dict[str, torch.Tensor] = {}
+        self._keep: Dict[str, object] = {}
 
     # ------------------------------------------------------------------ plumbing
     def close(self) -> None:
@@ -221,25 +221,45 @@ class Engine:
                                           self._stream()))
         return nv.value, nf.value
 
-    def extract_mesh(self, vol: torch.Tensor, bounds, iso: float, with_normals: bool = True, halo_lo: int = 0, halo_hi: int = 0,
-                     x_origin: int = 0, gres_x: Optional[int] = None):
-        """-> verts (V,3) f32, faces (F,3) i32, normals (V,3) f32 | None, all on the device, in the reference's conventions."""
+    def extract_mesh_async(self, vol: torch.Tensor, bounds, iso: float, cap_v: int, cap_f: int, with_normals: bool = True,
+                           halo_lo: int = 0, halo_hi: int = 0, x_origin: int = 0, gres_x: Optional[int] = None):
+        """avc_mc_extract: everything enqueued, nothing synchronised. -> (verts (cap_v,3), faces (cap_f,3), normals | None,
+        counts (4,) int64 on the device = {n_verts, n_faces, n_verts incl. the next slab's first plane, overflow flags})."""
         vol = self._f32(vol)
         if vol.dim() != 3:
             raise ValueError('volume must be (Rx,Ry,Rz)')
-        nv, nf = self.mc_count(vol, iso, halo_lo, halo_hi)
-        if nv == 0 and nf == 0:
-            z = torch.zeros((0, 3), device=self.device, dtype=torch.float32)
-            return z, torch.zeros((0, 3), device=self.device, dtype=torch.int32), (z.clone() if with_normals else None)
-        verts = torch.empty((nv, 3), device=self.device, dtype=torch.float32)
-        faces = torch.empty((nf, 3), device=self.device, dtype=torch.int32)
-        normals = torch.empty((nv, 3), device=self.device, dtype=torch.float32) if with_normals else None
+        verts = torch.empty((cap_v, 3), device=self.device, dtype=torch.float32)
+        faces = torch.empty((cap_f, 3), device=self.device, dtype=torch.int32)
+        normals = torch.empty((cap_v, 3), device=self.device, dtype=torch.float32) if with_normals else None
+        counts = torch.empty(4, device=self.device, dtype=torch.int64)
         b = np.asarray(bounds, dtype=np.float32).reshape(6)
         gx = vol.shape[0] if gres_x is None else gres_x
-        # the count above scanned exactly this volume and nothing touched the context since: emit reuses its block sums
-        self._check(self.lib.avc_mc_emit_counted(self._h, _ptr(vol), _lib.i3(vol.shape), _lib.f6(b), float(iso), halo_lo, halo_hi, x_origin, gx,
-                                         _ptr(verts), _ptr(normals), _ptr(faces), max(nv, 1), max(nf, 1), self._stream()))
-        return verts, faces, normals
+        self._check(self.lib.avc_mc_extract(self._h, _ptr(vol), _lib.i3(vol.shape), _lib.f6(b), float(iso), halo_lo, halo_hi, x_origin, gx,
+                                            _ptr(verts), _ptr(normals), _ptr(faces), int(cap_v), int(cap_f), _ptr(counts), self._stream()))
+        return verts, faces, normals, counts
+
+    def extract_mesh(self, vol: torch.Tensor, bounds, iso: float, with_normals: bool = True, halo_lo: int = 0, halo_hi: int = 0,
+                     x_origin: int = 0, gres_x: Optional[int] = None):
+        """-> verts (V,3) f32, faces (F,3) i32, normals (V,3) f32 | None, all on the device, in the reference's conventions.
+        The sizes are data dependent: the kernels run against capacity buffers (sized from the last meshes this engine extracted,
+        or 1/16 of the voxels the first time) and the ONE host synchronisation is the read of the counts after everything has been
+        enqueued; an overflow re-runs with the exact sizes."""
+        vol = self._f32(vol)
+        if vol.dim() != 3:
+            raise ValueError('volume must be (Rx,Ry,Rz)')
+        nvox = int(vol.numel())
+        hint = self._keep.get('mc_hint')
+        cap_v, cap_f = hint if hint else (max(4096, nvox // 16), max(8192, nvox // 8))
+        for _ in range(2):
+            verts, faces, normals, counts = self.extract_mesh_async(vol, bounds, iso, cap_v, cap_f, with_normals, halo_lo, halo_hi, x_origin, gres_x)
+            nv, nf, _, over = (int(x) for x in counts.tolist())            # the only synchronisation of the extraction
+            if not over:
+                break
+            cap_v, cap_f = max(nv, 1), max(nf, 1)
+        else:
+            raise AvcError(_lib.ECAPACITY, 'marching cubes overflowed its exact-size retry')
+        self._keep['mc_hint'] = (max(4096, nv + nv // 4), max(8192, nf + nf // 4))
+        return verts[:nv], faces[:nf], (normals[:nv] if with_normals else None)
 
     # ------------------------------------------------------------------ KNN / LBS
     def knn(self, query, ref, K: int = 1):

@@ -165,8 +165,19 @@ int avc_mc_emit(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], cons
                 float* verts /*[dev] (cap_v,3)*/, float* normals /*[dev] (cap_v,3)|NULL*/, int32_t* faces /*[dev] (cap_f,3)*/,
                 int64_t cap_v, int64_t cap_f, void* stream);
 
+/* Capacity-bounded, fully ASYNCHRONOUS extraction (no host round trip for the data-dependent sizes): one fused
+ * classify + chained-scan pass, one thread per vertex, one thread per triangle, all enqueued on `stream`. counts [dev] receives
+ * 4 x int64: {n_verts (owned), n_faces, n_verts including the next slab's first plane (ids >= n_verts, see x_halo_hi), overflow
+ * flags: bit 0 = n_verts > cap_v, bit 1 = n_faces > cap_f}. The counts are always exact; when a flag is set the buffers hold the
+ * first cap_v vertices / cap_f faces and the caller must re-run with larger buffers (never a silent truncation: the flag is the
+ * error). The caller reads `counts` whenever it needs the sizes (after synchronising `stream`).                               */
+int avc_mc_extract(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], const float bounds[6] /*[host]*/, float iso,
+                   int x_halo_lo, int x_halo_hi, int x_origin, int gres_x,
+                   float* verts /*[dev] (cap_v,3)*/, float* normals /*[dev] (cap_v,3)|NULL*/, int32_t* faces /*[dev] (cap_f,3)*/,
+                   int64_t cap_v, int64_t cap_f, int64_t* counts /*[dev] 4 x int64*/, void* stream);
+
 /* avc_mc_emit for the volume the IMMEDIATELY preceding avc_mc_count call on this context scanned (same pointer, extents, iso, halo):
- * reuses that call's block sums instead of counting and synchronising a second time. The caller guarantees the volume was not
+ * reuses that call's totals instead of counting and synchronising a second time. The caller guarantees the volume was not
  * modified in between; any other library call in between, or any differing argument, silently falls back to avc_mc_emit.       */
 int avc_mc_emit_counted(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[3], const float bounds[6] /*[host]*/, float iso,
                         int x_halo_lo, int x_halo_hi, int x_origin, int gres_x,

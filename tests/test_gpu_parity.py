@@ -250,6 +250,36 @@ def test_mc_emit_counted_reuse_and_fallback(eng):
         assert torch.equal(a, b)
 
 
+def test_mc_extract_capacity_bounded_async(eng):
+    """avc_mc_extract: no host round trip, device-side counts; too small a capacity sets the overflow flag, keeps the counts exact
+    and fills the first cap entries -- never a silent truncation. Many blocks (the chained look-back scan) and both iso values."""
+    rs = np.random.RandomState(21)
+    bounds = np.array([[-1, -1, -0.4], [1, 1, 0.4]], np.float32)
+    from oracle import mesh_oracle as mo
+    for shape, iso in (((96, 80, 64), 0.0), ((50, 33, 27), 0.3)):
+        vol_np = rs.normal(0, 1, shape).astype(np.float32)
+        vol = torch.from_numpy(vol_np).to(eng.device)
+        rv, rf, rn = mo.recon_mesh(vol_np, shape, bounds, iso)
+        nv, nf = rv.shape[0], rf.shape[0]
+        assert eng.mc_count(vol, iso) == (nv, nf)
+        v, f, n, counts = eng.extract_mesh_async(vol, bounds, iso, nv + 100, nf + 7)
+        c = counts.tolist()
+        assert c[0] == nv and c[1] == nf and c[2] == nv and c[3] == 0
+        assert np.array_equal(f[:nf].cpu().numpy(), rf) and maxabs(v[:nv].cpu().numpy(), rv) < 1e-6
+        for cap_v, cap_f, flags in ((nv // 2, nf + 1, 1), (nv, nf // 3, 2), (0, 0, 3)):
+            v2, f2, n2, c2 = eng.extract_mesh_async(vol, bounds, iso, cap_v, cap_f)
+            c2 = c2.tolist()
+            assert c2[:3] == [nv, nf, nv] and c2[3] == flags
+            assert torch.equal(v2[:min(cap_v, nv)], v[:min(cap_v, nv)]) and torch.equal(f2[:min(cap_f, nf)], f[:min(cap_f, nf)])
+        # the front end retries an overflow with the exact sizes and remembers them
+        eng._keep['mc_hint'] = (16, 16)
+        v3, f3, n3 = eng.extract_mesh(vol, bounds, iso)
+        assert torch.equal(v3, v[:nv]) and torch.equal(f3, f[:nf]) and torch.equal(n3, n[:nv])
+        for _ in range(3):                                   # repeated runs are deterministic (ticket order does not leak into the result)
+            v4, f4, n4 = eng.extract_mesh(vol, bounds, iso)
+            assert torch.equal(v4, v3) and torch.equal(f4, f3)
+
+
 def test_mesh_normals_vs_reference_golden(eng):
     """Sobel + trilinear normals against the reference's own conv3d / grid_sample output (mesh_golden.npz)."""
     from oracle import mesh_oracle as mo
@@ -276,14 +306,13 @@ def test_mesh_slabs_equal_whole(eng, res):
     v, f, n = eng.extract_mesh(torch.from_numpy(vol), bounds, 0.0)
     rv, rf, rn = mo.recon_mesh(vol, res, bounds, 0.0)
     assert np.array_equal(f.cpu().numpy(), rf) and maxabs(v.cpu().numpy(), rv) < 1e-6
-    # the A/B knobs select the older code paths: same mesh bit for bit
-    for knob in ('AVC_MC_SCALAR', 'AVC_MC_FACES'):
-        os.environ[knob] = '1' if knob == 'AVC_MC_SCALAR' else 'voxel'
-        try:
-            v2, f2, n2 = eng.extract_mesh(torch.from_numpy(vol), bounds, 0.0)
-        finally:
-            del os.environ[knob]
-        assert torch.equal(v2, v) and torch.equal(f2, f) and torch.equal(n2, n)
+    # the A/B knob selects the scalar classification path: same mesh bit for bit
+    os.environ['AVC_MC_SCALAR'] = '1'
+    try:
+        v2, f2, n2 = eng.extract_mesh(torch.from_numpy(vol), bounds, 0.0)
+    finally:
+        del os.environ['AVC_MC_SCALAR']
+    assert torch.equal(v2, v) and torch.equal(f2, f) and torch.equal(n2, n)
     for world in (2, 3, 5):
         parts = []
         for r in range(world):
