@@ -15,6 +15,8 @@ MAP_POSE, MAP_IMAGE = 0, 1
 KIND_AVATAR, KIND_RECON = 0, 1
 WEIGHT_SLOTS = 4
 ABI_VERSION = 5
+SHARD_HEADER_BYTES = 256
+IPC_HANDLE_BYTES = 64
 RASTER_CULL_BACK, RASTER_FLIP_X = 1, 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -50,6 +52,14 @@ SIGNATURES = {
     'avc_mc_emit': (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_f), _f, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i64, _vp]),
     'avc_mc_extract': (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_f), _f, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     'avc_mc_emit_counted': (_i, [_vp, _vp, C.POINTER(_i), C.POINTER(_f), _f, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _i64, _vp]),
+    'avc_shard_alloc': (_i, [_vp, C.c_size_t, C.POINTER(_vp), _vp]),
+    'avc_shard_open': (_i, [_vp, _vp, C.POINTER(_vp)]),
+    'avc_shard_close': (_i, [_vp, _vp]),
+    'avc_shard_free': (_i, [_vp, _vp]),
+    'avc_halo_push': (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i64, _i, _i64, C.c_uint64, _vp]),
+    'avc_halo_wait': (_i, [_vp, _vp, _i, _i, C.c_uint64, _vp]),
+    'avc_halo_ack': (_i, [_vp, _vp, _vp, C.c_uint64, _vp]),
+    'avc_renumber_faces': (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _vp]),
     'avc_knn': (_i, [_vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     'avc_near_flag': (_i, [_vp, _vp, _i64, _vp, _i, C.c_double, _vp, _vp]),
     'avc_lbs_weights': (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),

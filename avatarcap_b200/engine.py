@@ -133,13 +133,19 @@ class Engine:
 
     # ------------------------------------------------------------------ field evaluation (device tensors)
     def eval_occupancy(self, pts, center, want_offsets: bool = True, want_texture: bool = False, if_type: str = 'sdf',
-                       impl: Optional[str] = None) -> Dict[str, torch.Tensor]:
-        """OccupancyNet.query body for one batch element: pts (N,3), center (3,) -> occ (N,), off (N,3)[, rgb (N,3), alpha (N,)]."""
+                       impl: Optional[str] = None, out_occ: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """OccupancyNet.query body for one batch element: pts (N,3), center (3,) -> occ (N,), off (N,3)[, rgb (N,3), alpha (N,)].
+        out_occ: write the occupancy into this contiguous (N,) device tensor (e.g. a slab of a larger volume) instead of a new one."""
         if if_type not in ('sdf', 'occupancy'):
             raise ValueError('Invalid config.if_type!')
         p = self._f32(pts, 3)
         n = p.shape[0]
-        occ = torch.empty(n, device=self.device, dtype=torch.float32)
+        if out_occ is not None:
+            if out_occ.device != self.device or out_occ.dtype != torch.float32 or out_occ.numel() != n or not out_occ.is_contiguous():
+                raise ValueError('out_occ must be a contiguous float32 device tensor with one element per point')
+            occ = out_occ.view(-1)
+        else:
+            occ = torch.empty(n, device=self.device, dtype=torch.float32)
         off = torch.empty((n, 3), device=self.device, dtype=torch.float32) if want_offsets else None
         rgb = torch.empty((n, 3), device=self.device, dtype=torch.float32) if want_texture else None
         alpha = torch.empty(n, device=self.device, dtype=torch.float32) if want_texture else None
@@ -260,6 +266,12 @@ class Engine:
             raise AvcError(_lib.ECAPACITY, 'marching cubes overflowed its exact-size retry')
         self._keep['mc_hint'] = (max(4096, nv + nv // 4), max(8192, nf + nf // 4))
         return verts[:nv], faces[:nf], (normals[:nv] if with_normals else None)
+
+    def renumber_faces(self, faces: torch.Tensor, n_own: int, base_own: int, base_next: int) -> None:
+        """Slab-mesh seam rule, in place on an (F,3) int32 device tensor (shard.gather_mesh)."""
+        if faces.dtype != torch.int32 or not faces.is_contiguous() or faces.device != self.device:
+            raise ValueError('faces must be a contiguous int32 tensor on the engine device')
+        self._check(self.lib.avc_renumber_faces(self._h, _ptr(faces), faces.shape[0], int(n_own), int(base_own), int(base_next), self._stream()))
 
     # ------------------------------------------------------------------ KNN / LBS
     def knn(self, query, ref, K: int = 1):

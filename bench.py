@@ -27,9 +27,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_PT = {'occ': 1_773_568, 'occ+tex': 1_970_944, 'recon': 387_072}     # SURVEY.md section 8 / BASELINE.md section 2
-# dram__bytes_read.sum + dram__bytes_write.sum of field_tc2_kernel at 256^3, one launch (profiles/r1_ncu_tc2_256cube.md: 229.7 + 487.8 MB)
-NCU_TRAFFIC_BYTES = 717_489_152
 GRIDS = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512, 512, 512)}
+STRONG_GRID = (256, 256, 256)                                                # BASELINE metric: "@256^3 (1/2/4/8 GPU)"
+
+
+def ncu_traffic(kernel: str, entry: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the bench workload, from the committed
+    `ncu --set full` capture (profiles/field_traffic.json, written by profiles/ncu_summary.py from the .ncu-rep): a profiler
+    cannot run inside the timed region, so this is the capture of the same command, not a constant in the source. None when no
+    capture matches the kernel + entry point of this run."""
+    p = os.path.join(ROOT, 'profiles', 'field_traffic.json')
+    try:
+        for rec in json.load(open(p)):
+            if rec.get('kernel') == kernel and rec.get('entry') == entry:
+                return int(rec['dram_bytes']), rec.get('source')
+    except Exception:
+        pass
+    return None, None
 
 
 def host_cores() -> int:
@@ -108,6 +122,38 @@ def cpu_reference_rate(scene, pts: np.ndarray, seconds_budget: float, threads: i
     fo.occupancy_query(scene['avatar_sd'], sample, scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)
     dt = time.perf_counter() - t0
     return n / dt / 1e6, n, dt
+
+
+def gpu_torch_reference(scene, pts_dev, tf32: bool, chunk: int = 262144):
+    """The reference's own GPU path, restated: the oracle port (the same torch ops as network/mlp.py / arch_avatar.py, one
+    matmul + element-wise kernels per layer, every activation through HBM) run on the B200 in f32, in the reference's chunks of
+    262 144 points (arch_avatar.py:366), over the WHOLE grid of this rank. tf32 = torch 1.8's default for convolutions and
+    matmuls on sm_80+ (README.md:19, requirements.txt:10). -> (Mpts/s, ms, max |occ - ours| is checked by the caller)."""
+    import torch
+    from oracle import field_oracle as fo
+    dev = pts_dev.device
+    sd = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in scene['avatar_sd'].items()}
+    fm = torch.from_numpy(scene['pose_map']).to(dev); c = torch.from_numpy(scene['frame']['cano_smpl_center']).to(dev)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = tf32; torch.backends.cudnn.allow_tf32 = tf32
+    try:
+        n = pts_dev.shape[0]
+        occ = torch.empty(n, device=dev)
+
+        def run(m):
+            with torch.no_grad():
+                for i in range(0, m, chunk):
+                    p = pts_dev[i:i + chunk]
+                    off = fo.warp_query(sd, p, fm, c)
+                    rgb, alpha, o = fo.template_forward(sd, p + off)
+                    occ[i:i + chunk] = o[:, 0]
+        run(min(n, 4 * chunk)); torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); run(n); b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return n / ms / 1e3, ms, occ
 
 
 def build_scene():
@@ -204,9 +250,12 @@ def run_ours(args):
     n = pts.shape[0]
     center = frame['cano_smpl_center']
     n_out = {'occ': None}
+    # this rank's slab of the volume, padded for the halo planes: the field kernel writes the occupancy straight into it
+    # (collective constructor: CUDA IPC handles of the padded buffers are exchanged once, here, outside every timed region)
+    sv = shard.SlabVolume(res, world, rank, engine=eng, mode=args.halo)
 
     def step():
-        n_out['o'] = eng.eval_occupancy(pts, center, want_offsets=True, want_texture=True, impl=impl)
+        n_out['o'] = eng.eval_occupancy(pts, center, want_offsets=True, want_texture=True, impl=impl, out_occ=sv.own.view(-1))
 
     def barrier():
         if world > 1:
@@ -238,14 +287,6 @@ def run_ours(args):
         nt = torch.tensor([n], device=dev, dtype=torch.int64); dist.all_reduce(nt); n_all = int(nt[0])
     value = n_all * args.steps / (total_ms * 1e-3) / 1e6
 
-    # ---- mesh extraction (ms/frame): halo exchange (the path's one collective) + marching cubes + normals, per shard
-    occ = n_out['o']['occ'].reshape(x1 - x0, res[1], res[2])
-    lo, hi = shard.halo_planes(res[0], x0, x1)
-
-    def mesh_step():
-        vol = shard.exchange_halo(occ, rank, world, res[0]) if world > 1 else occ
-        return eng.extract_mesh(vol, frame['cano_bounds'], 0.0, True, lo, hi, x0 - lo, res[0])
-
     def median_ms(fn, reps):
         """Per-repetition CUDA-event times, median (one allocator / driver hiccup must not masquerade as kernel time); returns (ms, last result)."""
         fn(); torch.cuda.synchronize()
@@ -256,17 +297,131 @@ def run_ours(args):
             ts.append(a0.elapsed_time(a1))
         return float(np.median(ts)), out
 
+    # ---- mesh extraction (ms/frame): the path's one exchange step (boundary planes pushed into the neighbours' buffers over
+    # NVLink by our own kernel) + marching cubes + normals per shard, then the count-then-payload gather of the single mesh the
+    # reference's caller expects (recon_util.py:51-70) onto rank 0
+    occ = sv.own
+    hint = {}
+
+    def mesh_step():
+        sv.exchange()
+        nvox = sv.padded.numel()
+        cv_, cf_ = hint.get('cap', (max(4096, nvox // 16), max(8192, nvox // 8)))
+        while True:
+            v_, f_, n_, c_ = eng.extract_mesh_async(sv.padded, frame['cano_bounds'], 0.0, cv_, cf_, True, sv.lo, sv.hi, sv.x0 - sv.lo, res[0])
+            c_ = [int(x) for x in c_.tolist()]
+            if not c_[3]:
+                break
+            cv_, cf_ = max(c_[0], 1), max(c_[1], 1)
+        sv.release()
+        hint['cap'] = (c_[0] + c_[0] // 8 + 1024, c_[1] + c_[1] // 8 + 1024)
+        return v_, f_, n_, c_
+
     barrier()
-    mesh_ms, (v, f, nrm) = median_ms(mesh_step, 5)
+    mesh_ms, (v, f, nrm, cnt) = median_ms(mesh_step, 5)
     barrier()
+    gather_ms = 0.0
+    merged = None
+    if world > 1:
+        def gather_step():
+            return shard.gather_mesh(v, f.clone(), nrm, cnt[0], cnt[1], rank, world, eng)       # clone: the renumbering is in place
+        gather_ms, merged = median_ms(gather_step, 3)
+        barrier()
+    v, f, nrm = v[:cnt[0]], f[:cnt[1]], nrm[:cnt[0]]
     cv = torch.from_numpy(frame['cano_smpl_v']).to(dev); sw = torch.from_numpy(frame['smpl_skinning_weights']).to(dev)
     jm = torch.from_numpy(frame['cano2live_jnt_mats']).to(dev)
     eng.skin_mesh(v, nrm, cv, sw, jm); torch.cuda.synchronize()
     lbs_ms, _ = median_ms(lambda: eng.skin_mesh(v, nrm, cv, sw, jm), 3)
-    mt = torch.tensor([mesh_ms, lbs_ms], device=dev, dtype=torch.float64)
+    mt = torch.tensor([mesh_ms, lbs_ms, gather_ms], device=dev, dtype=torch.float64)
     nv = torch.tensor([v.shape[0], f.shape[0]], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(mt, op=dist.ReduceOp.MAX); dist.all_reduce(nv)
+
+    # ---- parity on real ranks (BASELINE config[3]/[4]): the merged mesh of the sharded volume must EQUAL the mesh one GPU extracts
+    # from the whole volume -- vertices, normals and faces bit for bit
+    merge_equal = None
+    if world > 1 and not args.no_parity:
+        parts = [torch.empty((shard.slab_range(res[0], world, r)[1] - shard.slab_range(res[0], world, r)[0], res[1], res[2]), device=dev)
+                 for r in range(world)] if rank == 0 else None
+        dist.gather(occ.contiguous(), parts, dst=0)
+        if rank == 0:
+            whole = torch.cat(parts, 0); del parts
+            wv, wf, wn = eng.extract_mesh(whole, frame['cano_bounds'], 0.0)
+            mv_, mf_, mn_, _ = merged
+            merge_equal = bool(wv.shape == mv_.shape and wf.shape == mf_.shape and torch.equal(wv, mv_) and torch.equal(wf, mf_) and torch.equal(wn, mn_))
+            del whole, wv, wf, wn
+        barrier()
+    merged = None
+
+    # ---- strong scaling (BASELINE metric "@256^3 (1/2/4/8 GPU)"): ONE 256^3 frame split over the N GPUs, everything a frame needs
+    # inside the timed region: field evaluation of the slab -> halo push / wait -> marching cubes + normals per slab -> counts
+    # all-gather -> payload gather of the single mesh onto rank 0.
+    strong = None
+    if not args.no_strong:
+        sres = STRONG_GRID if args.res is None else (args.res,) * 3
+        ssv = sv if (world == 1 and tuple(res) == tuple(sres)) else shard.SlabVolume(sres, world, rank, engine=eng, mode=args.halo)
+        spts = pts if ssv is sv else eng.make_grid(frame['cano_bounds'], sres, ssv.x0, ssv.nx)
+        shint = {}
+        parts_ms = {'field': [], 'mesh': [], 'gather': []}
+
+        def strong_step(record):
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
+            eng.eval_occupancy(spts, center, want_offsets=True, want_texture=True, impl=impl, out_occ=ssv.own.view(-1))
+            e1.record()
+            ssv.exchange()
+            nvox = ssv.padded.numel()
+            cv_, cf_ = shint.get('cap', (max(4096, nvox // 16), max(8192, nvox // 8)))
+            v_, f_, n_, c_ = eng.extract_mesh_async(ssv.padded, frame['cano_bounds'], 0.0, cv_, cf_, True, ssv.lo, ssv.hi, ssv.x0 - ssv.lo, sres[0])
+            allc = shard._all_counts(c_, world)
+            if allc[:, 3].any():
+                if allc[rank, 3]:
+                    v_, f_, n_, c_ = eng.extract_mesh_async(ssv.padded, frame['cano_bounds'], 0.0, max(int(allc[rank, 0]), 1), max(int(allc[rank, 1]), 1),
+                                                            True, ssv.lo, ssv.hi, ssv.x0 - ssv.lo, sres[0])
+                allc = shard._all_counts(c_, world)
+            ssv.release()
+            e2.record()
+            shint['cap'] = (int(allc[rank, 0]) * 9 // 8 + 1024, int(allc[rank, 1]) * 9 // 8 + 1024)
+            out = shard.gather_mesh(v_, f_, n_, int(allc[rank, 0]), int(allc[rank, 1]), rank, world, eng, counts=allc)
+            e3.record()
+            if record:
+                record.append((e0, e1, e2, e3))
+            return out
+
+        for _ in range(3):
+            strong_step(None)
+        barrier()
+        recs = []
+        ks = max(1, min(args.steps, 10))
+        for _ in range(ks):
+            sm = strong_step(recs)
+        barrier()
+        s_total = recs[0][0].elapsed_time(recs[-1][3])
+        s_parts = [float(np.mean([r[i].elapsed_time(r[i + 1]) for r in recs])) for i in range(3)]
+        st = torch.tensor([s_total] + s_parts, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        s_equal = None
+        if world > 1 and not args.no_parity:
+            sparts = [torch.empty((shard.slab_range(sres[0], world, r)[1] - shard.slab_range(sres[0], world, r)[0], sres[1], sres[2]), device=dev)
+                      for r in range(world)] if rank == 0 else None
+            dist.gather(ssv.own.contiguous(), sparts, dst=0)
+            if rank == 0:
+                whole = torch.cat(sparts, 0); del sparts
+                wv, wf, wn = eng.extract_mesh(whole, frame['cano_bounds'], 0.0)
+                s_equal = bool(wv.shape == sm[0].shape and wf.shape == sm[1].shape and torch.equal(wv, sm[0]) and torch.equal(wf, sm[1]) and torch.equal(wn, sm[2]))
+                del whole, wv, wf, wn
+            barrier()
+        npts = int(np.prod(sres))
+        limiter = max((('field evaluation', float(st[1])), ('halo exchange + marching cubes', float(st[2])), ('mesh gather', float(st[3]))), key=lambda kv: kv[1])
+        strong = {'grid': list(sres), 'value': npts * ks / (float(st[0]) * 1e-3) / 1e6, 'unit': 'Mpoints/s', 'scaling': 'strong', 'steps': ks,
+                  'ms_per_frame': float(st[0]) / ks, 'field_ms': float(st[1]), 'halo_mc_ms': float(st[2]), 'gather_ms': float(st[3]),
+                  'limiter': limiter[0], 'halo': ssv.mode if world > 1 else 'none', 'mesh_merge_equal': s_equal,
+                  'mesh_vertices': int(sm[3][:, 0].sum()), 'mesh_faces': int(sm[3][:, 1].sum()),
+                  'timed': 'field (occ+off+rgb+alpha) of the slab -> halo push/wait -> MC + normals -> counts all-gather -> payload gather to rank 0; max over ranks'}
+        del sm
+        if ssv is not sv:
+            barrier(); ssv.close()
 
     # ---- the reference's own per-frame geometry pipeline (main.py:357-389), MASKED like the reference: only grid points within
     # 10 cm of the body are evaluated, the rest is +-1 fill; N=1 only. Reported as `frame` (ms per stage), not part of `value`.
@@ -382,9 +537,26 @@ def run_ours(args):
                'd2h_bytes_per_step': int(n_all * 32), 'steps': k2, 'api': 'avc_eval_occupancy_host (pinned staging, 3-stream pipeline)'}
         assert float(np.abs(occ_h - n_out['o']['occ'].cpu().numpy()).max()) == 0.0
 
+    # ---- the reference's GPU PyTorch path on the same B200 (north_star: ">= 10x the reference PyTorch path on 1xB200 at 256^3"):
+    # oracle port on cuda, full 256^3, f32 with TF32 off (accuracy-matched) and TF32 on (torch 1.8's default)
+    gpu_torch = None
+    if world == 1 and not args.no_gpu_torch:
+        try:
+            ours = n_out['o']['occ']
+            gpu_torch = {'unit': 'Mpoints/s', 'points': int(n), 'chunk': 262144, 'what': 'oracle port of OccupancyNet.query + texture head, torch %s on cuda, '
+                         'one matmul + element-wise kernels per layer (the reference\'s structure)' % torch.__version__}
+            for tag, tf32 in (('f32', False), ('tf32', True)):
+                mp, ms, occ_t = gpu_torch_reference(scene, pts, tf32)
+                gpu_torch[tag] = {'value': mp, 'ms': ms, 'max_abs_vs_ours': float((occ_t - ours).abs().max())}
+                del occ_t
+            torch.cuda.empty_cache()
+        except Exception as ex:                                       # a baseline must never sink the headline measurement
+            gpu_torch = {'error': repr(ex)[:300]}
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         flop = FLOP_PER_PT['occ+tex']
+        traffic, traffic_src = ncu_traffic('field_tc2_kernel', 'avc_eval_occupancy') if (args.gpus == 1 and args.res is None and impl == 'tc2') else (None, None)
         ach = n * flop / (kernel_ms * 1e-3) / 1e12
         peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
         line = {
@@ -398,13 +570,18 @@ def run_ours(args):
                        'grid': list(res), 'points_per_gpu': n, 'kernel': impl, 'flop_per_point': flop,
                        'l2_policy': 'inputs (201 MB of points) + outputs (537 MB) exceed the 126 MB L2 every step'},
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                         'traffic': NCU_TRAFFIC_BYTES if (args.gpus == 1 and args.res is None) else None, 'peak_source': peak_src + ', sustained bf16 (kernel timed inside a long step)',
+                         'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src + ', sustained bf16 (kernel timed inside a long step)',
                          'note': 'algorithmic FLOPs (1x); the tcgen05 kernel issues 3x that as fp16 hi/lo passes'},
-            'mesh_extract_ms': float(mt[0]), 'lbs_skin_ms': float(mt[1]), 'mesh_vertices': int(nv[0]), 'mesh_faces': int(nv[1]),
+            'mesh_extract_ms': float(mt[0]), 'mesh_gather_ms': float(mt[2]), 'lbs_skin_ms': float(mt[1]), 'mesh_vertices': int(nv[0]), 'mesh_faces': int(nv[1]),
+            'mesh_merge_equal': merge_equal, 'halo': sv.mode if world > 1 else 'none',
             'clocks': clocks, 'gpu_launches': int(launches), 'wall_s': t_wall,
         }
         if e2e:
             line['e2e'] = e2e
+        if strong:
+            line['strong'] = strong
+        if gpu_torch:
+            line['gpu_torch_baseline'] = gpu_torch
         if frame_ms:
             line['frame'] = frame_ms
         if frames_out:
@@ -416,6 +593,9 @@ def run_ours(args):
             line['cpu_baseline'] = {'value': v_cpu, 'unit': 'Mpoints/s', 'cores': threads, 'kind': 'port',
                                     'sample': '%d-point sub-lattice of the same grid, %.1f s, torch CPU f32 oracle port' % (n_cpu, secs)}
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+    sv.close()
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     eng.close()
@@ -432,6 +612,10 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-frame', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling block (one 256^3 frame split over the N GPUs)')
+    ap.add_argument('--no-parity', action='store_true', help='skip the merged-mesh == single-GPU-mesh check on real ranks')
+    ap.add_argument('--no-gpu-torch', action='store_true', help='skip the reference-on-GPU (PyTorch) baseline')
+    ap.add_argument('--halo', default='auto', choices=['auto', 'p2p', 'sendrecv'], help='slab exchange: our peer-memory kernels (CUDA IPC) or NCCL send/recv')
     ap.add_argument('--frames-per-gpu', type=int, default=2, help='frame-parallel replicas (BASELINE config[5]); 0 disables')
     args = ap.parse_args()
     if args.gpus not in GRIDS:

@@ -185,6 +185,35 @@ int avc_mc_emit_counted(avc_ctx* ctx, const float* vol /*[dev]*/, const int res[
                         int64_t cap_v, int64_t cap_f, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- */
+/* multi-GPU slab exchange over peer memory (one process per GPU)            */
+/* The reference evaluates one volume on one GPU (main.py:357-367); sharding it in x-slabs needs ONE exchange step: marching
+ * cubes + normals on a slab read 2 planes of the slab below and 3 of the slab above. Each rank owns a padded buffer
+ *   [AVC_SHARD_HEADER_BYTES of flags | float data: lo halo | own planes | hi halo]
+ * allocated here (cudaMalloc) and exported as a CUDA IPC handle; the neighbours open it and STORE their boundary planes into it
+ * over NVLink from a kernel (avc_halo_push) -- no NCCL call, no staging copy, no host synchronisation. Offsets below are in
+ * float elements from the start of the data area. `epoch` counts exchanges from 1, identically on all ranks.
+ * Call order per volume on every rank, all on one stream:  field evaluation into `own` -> avc_halo_push -> avc_halo_wait ->
+ * avc_mc_extract on [lo | own | hi] -> avc_halo_ack.                                                                          */
+#define AVC_SHARD_HEADER_BYTES 256
+#define AVC_IPC_HANDLE_BYTES 64
+int avc_shard_alloc(avc_ctx* ctx, size_t data_bytes, void** out_base /*[dev] buffer incl. header*/, void* out_handle /*[host] 64 B*/);
+int avc_shard_open(avc_ctx* ctx, const void* handle /*[host] 64 B, from a peer process*/, void** out_base /*[dev], mapped peer memory*/);
+int avc_shard_close(avc_ctx* ctx, void* base /*from avc_shard_open*/);
+int avc_shard_free(avc_ctx* ctx, void* base /*from avc_shard_alloc; synchronises the device*/);
+/* store my first n_to_lo planes into the lower neighbour's buffer at lo_dst_off and my last n_to_hi planes into the upper
+ * neighbour's at hi_dst_off (peer_* = NULL: no such neighbour), after both have acknowledged epoch-1; then publish `epoch` */
+int avc_halo_push(avc_ctx* ctx, void* mine, void* peer_lo, void* peer_hi, int64_t plane_elems, int64_t own_off, int nx,
+                  int n_to_lo, int64_t lo_dst_off, int n_to_hi, int64_t hi_dst_off, uint64_t epoch, void* stream);
+/* stream-ordered wait (a spinning one-thread kernel with a 20 s watchdog) until the neighbours' planes of `epoch` have arrived */
+int avc_halo_wait(avc_ctx* ctx, void* mine, int need_lo, int need_hi, uint64_t epoch, void* stream);
+/* tell the neighbours that their planes of `epoch` have been consumed (enqueue after the kernels that read the halo) */
+int avc_halo_ack(avc_ctx* ctx, void* peer_lo, void* peer_hi, uint64_t epoch, void* stream);
+/* seam rule of the slab meshes: local ids < n_own -> + base_own, ids >= n_own (the next slab's first-plane vertices, numbered
+ * behind the slab's own by avc_mc_extract) -> - n_own + base_next. In place.                                               */
+int avc_renumber_faces(avc_ctx* ctx, int32_t* faces /*[dev] (n_faces,3)*/, int64_t n_faces, int64_t n_own, int64_t base_own,
+                       int64_t base_next, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
 /* LBS -- replaces utils/smpl_util.py and the pytorch3d KNN it calls                              */
 /* ---------------------------------------------------------------------------------------------- */
 /* pytorch3d.ops.knn_points (K<=4) against a small reference set (m <= 16384): squared L2 ascending.

@@ -182,27 +182,69 @@ _WORKER = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, %r)
 from avatarcap_b200 import shard
+from oracle import mesh_oracle as mo
 rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE'])
 dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% os.environ['MASTER_PORT'], rank=rank, world_size=world)
-rs = np.random.RandomState(0); res = (11, 4, 5)
-vol = torch.from_numpy(rs.normal(0, 1, res).astype(np.float32))
+rs = np.random.RandomState(0); res = (13, 6, 5)
 s, e = shard.slab_range(res[0], world, rank)
-out = shard.exchange_halo(vol[s:e].contiguous(), rank, world, res[0])
 lo, hi = shard.halo_planes(res[0], s, e)
+# 1. functional form
+vol = torch.from_numpy(rs.normal(0, 1, res).astype(np.float32))
+out = shard.exchange_halo(vol[s:e].contiguous(), rank, world, res[0])
 assert torch.equal(out, vol[s - lo:e + hi]), (rank, out.shape)
+# 2. SlabVolume: the field output lands in `own`, the neighbours' planes in the halo regions, no concatenation; several epochs
+sv = shard.SlabVolume(res, world, rank, device='cpu')
+assert sv.mode == 'sendrecv' and (sv.x0, sv.x1, sv.lo, sv.hi) == (s, e, lo, hi)
+assert sv.padded.data_ptr() + 4 * sv.lo * sv.plane == sv.own.data_ptr()            # one buffer, two views
+for epoch in range(3):
+    vol = torch.from_numpy(rs.normal(0, 1, res).astype(np.float32))
+    sv.own.copy_(vol[s:e])
+    sv.exchange()
+    assert torch.equal(sv.padded, vol[s - lo:e + hi]), (rank, epoch)
+    sv.release()
+# 3. count-then-payload mesh gather: slab meshes cut out of the oracle's whole mesh by vertex / face ownership, numbered the way
+#    the kernel numbers them (own vertices first, then the next slab's first-plane vertices)
+vnp = vol.numpy()
+v, f, vox, axis, cells = mo.marching_cubes(vnp, 0.0, return_owner=True)
+n = np.random.RandomState(1).normal(0, 1, v.shape).astype(np.float32)
+plane = res[1] * res[2]
+vplane = vox // plane; fplane = cells // plane
+ranges = [shard.slab_range(res[0], world, r) for r in range(world)]
+vb = [int((vplane < a).sum()) for a, _ in ranges] + [len(v)]
+mine_v = slice(vb[rank], vb[rank + 1])
+fsel = (fplane >= s) & (fplane < e)
+fl = f[fsel].astype(np.int64)
+n_own = vb[rank + 1] - vb[rank]
+local = np.where(fl < vb[rank + 1], fl - vb[rank], n_own + (fl - vb[rank + 1]))
+assert local.min(initial=0) >= 0
+pad = 7                                                                       # capacity buffers are larger than the counts
+tv = torch.zeros((n_own + pad, 3)); tv[:n_own] = torch.from_numpy(v[mine_v])
+tn = torch.zeros((n_own + pad, 3)); tn[:n_own] = torch.from_numpy(n[mine_v])
+tf = torch.zeros((len(local) + pad, 3), dtype=torch.int32); tf[:len(local)] = torch.from_numpy(local.astype(np.int32))
+gv, gf, gn, counts = shard.gather_mesh(tv, tf, tn, n_own, len(local), rank, world)
+assert counts.shape == (world, 2) and int(counts[:, 0].sum()) == len(v) and int(counts[:, 1].sum()) == len(f)
+if rank == 0:
+    assert torch.equal(gv, torch.from_numpy(v)) and torch.equal(gn, torch.from_numpy(n))
+    assert np.array_equal(gf.numpy(), f)
+else:
+    assert gv is None and gf is None
 dist.barrier(); dist.destroy_process_group()
 print('ok', rank)
 '''
 
 
-def test_halo_exchange_gloo_world2(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize('world,port', [(2, 29631), (3, 29641)])
+def test_halo_exchange_and_mesh_gather_gloo(tmp_path, world, port):
     script = tmp_path / 'w.py'
     script.write_text(_WORKER % ROOT)
     procs = []
-    for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', MASTER_PORT='29631', MASTER_ADDR='127.0.0.1')
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_PORT=str(port), MASTER_ADDR='127.0.0.1')
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-    outs = [p.communicate(timeout=240)[0] for p in procs]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
 
 
