@@ -41,6 +41,8 @@ SIGNATURES = {
     'avc_set_feature_map': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     'avc_set_feature_map_hwc': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     'avc_eval_occupancy': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    'avc_eval_occupancy_grid': (_i, [_vp, C.POINTER(_f), C.POINTER(_i), _i, _i, C.POINTER(_f), _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    'avc_eval_recon_grid': (_i, [_vp, C.POINTER(_f), C.POINTER(_i), _i, _i, C.POINTER(_f), _vp, _i, _vp]),
     'avc_eval_warp': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _i, _vp]),
     'avc_eval_template': (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp]),
     'avc_eval_recon': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _i, _vp]),

@@ -72,6 +72,7 @@ extern "C" void avc_ctx_destroy(avc_ctx* ctx) {
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_scratch2) cudaFree(ctx->d_scratch2);
   if (ctx->d_grid) cudaFree(ctx->d_grid);
+  if (ctx->d_gridpts) cudaFree(ctx->d_gridpts);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -208,10 +209,27 @@ static int pick_impl(avc_ctx* ctx, int* impl_io, bool* use_tc) {
   return avc_fail(ctx, AVC_EINVAL, "bad impl %d", impl);
 }
 
-static int eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* occ, float* off, float* rgb, float* alpha,
-                       int if_type, int impl, int mode, cudaStream_t st) {
+// dense-grid entry on the fp32 SIMT implementation (the cross-check path): the points are materialised once into a context buffer
+static int grid_points(avc_ctx* ctx, const AvcGridDesc* g, int64_t n, const float** pts, cudaStream_t st) {
+  const size_t need = (size_t)n * 3 * sizeof(float);
+  if (need > ctx->gridpts_cap) {
+    if (ctx->d_gridpts) { AVC_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(ctx->d_gridpts); }
+    ctx->d_gridpts = nullptr; ctx->gridpts_cap = 0;
+    AVC_CUDA(ctx, cudaMalloc(&ctx->d_gridpts, need));
+    ctx->gridpts_cap = need;
+  }
+  const float bounds[6] = {g->bmin[0], g->bmin[1], g->bmin[2], g->bmin[0] + g->len[0], g->bmin[1] + g->len[1], g->bmin[2] + g->len[2]};
+  const int64_t plane = (int64_t)g->res[1] * g->res[2];
+  int rc = avc_make_grid(ctx, bounds, g->res, g->x_first, (int)(n / plane), (float*)ctx->d_gridpts, st);
+  if (rc) return rc;
+  *pts = (const float*)ctx->d_gridpts;
+  return AVC_OK;
+}
+
+static int eval_avatar(avc_ctx* ctx, const float* pts, const AvcGridDesc* grid, int64_t n, const float center[3], float* occ, float* off, float* rgb,
+                       float* alpha, int if_type, int impl, int mode, cudaStream_t st) {
   if (!ctx) return AVC_EINVAL;
-  if (n < 0 || (n > 0 && !pts)) return avc_fail(ctx, AVC_EINVAL, "field eval: bad points");
+  if (n < 0 || (n > 0 && !pts && !grid)) return avc_fail(ctx, AVC_EINVAL, "field eval: bad points");
   if (if_type != AVC_IF_SDF && if_type != AVC_IF_OCCUPANCY) return avc_fail(ctx, AVC_EVALUE, "Invalid config.if_type!");   // arch_avatar.py:82
   if (!ctx->avatar.loaded) return avc_fail(ctx, AVC_ESTATE, "avatar weights not loaded");
   if (mode != AVC_MODE_TEMPLATE_ONLY && (!ctx->maps[AVC_MAP_POSE].d_hwc || !center))
@@ -220,35 +238,70 @@ static int eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float ce
   if (rc) return rc;
   const float zero[3] = {0, 0, 0};
   const float* c = center ? center : zero;
-  return use_tc ? avc_tc2_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st)
-                : avc_simt_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st);
+  if (use_tc) return avc_tc2_eval_avatar(ctx, pts, grid, n, c, occ, off, rgb, alpha, if_type, mode, st);
+  if (grid && n > 0) { rc = grid_points(ctx, grid, n, &pts, st); if (rc) return rc; }
+  return avc_simt_eval_avatar(ctx, pts, n, c, occ, off, rgb, alpha, if_type, mode, st);
+}
+
+// validates a dense-grid request and fills the descriptor; *n = number of grid points of the slab
+static int make_grid_desc(avc_ctx* ctx, const float bounds[6], const int res[3], int x_first, int x_count, AvcGridDesc* g, int64_t* n) {
+  if (!bounds || !res) return avc_fail(ctx, AVC_EINVAL, "grid eval: NULL argument");
+  if (res[0] < 1 || res[1] < 1 || res[2] < 1 || x_first < 0 || x_count < 0 || x_first + x_count > res[0]) return avc_fail(ctx, AVC_EINVAL, "grid eval: bad grid / slab");
+  for (int c = 0; c < 3; ++c) { g->bmin[c] = bounds[c]; g->len[c] = bounds[3 + c] - bounds[c]; g->res[c] = res[c]; }
+  g->x_first = x_first;
+  *n = (int64_t)x_count * res[1] * res[2];
+  return AVC_OK;
 }
 
 extern "C" int avc_eval_occupancy(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
                                   float* out_rgb, float* out_alpha, int if_type, int impl, void* stream) {
   if (ctx && n > 0 && !out_occ) return avc_fail(ctx, AVC_EINVAL, "avc_eval_occupancy: out_occ is NULL");
-  return eval_avatar(ctx, pts, n, center, out_occ, out_off, out_rgb, out_alpha, if_type, impl, AVC_MODE_QUERY, (cudaStream_t)stream);
+  return eval_avatar(ctx, pts, nullptr, n, center, out_occ, out_off, out_rgb, out_alpha, if_type, impl, AVC_MODE_QUERY, (cudaStream_t)stream);
+}
+
+extern "C" int avc_eval_occupancy_grid(avc_ctx* ctx, const float bounds[6], const int res[3], int x_first, int x_count, const float center[3],
+                                       float* out_occ, float* out_off, float* out_rgb, float* out_alpha, int if_type, int impl, void* stream) {
+  if (!ctx) return AVC_EINVAL;
+  AvcGridDesc g; int64_t n;
+  int rc = make_grid_desc(ctx, bounds, res, x_first, x_count, &g, &n);
+  if (rc) return rc;
+  if (n > 0 && !out_occ) return avc_fail(ctx, AVC_EINVAL, "avc_eval_occupancy_grid: out_occ is NULL");
+  return eval_avatar(ctx, nullptr, &g, n, center, out_occ, out_off, out_rgb, out_alpha, if_type, impl, AVC_MODE_QUERY, (cudaStream_t)stream);
 }
 
 extern "C" int avc_eval_warp(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_off, int impl, void* stream) {
   if (ctx && n > 0 && !out_off) return avc_fail(ctx, AVC_EINVAL, "avc_eval_warp: out_off is NULL");
-  return eval_avatar(ctx, pts, n, center, nullptr, out_off, nullptr, nullptr, AVC_IF_SDF, impl, AVC_MODE_WARP_ONLY, (cudaStream_t)stream);
+  return eval_avatar(ctx, pts, nullptr, n, center, nullptr, out_off, nullptr, nullptr, AVC_IF_SDF, impl, AVC_MODE_WARP_ONLY, (cudaStream_t)stream);
 }
 
 extern "C" int avc_eval_template(avc_ctx* ctx, const float* pts, int64_t n, float* out_rgb, float* out_alpha, float* out_occ, int if_type,
                                  int impl, void* stream) {
-  return eval_avatar(ctx, pts, n, nullptr, out_occ, nullptr, out_rgb, out_alpha, if_type, impl, AVC_MODE_TEMPLATE_ONLY, (cudaStream_t)stream);
+  return eval_avatar(ctx, pts, nullptr, n, nullptr, out_occ, nullptr, out_rgb, out_alpha, if_type, impl, AVC_MODE_TEMPLATE_ONLY, (cudaStream_t)stream);
 }
 
-extern "C" int avc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, int impl, void* stream) {
-  if (!ctx) return AVC_EINVAL;
-  if (n < 0 || (n > 0 && (!pts || !out_ov)) || !center) return avc_fail(ctx, AVC_EINVAL, "avc_eval_recon: bad argument");
+static int eval_recon(avc_ctx* ctx, const float* pts, const AvcGridDesc* grid, int64_t n, const float center[3], float* out_ov, int impl, cudaStream_t st) {
+  if (n < 0 || (n > 0 && ((!pts && !grid) || !out_ov)) || !center) return avc_fail(ctx, AVC_EINVAL, "avc_eval_recon: bad argument");
   if (!ctx->recon.loaded) return avc_fail(ctx, AVC_ESTATE, "recon weights not loaded");
   if (!ctx->maps[AVC_MAP_IMAGE].d_hwc) return avc_fail(ctx, AVC_ESTATE, "image feature map not set");
   bool use_tc; int rc = pick_impl(ctx, &impl, &use_tc);
   if (rc) return rc;
-  return use_tc ? avc_tc2_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream)
-                : avc_simt_eval_recon(ctx, pts, n, center, out_ov, (cudaStream_t)stream);
+  if (use_tc) return avc_tc2_eval_recon(ctx, pts, grid, n, center, out_ov, st);
+  if (grid && n > 0) { rc = grid_points(ctx, grid, n, &pts, st); if (rc) return rc; }
+  return avc_simt_eval_recon(ctx, pts, n, center, out_ov, st);
+}
+
+extern "C" int avc_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, int impl, void* stream) {
+  if (!ctx) return AVC_EINVAL;
+  return eval_recon(ctx, pts, nullptr, n, center, out_ov, impl, (cudaStream_t)stream);
+}
+
+extern "C" int avc_eval_recon_grid(avc_ctx* ctx, const float bounds[6], const int res[3], int x_first, int x_count, const float center[3],
+                                   float* out_ov, int impl, void* stream) {
+  if (!ctx) return AVC_EINVAL;
+  AvcGridDesc g; int64_t n;
+  int rc = make_grid_desc(ctx, bounds, res, x_first, x_count, &g, &n);
+  if (rc) return rc;
+  return eval_recon(ctx, nullptr, &g, n, center, out_ov, impl, (cudaStream_t)stream);
 }
 
 // -----------------------------------------------------------------------------------------------------------------

@@ -70,6 +70,7 @@ struct avc_ctx {
   void* d_scratch = nullptr; size_t scratch_cap = 0;
   void* d_scratch2 = nullptr; size_t scratch2_cap = 0;   // marching cubes: compact edge list
   void* d_grid = nullptr; size_t grid_cap = 0;           // KNN: uniform grid over the reference vertices
+  void* d_gridpts = nullptr; size_t gridpts_cap = 0;     // dense-grid entry on the SIMT implementation: materialised points
   void* h_pinned = nullptr;  size_t pinned_cap = 0;
   void* d_stage = nullptr;   size_t stage_cap = 0;
   cudaStream_t s_copy_in = nullptr, s_compute = nullptr, s_copy_out = nullptr;
@@ -102,10 +103,12 @@ int avc_simt_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float 
                          float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
 int avc_simt_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
 int avc_tc_available(const avc_ctx* ctx);
-// tcgen05 kernel on CTA pairs (field_tc2.cu)
-int avc_tc2_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off,
+// dense-grid descriptor: point g = grid point of flat index g + x_first*Ry*Rz of generate_volume_points (avatarcap_dataset.py:312-326)
+struct AvcGridDesc { float bmin[3], len[3]; int res[3]; int x_first; };
+// tcgen05 kernel on CTA pairs (field_tc2.cu); pts == NULL with grid != NULL: coordinates from the index, nothing read per point
+int avc_tc2_eval_avatar(avc_ctx* ctx, const float* pts, const AvcGridDesc* grid, int64_t n, const float center[3], float* out_occ, float* out_off,
                         float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st);
-int avc_tc2_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
+int avc_tc2_eval_recon(avc_ctx* ctx, const float* pts, const AvcGridDesc* grid, int64_t n, const float center[3], float* out_ov, cudaStream_t st);
 
 // mode for the avatar evaluation
 enum { AVC_MODE_QUERY = 0 /* warp + template */, AVC_MODE_WARP_ONLY = 1, AVC_MODE_TEMPLATE_ONLY = 2 };

@@ -64,7 +64,8 @@ struct TcOp {
 };
 
 struct TcArgs {
-  const float* pts; int64_t n;
+  const float* pts; int64_t n;          // pts == NULL: dense-grid mode, point g = grid point of linear index g (+ the slab offset)
+  float gb[3], gl[3]; int gr[3]; int gx_first;   // grid: bmin, bmax - bmin, resolution, first i-plane   (avatarcap_dataset.py:312-326)
   float cx, cy, cz;
   const float* map; int mC, mH, mW;
   float* out0; float* out_off; float* out_rgb; float* out_alpha;   // out0 = occ (avatar) or ov (recon)
@@ -436,6 +437,37 @@ __device__ __forceinline__ void hidden_pair(uint32_t t0, uint32_t t1, const floa
   if (lane == 0) mbar_arrive_leader_relaxed(bar1, rank);
 }
 
+// torch.linspace(0, 1, steps)[q] in float32 exactly as ATen computes it (and make_grid_kernel restates it)
+__device__ __forceinline__ float lin_coord(int q, int steps) {
+  if (steps <= 1) return 0.f;
+  const float step = __fdiv_rn(1.f, (float)(steps - 1));
+  return q < steps / 2 ? __fmul_rn(step, (float)q) : __fsub_rn(1.f, __fmul_rn(step, (float)(steps - 1 - q)));
+}
+// The 32 points of a warp are consecutive (g0 + lane): their xyz triples are 96 consecutive floats. Three fully coalesced 128-byte
+// accesses + shuffles instead of three stride-12 accesses that each touch 12 sectors.
+__device__ __forceinline__ void load3_coalesced(const float* __restrict__ base /*of the warp's first point*/, int64_t n_left /*valid points from g0*/,
+                                                int lane, float& x, float& y, float& z) {
+  float t[3];
+#pragma unroll
+  for (int u = 0; u < 3; ++u) { const int f = u * 32 + lane; t[u] = (f < 3 * n_left) ? __ldg(base + f) : 0.f; }
+  float c[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int f = 3 * lane + k, src = f & 31, u = f >> 5;          // float f lives in t[u] of lane src
+    const float a = __shfl_sync(0xffffffffu, t[0], src), b = __shfl_sync(0xffffffffu, t[1], src), d = __shfl_sync(0xffffffffu, t[2], src);
+    c[k] = u == 0 ? a : (u == 1 ? b : d);
+  }
+  x = c[0]; y = c[1]; z = c[2];
+}
+__device__ __forceinline__ void store3_coalesced(float* __restrict__ base, int64_t n_left, int lane, float x, float y, float z) {
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int f = u * 32 + lane, p = f / 3, k = f - 3 * p;           // float f = component k of the warp's point p
+    const float a = __shfl_sync(0xffffffffu, x, p), b = __shfl_sync(0xffffffffu, y, p), d = __shfl_sync(0xffffffffu, z, p);
+    if (p < n_left) base[f] = k == 0 ? a : (k == 1 ? b : d);
+  }
+}
+
 struct Taps { int i00, i01, i10, i11; float w00, w01, w10, w11; };
 __device__ __forceinline__ Taps make_taps(float gx, float gy, int H, int W) {   // == field_simt.cu (ATen grid_sample, border, align_corners)
   float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
@@ -466,6 +498,9 @@ __device__ __forceinline__ void gather8(const float* __restrict__ hwc, int C, co
     v[4 * h + 3] = ((a.w * t.w00 + b.w * t.w01) + d.w * t.w10) + e.w * t.w11;
   }
 }
+
+// point g of the launch: read from the caller's list (coalesced over the warp) or generated from the grid index
+__device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, int64_t g_warp0, int lane, float& px, float& py, float& pz);
 
 // One step of the input stage (skip operand of the first layer) for point (px,py,pz) with bilinear taps t:
 //   avatar: h0 in tensor-core order [f0..f63, x, y, z, 0...] (packer permutes the 67 columns accordingly)   arch_avatar.py:121-136
@@ -540,6 +575,25 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
     head(3, EPI_RECON_OUT, 0);
   }
   S.n_ops = n;
+}
+
+__device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, int64_t g_warp0, int lane, float& px, float& py, float& pz) {
+  px = py = pz = 0.f;
+  if (a.pts) {
+    const int64_t left = a.n - g_warp0;                          // warp-uniform
+    if (left > 0) load3_coalesced(a.pts + g_warp0 * 3, left, lane, px, py, pz);
+    return;
+  }
+  if (g >= a.n) return;
+  // generate_volume_points (avatarcap_dataset.py:312-326): flat = (i*Ry + j)*Rz + k, point = linspace * (bmax - bmin) + bmin
+  const unsigned int rz = (unsigned int)a.gr[2], ry = (unsigned int)a.gr[1];
+  const unsigned int u = (unsigned int)g;                       // the launcher refuses grid slabs of 2^31 points or more
+  const unsigned int t = u / rz; const int k = (int)(u - t * rz);
+  const unsigned int ii = t / ry; const int j = (int)(t - ii * ry);
+  const int i = (int)ii + a.gx_first;
+  px = __fadd_rn(__fmul_rn(lin_coord(i, a.gr[0]), a.gl[0]), a.gb[0]);
+  py = __fadd_rn(__fmul_rn(lin_coord(j, a.gr[1]), a.gl[1]), a.gb[1]);
+  pz = __fadd_rn(__fmul_rn(lin_coord(k, a.gr[2]), a.gl[2]), a.gb[2]);
 }
 
 __device__ __forceinline__ void input_slice(const TcArgs& a, unsigned char* buf, int row, int grp, int sl, const Taps& t, float px, float py, float pz) {
@@ -802,8 +856,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       const int n_slices = a.kind == AVC_KIND_RECON ? 3 : 5;
       float px, py, pz;
       if (tl == 0 || !gathers) {                                      // template-only programs have no prefetch: load every tile's points here
-        px = py = pz = 0.f;
-        if (valid) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; }
+        fetch_point(a, g, g - lane, lane, px, py, pz);
         if (gathers) {
           const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
           for (int sl = 0; sl < n_slices; ++sl) input_slice(a, skip, row, grp, sl, t, px, py, pz);
@@ -822,8 +875,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       auto prefetch_step = [&]() {
         if (pf == 0) {
           const int64_t g2 = ((pair + pair_step) * 2 + rank) * TILE + row;
-          nx_x = nx_y = nx_z = 0.f;
-          if (g2 < a.n) { nx_x = a.pts[g2 * 3]; nx_y = a.pts[g2 * 3 + 1]; nx_z = a.pts[g2 * 3 + 2]; }
+          fetch_point(a, g2, g2 - lane, lane, nx_x, nx_y, nx_z);
           nt = make_taps(nx_x - a.cx, -(nx_y - a.cy), a.mH, a.mW);
         } else {
           input_slice(a, skip_nx, row, grp, pf - 1, nt, nx_x, nx_y, nx_z);
@@ -926,7 +978,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
           }
           if (o.epi == EPI_WARP_OUT) {
             qx = px + r[0]; qy = py + r[1]; qz = pz + r[2];                       // cano_pts_chunk + offset_chunk  arch_avatar.py:372
-            if (grp == 0 && valid && a.out_off) { a.out_off[g * 3] = r[0]; a.out_off[g * 3 + 1] = r[1]; a.out_off[g * 3 + 2] = r[2]; }
+            if (grp == 0 && a.out_off && a.n > g - lane) store3_coalesced(a.out_off + (g - lane) * 3, a.n - (g - lane), lane, r[0], r[1], r[2]);
             need_pe = (a.mode != AVC_MODE_WARP_ONLY);
           } else if (o.epi == EPI_GEO_OUT) {
             if (grp == 0 && valid) {
@@ -934,10 +986,9 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
               if (a.out_alpha) a.out_alpha[g] = fmaxf(r[1], 0.f);                                        // :76
             }
           } else if (o.epi == EPI_CLR_OUT) {
-            if (grp == 0 && valid && a.out_rgb) {
-#pragma unroll
-              for (int i = 0; i < 3; ++i) a.out_rgb[g * 3 + i] = 1.f / (1.f + __expf(-r[i]));              // :75
-            }
+            if (grp == 0 && a.out_rgb && a.n > g - lane)                                                   // :75
+              store3_coalesced(a.out_rgb + (g - lane) * 3, a.n - (g - lane), lane, 1.f / (1.f + __expf(-r[0])), 1.f / (1.f + __expf(-r[1])),
+                               1.f / (1.f + __expf(-r[2])));
           } else if (o.epi == EPI_RECON_OUT) {
             if (grp == 0 && valid) a.out0[g] = 1.f / (1.f + __expf(-r[0]));                               // mlp.py:49-50
           }
@@ -962,14 +1013,18 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
 
 constexpr size_t TC_SMEM = (size_t)N_STAGES * STAGE_BYTES + 2 * SKIP_BYTES + SB_FLOATS_MAX * sizeof(float) + DOTW_F4_MAX * sizeof(float4) + sizeof(TcShared) + 64;
 
-int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, const float* pts, int64_t n, const float center[3], float* out0,
-              float* out_off, float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st) {
+int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, const float* pts, const AvcGridDesc* grid, int64_t n,
+              const float center[3], float* out0, float* out_off, float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st) {
   if (n == 0) return AVC_OK;
   int sb = 0;
   for (uint32_t l = 0; l < w.hdr.n_layers; ++l) sb += 2 * w.hdr.layers[l].np;
   if (sb > SB_FLOATS_MAX) return avc_fail(ctx, AVC_EFORMAT, "tensor-core path: scale/bias table too large (%d floats)", sb);
   TcArgs a;
   a.pts = pts; a.n = n; a.cx = center[0]; a.cy = center[1]; a.cz = center[2];
+  for (int c = 0; c < 3; ++c) { a.gb[c] = grid ? grid->bmin[c] : 0.f; a.gl[c] = grid ? grid->len[c] : 0.f; a.gr[c] = grid ? grid->res[c] : 1; }
+  a.gx_first = grid ? grid->x_first : 0;
+  if (grid) a.pts = nullptr;
+  if (grid && n >= ((int64_t)1 << 31)) return avc_fail(ctx, AVC_EINVAL, "dense-grid entry: at most 2^31 - 1 points per call (split the slab)");
   a.map = map ? map->d_hwc : nullptr; a.mC = map ? map->C : 0; a.mH = map ? map->H : 1; a.mW = map ? map->W : 1;
   a.out0 = out0; a.out_off = out_off; a.out_rgb = out_rgb; a.out_alpha = out_alpha; a.if_type = if_type; a.mode = mode; a.kind = kind;
   a.w16 = w.d_f16; a.f32 = w.d_f32; a.hdr = reinterpret_cast<const AvcBlobHeader*>(w.d_blob);
@@ -978,9 +1033,9 @@ int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, c
   AVC_CUDA(ctx, cudaFuncSetAttribute(field_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int64_t pairs = ((n + TILE - 1) / TILE + 1) / 2;
   const int max_clusters = ctx->sm_count / 2;
-  const int grid = 2 * (int)(pairs < (int64_t)max_clusters ? pairs : max_clusters);
+  const int n_ctas = 2 * (int)(pairs < (int64_t)max_clusters ? pairs : max_clusters);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = st;
+  cfg.gridDim = dim3(n_ctas); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
@@ -993,14 +1048,14 @@ int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, c
 
 int avc_tc_available(const avc_ctx* ctx) { return ctx && ctx->cc_major == 10 ? 1 : 0; }
 
-int avc_tc2_eval_avatar(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_occ, float* out_off, float* out_rgb,
-                       float* out_alpha, int if_type, int mode, cudaStream_t st) {
+int avc_tc2_eval_avatar(avc_ctx* ctx, const float* pts, const AvcGridDesc* grid, int64_t n, const float center[3], float* out_occ, float* out_off,
+                        float* out_rgb, float* out_alpha, int if_type, int mode, cudaStream_t st) {
   // the colour head runs when rgb is requested; alpha comes from the geo head
-  return launch_tc2(ctx, ctx->avatar, AVC_KIND_AVATAR, mode == AVC_MODE_TEMPLATE_ONLY ? nullptr : &ctx->maps[AVC_MAP_POSE], pts, n, center, out_occ,
-                   out_off, out_rgb, out_alpha, if_type, mode, st);
+  return launch_tc2(ctx, ctx->avatar, AVC_KIND_AVATAR, mode == AVC_MODE_TEMPLATE_ONLY ? nullptr : &ctx->maps[AVC_MAP_POSE], pts, grid, n, center,
+                    out_occ, out_off, out_rgb, out_alpha, if_type, mode, st);
 }
 
-int avc_tc2_eval_recon(avc_ctx* ctx, const float* pts, int64_t n, const float center[3], float* out_ov, cudaStream_t st) {
-  return launch_tc2(ctx, ctx->recon, AVC_KIND_RECON, &ctx->maps[AVC_MAP_IMAGE], pts, n, center, out_ov, nullptr, nullptr, nullptr, AVC_IF_SDF,
-                   AVC_MODE_QUERY, st);
+int avc_tc2_eval_recon(avc_ctx* ctx, const float* pts, const AvcGridDesc* grid, int64_t n, const float center[3], float* out_ov, cudaStream_t st) {
+  return launch_tc2(ctx, ctx->recon, AVC_KIND_RECON, &ctx->maps[AVC_MAP_IMAGE], pts, grid, n, center, out_ov, nullptr, nullptr, nullptr, AVC_IF_SDF,
+                    AVC_MODE_QUERY, st);
 }

@@ -159,6 +159,47 @@ class Engine:
             out['rgb'] = rgb; out['alpha'] = alpha
         return out
 
+    def eval_occupancy_grid(self, bounds, res, center, x_first: int = 0, x_count: Optional[int] = None, want_offsets: bool = True,
+                            want_texture: bool = False, if_type: str = 'sdf', impl: Optional[str] = None,
+                            out_occ: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """OccupancyNet.query over the dense grid of generate_volume_points (avatarcap_dataset.py:312-326), i-planes
+        [x_first, x_first + x_count): coordinates come from the point index inside the kernel -- no (N,3) point list exists.
+        Bit-identical to eval_occupancy(make_grid(bounds, res, x_first, x_count), ...)."""
+        if if_type not in ('sdf', 'occupancy'):
+            raise ValueError('Invalid config.if_type!')
+        res = tuple(int(r) for r in res)
+        x_count = res[0] - x_first if x_count is None else int(x_count)
+        n = x_count * res[1] * res[2]
+        if out_occ is not None:
+            if out_occ.device != self.device or out_occ.dtype != torch.float32 or out_occ.numel() != n or not out_occ.is_contiguous():
+                raise ValueError('out_occ must be a contiguous float32 device tensor with one element per grid point')
+            occ = out_occ.view(-1)
+        else:
+            occ = torch.empty(n, device=self.device, dtype=torch.float32)
+        off = torch.empty((n, 3), device=self.device, dtype=torch.float32) if want_offsets else None
+        rgb = torch.empty((n, 3), device=self.device, dtype=torch.float32) if want_texture else None
+        alpha = torch.empty(n, device=self.device, dtype=torch.float32) if want_texture else None
+        c = _lib.f3(center.detach().cpu().tolist() if isinstance(center, torch.Tensor) else center)
+        b = np.asarray(bounds.detach().cpu().numpy() if isinstance(bounds, torch.Tensor) else bounds, dtype=np.float32).reshape(6)
+        self._check(self.lib.avc_eval_occupancy_grid(self._h, _lib.f6(b), _lib.i3(res), int(x_first), x_count, c, _ptr(occ), _ptr(off), _ptr(rgb),
+                                                     _ptr(alpha), IF_SDF if if_type == 'sdf' else IF_OCCUPANCY, self._impl(impl), self._stream()))
+        out = {'occ': occ}
+        if off is not None:
+            out['off'] = off
+        if want_texture:
+            out['rgb'] = rgb; out['alpha'] = alpha
+        return out
+
+    def eval_recon_grid(self, bounds, res, center, x_first: int = 0, x_count: Optional[int] = None, impl: Optional[str] = None) -> torch.Tensor:
+        """ReconNetwork.infer's decoder over the dense grid (main.py:438-440), coordinates from the index."""
+        res = tuple(int(r) for r in res)
+        x_count = res[0] - x_first if x_count is None else int(x_count)
+        ov = torch.empty(x_count * res[1] * res[2], device=self.device, dtype=torch.float32)
+        c = _lib.f3(center.detach().cpu().tolist() if isinstance(center, torch.Tensor) else center)
+        b = np.asarray(bounds.detach().cpu().numpy() if isinstance(bounds, torch.Tensor) else bounds, dtype=np.float32).reshape(6)
+        self._check(self.lib.avc_eval_recon_grid(self._h, _lib.f6(b), _lib.i3(res), int(x_first), x_count, c, _ptr(ov), self._impl(impl), self._stream()))
+        return ov
+
     def eval_warp(self, pts, center, impl: Optional[str] = None) -> torch.Tensor:
         p = self._f32(pts, 3); n = p.shape[0]
         off = torch.empty((n, 3), device=self.device, dtype=torch.float32)
@@ -234,9 +275,10 @@ class Engine:
         vol = self._f32(vol)
         if vol.dim() != 3:
             raise ValueError('volume must be (Rx,Ry,Rz)')
-        verts = torch.empty((cap_v, 3), device=self.device, dtype=torch.float32)
-        faces = torch.empty((cap_f, 3), device=self.device, dtype=torch.int32)
-        normals = torch.empty((cap_v, 3), device=self.device, dtype=torch.float32) if with_normals else None
+        # (a zero-row torch tensor has a NULL data pointer: keep one spare row so that capacity 0 is a legal, always-overflowing request)
+        verts = torch.empty((cap_v + 1, 3), device=self.device, dtype=torch.float32)[:cap_v]
+        faces = torch.empty((cap_f + 1, 3), device=self.device, dtype=torch.int32)[:cap_f]
+        normals = torch.empty((cap_v + 1, 3), device=self.device, dtype=torch.float32)[:cap_v] if with_normals else None
         counts = torch.empty(4, device=self.device, dtype=torch.int64)
         b = np.asarray(bounds, dtype=np.float32).reshape(6)
         gx = vol.shape[0] if gres_x is None else gres_x

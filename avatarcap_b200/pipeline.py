@@ -42,9 +42,10 @@ def avatar_frame(engine: Engine, frame: Dict, pose_feat_map, vol_res, flag: Opti
     Masked mode (the reference's): pts = grid[flag], fill = +-1 for the other voxels (main.py:362-363)."""
     bounds = np.asarray(frame['cano_bounds'], dtype=np.float32)
     engine.set_pose_feature_map(pose_feat_map)
-    if flag is None:
-        pts = engine.make_grid(bounds, vol_res)
-    out = engine.eval_occupancy(pts, frame['cano_smpl_center'], want_offsets=True, impl=impl)
+    if flag is None:          # dense: coordinates from the grid index inside the kernel, no point list
+        out = engine.eval_occupancy_grid(bounds, vol_res, frame['cano_smpl_center'], want_offsets=True, impl=impl)
+    else:
+        out = engine.eval_occupancy(pts, frame['cano_smpl_center'], want_offsets=True, impl=impl)
     vol = out['occ'] if flag is None else engine.scatter_fill(flag, out['occ'], fill)
     vol = vol.reshape(tuple(vol_res))
     v, f, n = engine.extract_mesh(vol, bounds, iso)
@@ -59,8 +60,9 @@ def recon_frame(engine: Engine, frame: Dict, img_feat_map, vol_res, flag: Option
     bounds = np.asarray(frame['cano_bounds'], dtype=np.float32)
     engine.set_image_feature_map(img_feat_map)
     if flag is None:
-        pts = engine.make_grid(bounds, vol_res)
-    ov = engine.eval_recon(pts, frame['cano_smpl_center'], impl=impl)
+        ov = engine.eval_recon_grid(bounds, vol_res, frame['cano_smpl_center'], impl=impl)
+    else:
+        ov = engine.eval_recon(pts, frame['cano_smpl_center'], impl=impl)
     vol = ov if flag is None else engine.scatter_fill(flag, ov, fill)
     vol = vol.reshape(tuple(vol_res))
     v, f, n = engine.extract_mesh(vol, bounds, iso)

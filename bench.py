@@ -255,7 +255,9 @@ def run_ours(args):
     sv = shard.SlabVolume(res, world, rank, engine=eng, mode=args.halo)
 
     def step():
-        n_out['o'] = eng.eval_occupancy(pts, center, want_offsets=True, want_texture=True, impl=impl, out_occ=sv.own.view(-1))
+        # dense-grid entry (SURVEY.md 8b/8d "dense-grid mode"): the kernel derives the coordinates from the point index, nothing is read per point
+        n_out['o'] = eng.eval_occupancy_grid(frame['cano_bounds'], res, center, x0, x1 - x0, want_offsets=True, want_texture=True, impl=impl,
+                                             out_occ=sv.own.view(-1))
 
     def barrier():
         if world > 1:
@@ -286,6 +288,20 @@ def run_ours(args):
     if world > 1:
         nt = torch.tensor([n], device=dev, dtype=torch.int64); dist.all_reduce(nt); n_all = int(nt[0])
     value = n_all * args.steps / (total_ms * 1e-3) / 1e6
+    # the same workload through the point-list entry (what round 1 timed: 12 B/point read from HBM); results must be the same bits
+    pl = eng.eval_occupancy(pts, center, want_offsets=True, want_texture=True, impl=impl)
+    same_bits = bool(all(torch.equal(pl[k], n_out['o'][k]) for k in ('occ', 'off', 'rgb', 'alpha')))
+    del pl
+    pa = torch.cuda.Event(enable_timing=True); pb = torch.cuda.Event(enable_timing=True)
+    kpl = max(1, min(args.steps, 3))
+    barrier(); pa.record()
+    for _ in range(kpl):
+        eng.eval_occupancy(pts, center, want_offsets=True, want_texture=True, impl=impl)
+    pb.record(); barrier()
+    tpl = torch.tensor([pa.elapsed_time(pb)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tpl, op=dist.ReduceOp.MAX)
+    point_list = {'value': n_all * kpl / (float(tpl[0]) * 1e-3) / 1e6, 'unit': 'Mpoints/s', 'steps': kpl, 'bit_identical_to_grid_entry': same_bits}
 
     def median_ms(fn, reps):
         """Per-repetition CUDA-event times, median (one allocator / driver hiccup must not masquerade as kernel time); returns (ms, last result)."""
@@ -360,14 +376,14 @@ def run_ours(args):
     if not args.no_strong:
         sres = STRONG_GRID if args.res is None else (args.res,) * 3
         ssv = sv if (world == 1 and tuple(res) == tuple(sres)) else shard.SlabVolume(sres, world, rank, engine=eng, mode=args.halo)
-        spts = pts if ssv is sv else eng.make_grid(frame['cano_bounds'], sres, ssv.x0, ssv.nx)
         shint = {}
         parts_ms = {'field': [], 'mesh': [], 'gather': []}
 
         def strong_step(record):
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record()
-            eng.eval_occupancy(spts, center, want_offsets=True, want_texture=True, impl=impl, out_occ=ssv.own.view(-1))
+            eng.eval_occupancy_grid(frame['cano_bounds'], sres, center, ssv.x0, ssv.nx, want_offsets=True, want_texture=True, impl=impl,
+                                    out_occ=ssv.own.view(-1))
             e1.record()
             ssv.exchange()
             nvox = ssv.padded.numel()
@@ -384,7 +400,7 @@ def run_ours(args):
             shint['cap'] = (int(allc[rank, 0]) * 9 // 8 + 1024, int(allc[rank, 1]) * 9 // 8 + 1024)
             out = shard.gather_mesh(v_, f_, n_, int(allc[rank, 0]), int(allc[rank, 1]), rank, world, eng, counts=allc)
             e3.record()
-            if record:
+            if record is not None:
                 record.append((e0, e1, e2, e3))
             return out
 
@@ -556,7 +572,7 @@ def run_ours(args):
     if rank == 0:
         peaks, peak_src = measured_peaks()
         flop = FLOP_PER_PT['occ+tex']
-        traffic, traffic_src = ncu_traffic('field_tc2_kernel', 'avc_eval_occupancy') if (args.gpus == 1 and args.res is None and impl == 'tc2') else (None, None)
+        traffic, traffic_src = ncu_traffic('field_tc2_kernel', 'avc_eval_occupancy_grid') if (args.gpus == 1 and args.res is None and impl == 'tc2') else (None, None)
         ach = n * flop / (kernel_ms * 1e-3) / 1e12
         peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
         line = {
@@ -568,7 +584,8 @@ def run_ours(args):
             'config': {'workload': 'OccupancyNet.query + texture head (warp MLP, template MLP, geo + colour heads) over a dense '
                                    '%dx%dx%d canonical grid, x-slabs over %d GPU(s); BASELINE config[1] per GPU' % (res + (world,)),
                        'grid': list(res), 'points_per_gpu': n, 'kernel': impl, 'flop_per_point': flop,
-                       'l2_policy': 'inputs (201 MB of points) + outputs (537 MB) exceed the 126 MB L2 every step'},
+                       'entry': 'avc_eval_occupancy_grid (coordinates from the point index)',
+                       'l2_policy': 'the outputs (537 MB per step) exceed the 126 MB L2 every step; the point-list entry (point_list) also reads 201 MB of points'},
             'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                          'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src + ', sustained bf16 (kernel timed inside a long step)',
                          'note': 'algorithmic FLOPs (1x); the tcgen05 kernel issues 3x that as fp16 hi/lo passes'},
@@ -578,6 +595,7 @@ def run_ours(args):
         }
         if e2e:
             line['e2e'] = e2e
+        line['point_list'] = point_list
         if strong:
             line['strong'] = strong
         if gpu_torch:

@@ -111,6 +111,17 @@ int avc_eval_occupancy(avc_ctx* ctx, const float* pts /*[dev] (n,3)*/, int64_t n
                        float* out_occ /*[dev]*/, float* out_off /*[dev]|NULL*/, float* out_rgb /*[dev]|NULL*/,
                        float* out_alpha /*[dev]|NULL*/, int if_type, int impl, void* stream);
 
+/* Dense-grid form of avc_eval_occupancy: the points are those of generate_volume_points (dataset/avatarcap_dataset.py:312-326) for
+ * the i-planes [x_first, x_first + x_count) of a (Rx,Ry,Rz) grid over `bounds` -- what main.py:357-360 evaluates when every grid
+ * point is valid. The kernel derives the coordinates from the point index (bit-identical to avc_make_grid + avc_eval_occupancy),
+ * so nothing is read per point and the 12 B/point list never exists. Outputs are in grid order, (x_count*Ry*Rz) rows.          */
+int avc_eval_occupancy_grid(avc_ctx* ctx, const float bounds[6] /*[host]*/, const int res[3], int x_first, int x_count,
+                            const float center[3] /*[host]*/, float* out_occ /*[dev]*/, float* out_off /*[dev]|NULL*/,
+                            float* out_rgb /*[dev]|NULL*/, float* out_alpha /*[dev]|NULL*/, int if_type, int impl, void* stream);
+/* the same for ReconNetwork.infer's decoder (main.py:438-440) */
+int avc_eval_recon_grid(avc_ctx* ctx, const float bounds[6] /*[host]*/, const int res[3], int x_first, int x_count,
+                        const float center[3] /*[host]*/, float* out_ov /*[dev]*/, int impl, void* stream);
+
 /* WarpingField.query alone (arch_avatar.py:113-140): offsets (n,3) */
 int avc_eval_warp(avc_ctx* ctx, const float* pts /*[dev]*/, int64_t n, const float center[3] /*[host]*/,
                   float* out_off /*[dev] (n,3)*/, int impl, void* stream);
