@@ -178,11 +178,29 @@ __device__ __forceinline__ bool knn_level(const GridLevel& V, float qx, float qy
   const GridDesc G = *V.G;
   top_init(best);
   int cx, cy, cz; grid_cell(G, qx, qy, qz, cx, cy, cz);
-  // shells 0 and 1 together (shell 0 alone can never satisfy the stop test): the centre column first, it tightens the bound for the other 8
-  knn_visit_run<K>(V, G, cx, cy, max(cz - 1, 0), min(cz + 1, G.dz - 1), qx, qy, qz, best);
-  for (int i = max(cx - 1, 0); i <= min(cx + 1, G.dx - 1); ++i)
-    for (int j = max(cy - 1, 0); j <= min(cy + 1, G.dy - 1); ++j)
-      if (i != cx || j != cy) knn_visit_run<K>(V, G, i, j, max(cz - 1, 0), min(cz + 1, G.dz - 1), qx, qy, qz, best);
+  // shells 0 and 1 together (shell 0 alone can never satisfy the stop test). The 9 z-runs' [start, end) pairs are fetched first, as
+  // 18 independent loads (the search is bound by the latency of dependent index loads), then the centre column is scanned before the
+  // other 8 so that it tightens the bound they are pruned against.
+  {
+    const int k0 = max(cz - 1, 0), k1 = min(cz + 1, G.dz - 1);
+    int rs[9], re[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int i = cx + t / 3 - 1, j = cy + t % 3 - 1;
+      const bool ok = i >= 0 && i < G.dx && j >= 0 && j < G.dy;
+      const int c = ok ? (i * G.dy + j) * G.dz : 0;
+      rs[t] = ok ? __ldg(V.start + c + k0) : 0; re[t] = ok ? __ldg(V.start + c + k1 + 1) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 9; ++u) {
+      const int t = u == 0 ? 4 : (u <= 4 ? u - 1 : u);                 // centre (t = 4) first
+      if (u > 0 && best.d[K - 1] < 3.0e38f) {
+        const float gx = axis_gap(qx, G.ox + (float)(cx + t / 3 - 1) * G.h, G.h), gy = axis_gap(qy, G.oy + (float)(cy + t % 3 - 1) * G.h, G.h);
+        if (gx * gx + gy * gy > best.d[K - 1]) continue;
+      }
+      for (int p = rs[t]; p < re[t]; ++p) { const float4 v = __ldg(V.sorted + p); top_insert<K>(best, dist2_rn(qx, qy, qz, v), __float_as_int(v.w)); }
+    }
+  }
   float rh = G.h * 0.999f;                         // 0.1 % slack for the float rounding of the cell assignment
   bool done = best.d[K - 1] <= rh * rh;
   for (int r = 2; r <= G.rmax && !done; ++r) {
@@ -300,6 +318,7 @@ __device__ __forceinline__ void gauss_weights(const Top4& best, float w[4]) {
 struct EpiKnn {            // pytorch3d.ops.knn_points: squared distances ascending + int64 indices
   float* out_d2; int64_t* out_idx; int k;
   static constexpr bool MATS = false;
+  static constexpr int MIN_BLOCKS = 2;       // 128 registers: the K = 4 insertion network spills badly below that
   __device__ __forceinline__ const float* mats() const { return nullptr; }
   __device__ __forceinline__ void operator()(int64_t g, float, float, float, const Top4& best, const float*) const {
     for (int i = 0; i < k; ++i) {
@@ -311,6 +330,7 @@ struct EpiKnn {            // pytorch3d.ops.knn_points: squared distances ascend
 struct EpiLbs {            // SmplUtil.calculate_lbs   smpl_util.py:24-39
   const float* skin_w; float* out_lbs;
   static constexpr bool MATS = false;
+  static constexpr int MIN_BLOCKS = 3;       // 80 registers, no spills: the search is latency bound, occupancy pays
   __device__ __forceinline__ const float* mats() const { return nullptr; }
   __device__ __forceinline__ void operator()(int64_t g, float, float, float, const Top4& best, const float*) const {
     float w[4]; gauss_weights(best, w);
@@ -322,6 +342,7 @@ struct EpiLbs {            // SmplUtil.calculate_lbs   smpl_util.py:24-39
 struct EpiSkinMesh {       // calculate_lbs + skinning (+ skinning_normal)   main.py:385-389, smpl_util.py:58-81
   const float* skin_w; const float* jm; const float* normals; float* out_v; float* out_n;
   static constexpr bool MATS = true;
+  static constexpr int MIN_BLOCKS = 3;
   __device__ __forceinline__ const float* mats() const { return jm; }
   __device__ __forceinline__ void operator()(int64_t g, float x, float y, float z, const Top4& best, const float* s_m) const {
     float w[4]; gauss_weights(best, w);
@@ -346,6 +367,7 @@ struct P2C {
 struct EpiPosedToCano {    // GeoTexAvatar.forward posed branch   arch_avatar.py:189-205, CanoBlendWeightVolume.forward :152-165
   const float* skin_w; const float* l2c; P2C p; const float* wvol; float* out_cano; uint8_t* out_near;
   static constexpr bool MATS = true;
+  static constexpr int MIN_BLOCKS = 2;
   __device__ __forceinline__ const float* mats() const { return l2c; }
   __device__ __forceinline__ void operator()(int64_t g, float x, float y, float z, const Top4& best, const float* s_m) const {
     if (out_near) out_near[g] = best.d[0] < 0.08f * 0.08f ? 1 : 0;         // :191
@@ -386,7 +408,7 @@ struct EpiPosedToCano {    // GeoTexAvatar.forward posed branch   arch_avatar.py
 
 // main launch: one query per thread through the grid; queries the grid cannot finish are appended to the far list
 template <int K, class Epi>
-__global__ void __launch_bounds__(KNN_NT, 2) knn_main_kernel(const float* __restrict__ q, int64_t n, const float* __restrict__ ref, int m, GridView V, Epi epi) {
+__global__ void __launch_bounds__(KNN_NT, Epi::MIN_BLOCKS) knn_main_kernel(const float* __restrict__ q, int64_t n, const float* __restrict__ ref, int m, GridView V, Epi epi) {
   __shared__ float s_m[Epi::MATS ? 24 * 16 : 1];
   if (Epi::MATS) {
     for (int t = threadIdx.x; t < 24 * 16; t += blockDim.x) s_m[t] = epi.mats()[t];

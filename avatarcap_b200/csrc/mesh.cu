@@ -515,7 +515,7 @@ extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], fl
 static int mc_extract_async(avc_ctx* ctx, const float* vol, const int res[3], const float bounds[6], float iso, int x_halo_lo, int x_halo_hi,
                             int x_origin, int gres_x, float* verts, float* normals, int32_t* faces, int64_t cap_v, int64_t cap_f,
                             int64_t* d_counts, cudaStream_t st) {
-  if (!ctx || !vol || !res || !bounds || !verts || !faces) return avc_fail(ctx, AVC_EINVAL, "marching cubes: NULL argument");
+  if (!ctx || !vol || !res || !bounds || (cap_v > 0 && !verts) || (cap_f > 0 && !faces)) return avc_fail(ctx, AVC_EINVAL, "marching cubes: NULL argument");
   if (cap_v < 0 || cap_f < 0) return avc_fail(ctx, AVC_EINVAL, "marching cubes: negative capacity");
   if (gres_x < res[0] - x_halo_lo - x_halo_hi || x_origin < -x_halo_lo) return avc_fail(ctx, AVC_EINVAL, "marching cubes: bad slab placement");
   McDims d; int nblk; McScratch S;
