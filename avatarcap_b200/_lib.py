@@ -40,6 +40,11 @@ SIGNATURES = {
     'avc_select_weights': (_i, [_vp, _i, _i]),
     'avc_set_feature_map': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     'avc_set_feature_map_hwc': (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    'avc_encoder_create': (_i, [_vp, _vp, _i64, _vp, C.c_size_t, _vp, _i64, C.POINTER(_vp)]),
+    'avc_encoder_run': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'avc_encoder_shape': (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    'avc_encoder_read_buffer': (_i, [_vp, _i, _vp, _i64, _vp]),
+    'avc_encoder_destroy': (None, [_vp]),
     'avc_eval_occupancy': (_i, [_vp, _vp, _i64, C.POINTER(_f), _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'avc_eval_occupancy_grid': (_i, [_vp, C.POINTER(_f), C.POINTER(_i), _i, _i, C.POINTER(_f), _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'avc_eval_recon_grid': (_i, [_vp, C.POINTER(_f), C.POINTER(_i), _i, _i, C.POINTER(_f), _vp, _i, _vp]),

@@ -196,6 +196,195 @@ class ImageFeatureEncoder:
         return self._run(x)
 
 
+# ---------------------------------------------------------------------------------------------------------------------------------
+# HGFilter on the tensor cores: the network as a PROGRAM of library ops (csrc/conv_tc.cu). This module only restates the STRUCTURE of
+# HGFilter.forward / ConvBlock.forward / HourGlass._forward (HGFilters.py:61-75, 97-118, 177-219) as a list of ops over numbered
+# buffers and packs the weights (fp16 hi / lo planes, (C_out, taps, C_in) K-major, power-of-two pre-scale); every arithmetic
+# operation runs in the CUDA library: tcgen05 implicit-GEMM convolutions fed by TMA tensor loads, GroupNorm, pooling, bicubic
+# up-sampling and the 7x7 stem as kernels of ours, all captured in one CUDA graph.
+OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD = 1, 2, 3, 4, 5, 6
+
+
+class _Program:
+    def __init__(self):
+        self.f32_sizes, self.planes, self.plane_key, self.ops = [], [], {}, []
+        self.weights = bytearray()
+        self.params = []
+        self.marks = {}                    # name -> (f32 buffer, (H, W, C)): intermediate tensors the tests compare one by one
+
+    def buf(self, n_floats: int) -> int:
+        self.f32_sizes.append(int(n_floats)); return len(self.f32_sizes) - 1
+
+    def plane(self, pixels: int, c: int) -> int:
+        """fp16 hi / lo plane pair (pixels, max(c, 64)); one per distinct shape (its only reader is the convolution right behind)"""
+        key = (int(pixels), max(64, int(c)))
+        if key not in self.plane_key:
+            self.planes.append(key); self.plane_key[key] = len(self.planes) - 1
+        return self.plane_key[key]
+
+    def param(self, arr) -> int:
+        off = sum(len(a) for a in self.params)
+        self.params.append(np.asarray(arr, np.float32).reshape(-1)); return off
+
+    def conv_weight(self, w: np.ndarray):
+        """(C_out, C_in, kh, kw) f32 -> byte offset of [hi plane | lo plane], each (C_out, taps, C_in_pad) fp16, and the scale exponent"""
+        co, ci, kh, kw = w.shape
+        cpad = max(64, ci)
+        m = float(np.abs(w).max())
+        s = int(np.floor(-np.log2(m))) if m > 0 else 0          # max |w| * 2^s in [0.5, 1): the fp16 lo parts stay out of the subnormals
+        s = max(-40, min(40, s))
+        ws = np.zeros((co, kh * kw, cpad), np.float32)
+        ws[:, :, :ci] = np.ldexp(w.astype(np.float32), s).transpose(0, 2, 3, 1).reshape(co, kh * kw, ci)
+        hi = ws.astype(np.float16); lo = (ws - hi.astype(np.float32)).astype(np.float16)
+        while len(self.weights) % 128:
+            self.weights += b'\0'
+        off = len(self.weights)
+        self.weights += hi.tobytes() + lo.tobytes()
+        return off, s, cpad
+
+    def op(self, *words):
+        w = list(int(x) for x in words) + [0] * (16 - len(words)); assert len(w) == 16
+        self.ops.append(w)
+
+    def pack(self, in_chw, out_buf, out_hwc):
+        hdr = [0x45435641, len(self.f32_sizes), len(self.planes), len(self.ops), in_chw[0], in_chw[1], in_chw[2], out_buf, out_hwc[2], out_hwc[0], out_hwc[1]]
+        words = hdr + [0] * (16 - len(hdr)) + self.f32_sizes + [x for pl in self.planes for x in pl] + [x for o in self.ops for x in o]
+        return (np.asarray(words, np.int32), bytes(self.weights), np.concatenate(self.params).astype(np.float32) if self.params else np.zeros(1, np.float32))
+
+
+def build_hgfilter_program(state_dict: Dict, prefix: str = '', in_hw=(512, 512)):
+    """HGFilter(1, 4, 6, 32, 'group', 'no_down', False).forward (HGFilters.py:177-219) -> (program int32, weights fp16 bytes, params f32)."""
+    g = lambda k: np.asarray(state_dict[prefix + k].detach().cpu().numpy() if hasattr(state_dict[prefix + k], 'detach') else state_dict[prefix + k], np.float32)   # noqa: E731
+    Hin, Win = in_hw
+    if Hin % 32 or Win % 32 or Hin != Win:
+        raise ValueError('normal maps must be square with an edge that is a multiple of 32')
+    H, W = Hin // 2, Win // 2
+    pr = _Program()
+
+    def gn(src, P, C, ld, c_off, name, relu, plane=-1, dst32=-1):
+        if name is None:
+            pr.op(OP_GN, src, P, C, ld, c_off, -1, -1, relu, plane, dst32, C)
+        else:
+            pr.op(OP_GN, src, P, C, ld, c_off, pr.param(g(name + '.weight')), pr.param(g(name + '.bias')), relu, plane, dst32, C)
+
+    def conv(plane, wname, out, h, w, n_out, c_off, ldc, accumulate=0, bias=None):
+        wt = g(wname)
+        off, s, cpad = pr.conv_weight(wt)
+        assert wt.shape[0] == n_out
+        pr.op(OP_CONV, plane, off, out, h, w, cpad, n_out, wt.shape[2] * wt.shape[3], c_off, ldc, accumulate, -1 if bias is None else pr.param(g(bias)), s)
+
+    def block(x, h, w, cin, cout, name):
+        """ConvBlock.forward (HGFilters.py:61-75): the three 3x3 convolutions write the channel slices of ONE output tensor (the
+        reference's torch.cat), the residual is added last (identity: add; otherwise the 1x1 convolution accumulates into it)."""
+        P = h * w
+        out = pr.buf(P * cout)
+        c1, c2 = cout // 2, cout // 4
+        gn(x, P, cin, cin, 0, name + '.bn1', 1, plane=pr.plane(P, cin))
+        conv(pr.plane(P, cin), name + '.conv1.weight', out, h, w, c1, 0, cout)
+        gn(out, P, c1, cout, 0, name + '.bn2', 1, plane=pr.plane(P, c1))
+        conv(pr.plane(P, c1), name + '.conv2.weight', out, h, w, c2, c1, cout)
+        gn(out, P, c2, cout, c1, name + '.bn3', 1, plane=pr.plane(P, c2))
+        conv(pr.plane(P, c2), name + '.conv3.weight', out, h, w, c2, c1 + c2, cout)
+        if cin != cout:
+            gn(x, P, cin, cin, 0, name + '.bn4', 1, plane=pr.plane(P, cin))
+            conv(pr.plane(P, cin), name + '.downsample.2.weight', out, h, w, cout, 0, cout, accumulate=1)
+        else:
+            pr.op(OP_ADD, out, x, P * cout)
+        return out
+
+    def hourglass(level, x, h, w):
+        """HourGlass._forward (HGFilters.py:97-118), 256 features."""
+        up1 = block(x, h, w, 256, 256, 'm0.b1_%d' % level)
+        low = pr.buf((h // 2) * (w // 2) * 256)
+        pr.op(OP_POOL, x, low, h, w, 256)
+        low = block(low, h // 2, w // 2, 256, 256, 'm0.b2_%d' % level)
+        low = hourglass(level - 1, low, h // 2, w // 2) if level > 1 else block(low, h // 2, w // 2, 256, 256, 'm0.b2_plus_%d' % level)
+        low = block(low, h // 2, w // 2, 256, 256, 'm0.b3_%d' % level)
+        out = pr.buf(h * w * 256)
+        pr.op(OP_UPADD, up1, low, out, h // 2, w // 2, 256)
+        return out
+
+    P = H * W
+    stem = pr.buf(P * 64)
+    pr.op(OP_STEM, pr.param(g('conv1.weight')), pr.param(g('conv1.bias')), stem, Hin, Win)        # conv1 7x7 s2 (HGFilters.py:180)
+    pr.marks['stem'] = (stem, (H, W, 64))
+    x = pr.buf(P * 64)
+    gn(stem, P, 64, 64, 0, 'bn1', 1, dst32=x)                                                  # relu(bn1(.))
+    pr.marks['bn1'] = (x, (H, W, 64))
+    x = block(x, H, W, 64, 128, 'conv2')                                                       # down_type == 'no_down'
+    pr.marks['conv2'] = (x, (H, W, 128))
+    x = block(x, H, W, 128, 128, 'conv3')
+    pr.marks['conv3'] = (x, (H, W, 128))
+    x = block(x, H, W, 128, 256, 'conv4')
+    pr.marks['conv4'] = (x, (H, W, 256))
+    x = hourglass(4, x, H, W)
+    pr.marks['hourglass'] = (x, (H, W, 256))
+    x = block(x, H, W, 256, 256, 'top_m_0')
+    pr.marks['top_m_0'] = (x, (H, W, 256))
+    ll = pr.buf(P * 256)
+    gn(x, P, 256, 256, 0, None, 0, plane=pr.plane(P, 256))                                     # conv_last0 reads the raw tensor
+    conv(pr.plane(P, 256), 'conv_last0.weight', ll, H, W, 256, 0, 256, bias='conv_last0.bias')
+    gn(ll, P, 256, 256, 0, 'bn_end0', 1, plane=pr.plane(P, 256))
+    pr.marks['conv_last0'] = (ll, (H, W, 256))
+    out = pr.buf(P * 32)
+    conv(pr.plane(P, 256), 'l0.weight', out, H, W, 32, 0, 32, bias='l0.bias')                  # use_sigmoid=False: no tanh
+    build_hgfilter_program.last_marks = pr.marks
+    return pr.pack((6, Hin, Win), out, (H, W, 32))
+
+
+class ImageFeatureEncoderTC:
+    """ImageFeatureEncoder on kernels of this library (tcgen05 convolutions): same call, same result layout.
+    img_feat_map = HGFilter(cat([front_normal, back_normal], 1))[0][-1]: (1,6,512,512) -> (1,32,256,256), channels_last."""
+
+    def __init__(self, state_dict: Dict, prefix: str = '', engine=None, in_hw=(512, 512), use_graph: bool = True):
+        import ctypes as C
+        from .engine import default_engine
+        self.engine = engine if engine is not None else default_engine()
+        self.device = self.engine.device
+        self.use_graph = bool(use_graph)
+        self.in_hw = tuple(in_hw)
+        prog, wbytes, params = build_hgfilter_program(state_dict, prefix, in_hw)
+        self.marks = dict(build_hgfilter_program.last_marks)
+        self._out_hwc = (in_hw[0] // 2, in_hw[1] // 2, 32)
+        h = C.c_void_p()
+        e = self.engine
+        e._check(e.lib.avc_encoder_create(e._h, prog.ctypes.data_as(C.c_void_p), len(prog), wbytes, len(wbytes), params.ctypes.data_as(C.c_void_p),
+                                          len(params), C.byref(h)))
+        self._h = h
+        self._in = torch.empty((6,) + self.in_hw, device=self.device, dtype=torch.float32)
+        self._out = torch.empty(self._out_hwc, device=self.device, dtype=torch.float32)
+
+    def close(self) -> None:
+        if getattr(self, '_h', None) and getattr(self.engine, '_h', None):
+            self.engine.lib.avc_encoder_destroy(self._h)
+        self._h = None
+
+    def intermediate(self, name: str) -> torch.Tensor:
+        """(H, W, C) f32 copy of a marked intermediate tensor of the last run (tests / debugging)."""
+        import ctypes as C
+        buf, shape = self.marks[name]
+        t = torch.empty(shape, device=self.device, dtype=torch.float32)
+        e = self.engine
+        e._check(e.lib.avc_encoder_read_buffer(self._h, int(buf), C.c_void_p(t.data_ptr()), t.numel(), e._stream()))
+        return t
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, normals) -> torch.Tensor:
+        import ctypes as C
+        x = torch.as_tensor(normals)
+        if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != 6 or tuple(x.shape[2:]) != self.in_hw:
+            raise ValueError('normal maps must be (1,6,%d,%d), got %s' % (self.in_hw + (tuple(x.shape),)))
+        self._in.copy_(x[0].to(device=self.device, dtype=torch.float32))
+        e = self.engine
+        e._check(e.lib.avc_encoder_run(self._h, C.c_void_p(self._in.data_ptr()), C.c_void_p(self._out.data_ptr()), int(self.use_graph), e._stream()))
+        return self._out.permute(2, 0, 1)[None]            # (1,32,H,W) view with channels_last strides; overwritten by the next call
+
+
 def subsample_index(c: int, h: int, w: int, count: int, seed: int) -> np.ndarray:
     """Seeded flat (h*w) pixel positions used by the golden fixtures (all channels are kept at each position)."""
     return np.sort(np.random.RandomState(seed).choice(h * w, size=min(count, h * w), replace=False))

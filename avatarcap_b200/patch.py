@@ -256,6 +256,12 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
         def get_feat_maps(self, image):
             if not _inference(self) or not image.is_cuda:
                 return o_gfm(self, image)
+            e = _engine()
+            if e.has_tensor_core_path and image.shape[0] == 1 and image.shape[2] == image.shape[3] and image.shape[2] % 32 == 0:
+                # HGFilter on the library's own tcgen05 convolutions (csrc/conv_tc.cu), one program + CUDA graph per module and input size
+                hw = (int(image.shape[2]), int(image.shape[3]))
+                cls = lambda sd, device: enc_mod.ImageFeatureEncoderTC(sd, engine=e, in_hw=hw)      # noqa: E731
+                return [_encoder('hgtc%dx%d' % hw, self.image_encoder, cls)(image)]
             return [_encoder('hg', self.image_encoder, enc_mod.ImageFeatureEncoder)(image)]      # list like HGFilter's `outputs`
         arch_recon.ReconNetwork.get_feat_maps = get_feat_maps
 

@@ -483,6 +483,12 @@ def run_ours(args):
             enc_ms['encoder_unet%s_ms' % tag], _ = timed(lambda: pe(xin))
             enc_ms['encoder_hgfilter%s_ms' % tag], _ = timed(lambda: ie(nin))
             del pe, ie
+        try:                                                                       # HGFilter on our tcgen05 convolutions (csrc/conv_tc.cu)
+            ietc = encoders.ImageFeatureEncoderTC(synth.hgfilter_state_dict(), engine=eng)
+            enc_ms['encoder_hgfilter_tc_ms'], _ = timed(lambda: ietc(nin))
+            ietc.close()
+        except Exception as ex:
+            enc_ms['encoder_hgfilter_tc_error'] = repr(ex)[:200]
         frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
         frame_ms.update(enc_ms); frame_ms.update(recon_ms)

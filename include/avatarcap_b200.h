@@ -101,6 +101,23 @@ int avc_set_feature_map(avc_ctx* ctx, int which, const float* chw /*[dev]*/, int
 int avc_set_feature_map_hwc(avc_ctx* ctx, int which, const float* hwc /*[dev]*/, int C, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- */
+/* per-frame image encoder on the tensor cores ("next" row 1)                                      */
+/* ReconNetwork.get_feat_maps (arch_recon.py:41-43) = HGFilter.forward (network/HGFilters.py:177-219). The network is handed over
+ * as a PROGRAM of library ops over numbered buffers (avatarcap_b200/encoders.py build_hgfilter_program: 7x7 stem, GroupNorm + ReLU +
+ * fp16 hi/lo split, tcgen05 implicit-GEMM 3x3 / 1x1 convolution fed by TMA tensor loads, residual add, 2x2 average pool, bicubic x2
+ * up-sampling) plus a weight blob (fp16 hi / lo planes, (C_out, taps, C_in) each) and a parameter blob (f32). The library owns copies.
+ * avc_encoder_run: in [dev] (C,H,W) f32 as the reference feeds it, out [dev] (H/2, W/2, 32) f32 = the (H,W,C) order
+ * avc_set_feature_map_hwc takes; use_graph != 0 replays the program from a CUDA graph captured on first use.                      */
+typedef struct avc_encoder avc_encoder;
+int  avc_encoder_create(avc_ctx* ctx, const int32_t* program /*[host]*/, int64_t n_words, const void* weights_f16 /*[host]*/, size_t weight_bytes,
+                        const float* params_f32 /*[host]*/, int64_t n_params, avc_encoder** out);
+int  avc_encoder_run(avc_encoder* enc, const float* in /*[dev]*/, float* out /*[dev]*/, int use_graph, void* stream);
+int  avc_encoder_shape(const avc_encoder* enc, int in_chw[3], int out_hwc[3]);
+/* tests / debugging: copy f32 buffer `buf` of the program (its contents after the last run) to dst */
+int  avc_encoder_read_buffer(avc_encoder* enc, int buf, float* dst /*[dev]*/, int64_t n_floats, void* stream);
+void avc_encoder_destroy(avc_encoder* enc);
+
+/* ---------------------------------------------------------------------------------------------- */
 /* field evaluation                                                                               */
 /* ---------------------------------------------------------------------------------------------- */
 /* OccupancyNet.query (arch_avatar.py:356-381): off = WarpingField.query(p) (:113-140); (rgb,alpha,occ) =

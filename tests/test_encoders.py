@@ -81,3 +81,37 @@ def test_encoders_gpu_graph_vs_golden_and_hwc_handoff():
     b = eng.eval_occupancy(pts, frame['cano_smpl_center'])
     assert torch.equal(a['occ'], b['occ']) and torch.equal(a['off'], b['off'])
     eng.close()
+
+
+@pytest.mark.gpu
+def test_hgfilter_tensor_core_vs_golden():
+    """HGFilter on kernels of the library (csrc/conv_tc.cu: tcgen05 implicit-GEMM convolutions fed by TMA tensor loads, fp16 hi/lo split
+    operands): within 1e-5 of the reference's own HGFilter (golden made on the CPU by tests/golden/gen_encoder_golden.py), as close as
+    the cuDNN f32 restatement, deterministic, graph == eager, and the (H,W,C) result feeds the recon decoder unchanged."""
+    from avatarcap_b200.engine import Engine
+    g = load_golden('encoder_golden.npz')
+    eng = Engine()
+    if not eng.has_tensor_core_path:
+        pytest.skip('needs sm_100')
+    y = torch.from_numpy(synth.normal_maps()).cuda()
+    tc = encoders.ImageFeatureEncoderTC(synth.hgfilter_state_dict(), engine=eng, use_graph=True)
+    out = tc(y).clone()
+    assert tuple(out.shape) == (1, 32, 256, 256) and out.is_contiguous(memory_format=torch.channels_last)
+    err = _report('hgfilter tcgen05', _sampled(out, g['img_idx']), g['img_feat'])
+    assert err < 1e-5
+    ref = encoders.ImageFeatureEncoder(synth.hgfilter_state_dict(), device='cuda', use_graph=False, benchmark=False)(y)
+    print('vs the cuDNN f32 restatement: max-abs %.3g' % float((out - ref).abs().max()))
+    assert float((out - ref).abs().max()) < 2e-5
+    again = tc(y * 0.5 + 0.1).clone(); assert float((again - out).abs().max()) > 1e-4
+    assert torch.equal(tc(y), out)                                            # replays are bit-reproducible (fixed-order GroupNorm sums)
+    eager = encoders.ImageFeatureEncoderTC(synth.hgfilter_state_dict(), engine=eng, use_graph=False)
+    assert torch.equal(eager(y), out)
+    # hand-off to the per-point decoder
+    eng.load_recon(synth.recon_state_dict())
+    frame = synth.make_frame(synth.SynthBody(), None)
+    pts = eng.make_grid(frame['cano_bounds'], (32, 32, 32))
+    eng.set_image_feature_map(out)
+    a = eng.eval_recon(pts, frame['cano_smpl_center'])
+    eng.set_image_feature_map(out.contiguous())
+    assert torch.equal(a, eng.eval_recon(pts, frame['cano_smpl_center']))
+    tc.close(); eager.close(); eng.close()
