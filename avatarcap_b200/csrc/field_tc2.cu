@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -61,6 +62,8 @@ struct TcOp {
                       // epilogue; float4 index of that head's weights in s_dotw, `epi` then names the OUTPUT stage. -1: plain hidden layer
   int dot_k;          // K of that head (channels of this op)
   int dot_layer;      // the head's layer in the blob (f32 section: W[n][K], scale[n], bias[n])
+  int passes;         // 3: hi*hi + hi*lo + lo*hi (the 1e-4 occupancy budget needs it); 1: hi*hi only (the colour head: an 8-bit colour, emulated
+                      // error 3e-6 on rgb, tests/diag_pass_pruning.py -> profiles/r2_pass_pruning.txt)
 };
 
 struct TcArgs {
@@ -443,31 +446,6 @@ __device__ __forceinline__ float lin_coord(int q, int steps) {
   const float step = __fdiv_rn(1.f, (float)(steps - 1));
   return q < steps / 2 ? __fmul_rn(step, (float)q) : __fsub_rn(1.f, __fmul_rn(step, (float)(steps - 1 - q)));
 }
-// The 32 points of a warp are consecutive (g0 + lane): their xyz triples are 96 consecutive floats. Three fully coalesced 128-byte
-// accesses + shuffles instead of three stride-12 accesses that each touch 12 sectors.
-__device__ __forceinline__ void load3_coalesced(const float* __restrict__ base /*of the warp's first point*/, int64_t n_left /*valid points from g0*/,
-                                                int lane, float& x, float& y, float& z) {
-  float t[3];
-#pragma unroll
-  for (int u = 0; u < 3; ++u) { const int f = u * 32 + lane; t[u] = (f < 3 * n_left) ? __ldg(base + f) : 0.f; }
-  float c[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int f = 3 * lane + k, src = f & 31, u = f >> 5;          // float f lives in t[u] of lane src
-    const float a = __shfl_sync(0xffffffffu, t[0], src), b = __shfl_sync(0xffffffffu, t[1], src), d = __shfl_sync(0xffffffffu, t[2], src);
-    c[k] = u == 0 ? a : (u == 1 ? b : d);
-  }
-  x = c[0]; y = c[1]; z = c[2];
-}
-__device__ __forceinline__ void store3_coalesced(float* __restrict__ base, int64_t n_left, int lane, float x, float y, float z) {
-#pragma unroll
-  for (int u = 0; u < 3; ++u) {
-    const int f = u * 32 + lane, p = f / 3, k = f - 3 * p;           // float f = component k of the warp's point p
-    const float a = __shfl_sync(0xffffffffu, x, p), b = __shfl_sync(0xffffffffu, y, p), d = __shfl_sync(0xffffffffu, z, p);
-    if (p < n_left) base[f] = k == 0 ? a : (k == 1 ? b : d);
-  }
-}
-
 struct Taps { int i00, i01, i10, i11; float w00, w01, w10, w11; };
 __device__ __forceinline__ Taps make_taps(float gx, float gy, int H, int W) {   // == field_simt.cu (ATen grid_sample, border, align_corners)
   float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
@@ -499,8 +477,8 @@ __device__ __forceinline__ void gather8(const float* __restrict__ hwc, int C, co
   }
 }
 
-// point g of the launch: read from the caller's list (coalesced over the warp) or generated from the grid index
-__device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, int64_t g_warp0, int lane, float& px, float& py, float& pz);
+// point g of the launch: read from the caller's list or generated from the grid index
+__device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, float& px, float& py, float& pz);
 
 // One step of the input stage (skip operand of the first layer) for point (px,py,pz) with bilinear taps t:
 //   avatar: h0 in tensor-core order [f0..f63, x, y, z, 0...] (packer permutes the 67 columns accordingly)   arch_avatar.py:121-136
@@ -518,6 +496,8 @@ __device__ __forceinline__ void trace_ev(long long* trace, int t, int oi, int e)
 // TMEM regions: X = columns [0,256), Y = [256,512). See the file header for the ping-pong scheme.
 void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool texture) {
   int n = 0, sb = 0;
+  // A/B knob: AVC_CLR_PASSES=3 evaluates the colour head with the full split product like everything else
+  const int clr_passes = [] { const char* e = getenv("AVC_CLR_PASSES"); return (e && atoi(e) == 3) ? 3 : 1; }();
   int sb_off[AVC_MAX_LAYERS];
   unsigned int stream_pos[AVC_MAX_LAYERS];      // running offset inside each layer's weight stream (pieces in op order)
   for (int l = 0; l < (int)hdr->n_layers; ++l) { sb_off[l] = sb; sb += 2 * hdr->layers[l].np; stream_pos[l] = (unsigned int)hdr->layers[l].tc_w_off; }
@@ -527,7 +507,7 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
     const AvcLayerDesc& L = hdr->layers[layer];
     o.layer = layer; o.n = nn; o.n_row_off = row_off; o.np = L.np; o.ks_smem = ks_s; o.ks_smem_w0 = ks_s_w0; o.ks_tmem = ks_t; o.ks_tmem_w0 = ks_t_w0;
     o.a_col = a_col; o.d_col = d_col; o.accumulate = accum; o.wait_epi = wait_epi; o.commit_d = commit; o.epi = epi; o.act = L.act;
-    o.sb_off = sb_off[layer] + 2 * row_off; o.signal_done = signal; o.wait_a = 1; o.dot_w = -1; o.dot_k = 0; o.dot_layer = -1;
+    o.sb_off = sb_off[layer] + 2 * row_off; o.signal_done = signal; o.wait_a = 1; o.dot_w = -1; o.dot_k = 0; o.dot_layer = -1; o.passes = 3;
     o.w_off = stream_pos[layer]; stream_pos[layer] += (unsigned int)(nn * 64 * (ks_s + ks_t));
   };
   int dot_pos = 0;
@@ -562,7 +542,9 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
       if (texture) {
         add(17, 256, 0, 0, 0, 16, 0, X, Y, 0, 1, 1, EPI_HIDDEN, 0);    // clr fc0 (waits until the geo head has been read out of Y)
         S.ops[n - 1].wait_a = 0;                                       // s7 was completed for geo fc0 already
+        S.ops[n - 1].passes = clr_passes;
         add(18, 128, 0, 0, 0, 16, 0, Y, X, 0, 0, 1, EPI_HIDDEN, 0);    // clr fc1 -> X[0,128)
+        S.ops[n - 1].passes = clr_passes;
         head(19, EPI_CLR_OUT, 0);
       }
     }
@@ -577,14 +559,10 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
   S.n_ops = n;
 }
 
-__device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, int64_t g_warp0, int lane, float& px, float& py, float& pz) {
+__device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, float& px, float& py, float& pz) {
   px = py = pz = 0.f;
-  if (a.pts) {
-    const int64_t left = a.n - g_warp0;                          // warp-uniform
-    if (left > 0) load3_coalesced(a.pts + g_warp0 * 3, left, lane, px, py, pz);
-    return;
-  }
   if (g >= a.n) return;
+  if (a.pts) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; return; }
   // generate_volume_points (avatarcap_dataset.py:312-326): flat = (i*Ry + j)*Rz + k, point = linspace * (bmax - bmin) + bmin
   const unsigned int rz = (unsigned int)a.gr[2], ry = (unsigned int)a.gr[1];
   const unsigned int u = (unsigned int)g;                       // the launcher refuses grid slabs of 2^31 points or more
@@ -812,6 +790,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
 #pragma unroll
                   for (int u = 0; u < 4; ++u) {
                     const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
+                    if (o.passes == 1) { mma_ts(d_addr, a_hi, bh[u], idesc, acc); acc = 1u; continue; }      // colour head: hi*hi only
                     // hi*hi and hi*lo back to back with A(hi) held in the collector buffer (one TMEM operand fetch for two MMAs), then lo*hi
                     mma_ts_c(d_addr, a_hi, bh[u], idesc, acc, 1); acc = 1u;
                     mma_ts_c(d_addr, a_hi, bl[u], idesc, 1u, 2);
@@ -856,7 +835,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       const int n_slices = a.kind == AVC_KIND_RECON ? 3 : 5;
       float px, py, pz;
       if (tl == 0 || !gathers) {                                      // template-only programs have no prefetch: load every tile's points here
-        fetch_point(a, g, g - lane, lane, px, py, pz);
+        fetch_point(a, g, px, py, pz);
         if (gathers) {
           const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
           for (int sl = 0; sl < n_slices; ++sl) input_slice(a, skip, row, grp, sl, t, px, py, pz);
@@ -875,7 +854,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       auto prefetch_step = [&]() {
         if (pf == 0) {
           const int64_t g2 = ((pair + pair_step) * 2 + rank) * TILE + row;
-          fetch_point(a, g2, g2 - lane, lane, nx_x, nx_y, nx_z);
+          fetch_point(a, g2, nx_x, nx_y, nx_z);
           nt = make_taps(nx_x - a.cx, -(nx_y - a.cy), a.mH, a.mW);
         } else {
           input_slice(a, skip_nx, row, grp, pf - 1, nt, nx_x, nx_y, nx_z);
@@ -978,7 +957,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
           }
           if (o.epi == EPI_WARP_OUT) {
             qx = px + r[0]; qy = py + r[1]; qz = pz + r[2];                       // cano_pts_chunk + offset_chunk  arch_avatar.py:372
-            if (grp == 0 && a.out_off && a.n > g - lane) store3_coalesced(a.out_off + (g - lane) * 3, a.n - (g - lane), lane, r[0], r[1], r[2]);
+            if (grp == 0 && valid && a.out_off) { a.out_off[g * 3] = r[0]; a.out_off[g * 3 + 1] = r[1]; a.out_off[g * 3 + 2] = r[2]; }
             need_pe = (a.mode != AVC_MODE_WARP_ONLY);
           } else if (o.epi == EPI_GEO_OUT) {
             if (grp == 0 && valid) {
@@ -986,9 +965,10 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
               if (a.out_alpha) a.out_alpha[g] = fmaxf(r[1], 0.f);                                        // :76
             }
           } else if (o.epi == EPI_CLR_OUT) {
-            if (grp == 0 && a.out_rgb && a.n > g - lane)                                                   // :75
-              store3_coalesced(a.out_rgb + (g - lane) * 3, a.n - (g - lane), lane, 1.f / (1.f + __expf(-r[0])), 1.f / (1.f + __expf(-r[1])),
-                               1.f / (1.f + __expf(-r[2])));
+            if (grp == 0 && valid && a.out_rgb) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) a.out_rgb[g * 3 + i] = 1.f / (1.f + __expf(-r[i]));              // :75
+            }
           } else if (o.epi == EPI_RECON_OUT) {
             if (grp == 0 && valid) a.out0[g] = 1.f / (1.f + __expf(-r[0]));                               // mlp.py:49-50
           }

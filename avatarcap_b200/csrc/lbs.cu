@@ -257,20 +257,26 @@ __global__ void __launch_bounds__(KNN_NT) near_flag_kernel(const float* __restri
     const GridDesc G = *V.L[0].G;
     const int R = (int)floorf(rad * G.inv_h) + 1;   // >= ceil, with a full cell of slack when radius is a multiple of h
     int cx, cy, cz; grid_cell(G, qx, qy, qz, cx, cy, cz);
+    // one z-run of cells (i, j, .): skipped when the column is farther than the radius, clipped in z to the cells the ball reaches
+    auto visit = [&](int i, int j) {
+      const float gx = axis_gap(qx, G.ox + (float)i * G.h, G.h), gy = axis_gap(qy, G.oy + (float)j * G.h, G.h);
+      const float dxy2 = gx * gx + gy * gy;
+      if (dxy2 >= r2) return;
+      const float rz = sqrtf(r2 - dxy2) + G.h * (1.f / 256.f);
+      const int k0 = max(max(cz - R, 0), (int)floorf((qz - rz - G.oz) * G.inv_h)), k1 = min(min(cz + R, G.dz - 1), (int)floorf((qz + rz - G.oz) * G.inv_h));
+      if (k0 > k1) return;
+      const int c = (i * G.dy + j) * G.dz;
+      const int e = __ldg(V.L[0].start + c + k1 + 1);
+      for (int p = __ldg(V.L[0].start + c + k0); p < e; ++p) if (dist2_rn(qx, qy, qz, __ldg(V.L[0].sorted + p)) < r2) { hit = true; break; }
+    };
+    // rings of columns around the query's column, nearest first: a near query hits in ring 0 or 1
     for (int ring = 0; ring <= R && !hit; ++ring)
       for (int i = max(cx - ring, 0); i <= min(cx + ring, G.dx - 1) && !hit; ++i) {
-        const bool edge_i = abs(i - cx) == ring;
-        for (int j = max(cy - ring, 0); j <= min(cy + ring, G.dy - 1) && !hit; j += (edge_i ? 1 : max(2 * ring, 1))) {
-          if (!edge_i && abs(j - cy) != ring) continue;            // (only reached when cy - ring was clamped)
-          const float gx = axis_gap(qx, G.ox + (float)i * G.h, G.h), gy = axis_gap(qy, G.oy + (float)j * G.h, G.h);
-          const float dxy2 = gx * gx + gy * gy;
-          if (dxy2 >= r2) continue;
-          const float rz = sqrtf(r2 - dxy2) + G.h * (1.f / 256.f);
-          const int k0 = max(max(cz - R, 0), (int)floorf((qz - rz - G.oz) * G.inv_h)), k1 = min(min(cz + R, G.dz - 1), (int)floorf((qz + rz - G.oz) * G.inv_h));
-          if (k0 > k1) continue;
-          const int c = (i * G.dy + j) * G.dz;
-          const int e = __ldg(V.L[0].start + c + k1 + 1);
-          for (int p = __ldg(V.L[0].start + c + k0); p < e; ++p) if (dist2_rn(qx, qy, qz, __ldg(V.L[0].sorted + p)) < r2) { hit = true; break; }
+        if (abs(i - cx) == ring) {                                 // a full row of the ring
+          for (int j = max(cy - ring, 0); j <= min(cy + ring, G.dy - 1) && !hit; ++j) visit(i, j);
+        } else {                                                   // interior row: its two end columns
+          if (cy - ring >= 0) visit(i, cy - ring);
+          if (!hit && cy + ring <= G.dy - 1) visit(i, cy + ring);
         }
       }
   }
