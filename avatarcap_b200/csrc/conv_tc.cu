@@ -161,8 +161,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       const int buf = it & 1;
       mbar_wait(&S.acc_empty[buf], (uint32_t)((it >> 1) & 1) ^ 1u);       // the epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_addr = tmem + (uint32_t)(buf * 256);
-      uint32_t acc = 0;
+      // Two accumulators per tile when they fit (N <= 128): the hi*hi products in one, the two 2^-11-sized cross terms in the other,
+      // summed in fp32 by the epilogue. The tensor core adds into the fp32 accumulator with truncation, a bias that grows with the
+      // number of accumulation steps (3 x 144 for a 3x3 convolution over 256 channels); keeping the small terms apart takes two
+      // thirds of the steps -- and their rounding -- off the main sum.
+      const bool dual = a.N <= 128;
+      const uint32_t d_addr = tmem + (uint32_t)(buf * 256), d_cross = dual ? d_addr + 128u : d_addr;
+      uint32_t acc = 0, acc_x = dual ? 0u : 1u;
       for (int k = 0; k < k_iters; ++k) {
         mbar_wait(&S.full[s], ph);
         tc_fence_after();
@@ -173,8 +178,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int u = 0; u < 4; ++u) {                                  // 4 x K16 inside the 128-byte atom: +32 B = +2 in the address field
             mma_ss1(d_addr, ah + 2 * u, bh + 2 * u, idesc, acc); acc = 1u;
-            mma_ss1(d_addr, ah + 2 * u, bl + 2 * u, idesc, 1u);
-            mma_ss1(d_addr, al + 2 * u, bh + 2 * u, idesc, 1u);
+            mma_ss1(d_cross, ah + 2 * u, bl + 2 * u, idesc, acc_x); acc_x = 1u;
+            mma_ss1(d_cross, al + 2 * u, bh + 2 * u, idesc, 1u);
           }
           tc_commit1(&S.empty[s]);                                       // the stage is free once these MMAs have read it
           if (k == k_iters - 1) tc_commit1(&S.acc_full[buf]);            // ... and the tile's accumulator is complete
@@ -198,6 +203,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int c0 = 0; c0 < a.N; c0 += 32) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
+        if (a.N <= 128) {                                                // + the cross-term accumulator (see the MMA issuer)
+          float x[32];
+          tmem_ld32(t_row + 128u + (uint32_t)c0, x);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += x[i];
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= a.scale;
         if (a.bias) {

@@ -68,7 +68,7 @@ struct TcOp {
 
 struct TcArgs {
   const float* pts; int64_t n;          // pts == NULL: dense-grid mode, point g = grid point of linear index g (+ the slab offset)
-  float gb[3], gl[3]; int gr[3]; int gx_first;   // grid: bmin, bmax - bmin, resolution, first i-plane   (avatarcap_dataset.py:312-326)
+  float gb[3], gl[3], gstep[3]; int gr[3]; int gx_first;   // grid: bmin, bmax - bmin, 1/(res-1), resolution, first i-plane   (avatarcap_dataset.py:312-326)
   float cx, cy, cz;
   const float* map; int mC, mH, mW;
   float* out0; float* out_off; float* out_rgb; float* out_alpha;   // out0 = occ (avatar) or ov (recon)
@@ -440,12 +440,12 @@ __device__ __forceinline__ void hidden_pair(uint32_t t0, uint32_t t1, const floa
   if (lane == 0) mbar_arrive_leader_relaxed(bar1, rank);
 }
 
-// torch.linspace(0, 1, steps)[q] in float32 exactly as ATen computes it (and make_grid_kernel restates it)
-__device__ __forceinline__ float lin_coord(int q, int steps) {
-  if (steps <= 1) return 0.f;
-  const float step = __fdiv_rn(1.f, (float)(steps - 1));
+// torch.linspace(0, 1, steps)[q] in float32 exactly as ATen computes it (and make_grid_kernel restates it); step = fl(1 / (steps - 1)) comes from
+// the host (an IEEE division there, no division subroutine in this kernel: its instruction footprint is on the critical path)
+__device__ __forceinline__ float lin_coord(int q, int steps, float step) {
   return q < steps / 2 ? __fmul_rn(step, (float)q) : __fsub_rn(1.f, __fmul_rn(step, (float)(steps - 1 - q)));
 }
+
 struct Taps { int i00, i01, i10, i11; float w00, w01, w10, w11; };
 __device__ __forceinline__ Taps make_taps(float gx, float gy, int H, int W) {   // == field_simt.cu (ATen grid_sample, border, align_corners)
   float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
@@ -477,7 +477,10 @@ __device__ __forceinline__ void gather8(const float* __restrict__ hwc, int C, co
   }
 }
 
-// point g of the launch: read from the caller's list or generated from the grid index
+// point g of the launch: read from the caller's list (GRID = false) or generated from the grid index (GRID = true). Two kernel
+// instantiations: the A/B against the round-1 library showed that a few hundred extra instructions in this kernel (a float-division
+// subroutine, shuffle-coalesced I/O) cost 7-9 % -- the issuer warps' loop lives off the instruction cache.
+template <bool GRID>
 __device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, float& px, float& py, float& pz);
 
 // One step of the input stage (skip operand of the first layer) for point (px,py,pz) with bilinear taps t:
@@ -559,19 +562,20 @@ void build_ops(TcArgs& S, const AvcBlobHeader* hdr, int kind, int mode, bool tex
   S.n_ops = n;
 }
 
+template <bool GRID>
 __device__ __forceinline__ void fetch_point(const TcArgs& a, int64_t g, float& px, float& py, float& pz) {
   px = py = pz = 0.f;
   if (g >= a.n) return;
-  if (a.pts) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; return; }
+  if (!GRID) { px = a.pts[g * 3]; py = a.pts[g * 3 + 1]; pz = a.pts[g * 3 + 2]; return; }
   // generate_volume_points (avatarcap_dataset.py:312-326): flat = (i*Ry + j)*Rz + k, point = linspace * (bmax - bmin) + bmin
   const unsigned int rz = (unsigned int)a.gr[2], ry = (unsigned int)a.gr[1];
   const unsigned int u = (unsigned int)g;                       // the launcher refuses grid slabs of 2^31 points or more
   const unsigned int t = u / rz; const int k = (int)(u - t * rz);
   const unsigned int ii = t / ry; const int j = (int)(t - ii * ry);
   const int i = (int)ii + a.gx_first;
-  px = __fadd_rn(__fmul_rn(lin_coord(i, a.gr[0]), a.gl[0]), a.gb[0]);
-  py = __fadd_rn(__fmul_rn(lin_coord(j, a.gr[1]), a.gl[1]), a.gb[1]);
-  pz = __fadd_rn(__fmul_rn(lin_coord(k, a.gr[2]), a.gl[2]), a.gb[2]);
+  px = __fadd_rn(__fmul_rn(lin_coord(i, a.gr[0], a.gstep[0]), a.gl[0]), a.gb[0]);
+  py = __fadd_rn(__fmul_rn(lin_coord(j, a.gr[1], a.gstep[1]), a.gl[1]), a.gb[1]);
+  pz = __fadd_rn(__fmul_rn(lin_coord(k, a.gr[2], a.gstep[2]), a.gl[2]), a.gb[2]);
 }
 
 __device__ __forceinline__ void input_slice(const TcArgs& a, unsigned char* buf, int row, int grp, int sl, const Taps& t, float px, float py, float pz) {
@@ -596,6 +600,7 @@ __device__ __forceinline__ void input_slice(const TcArgs& a, unsigned char* buf,
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+template <bool GRID>
 __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) unsigned char dsm[];
   unsigned char* ring = dsm;                                       // N_STAGES * STAGE_BYTES
@@ -787,14 +792,18 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
                 tc_fence_after();
                 if (me == 0) asm volatile("bar.sync 1, 64;" ::: "memory"); else asm volatile("bar.sync 2, 64;" ::: "memory");
                 if (elect_one()) {
+                  if (o.passes == 1) {                                         // colour head: hi*hi only (one branch per stage, outside the MMA chain)
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
-                    if (o.passes == 1) { mma_ts(d_addr, a_hi, bh[u], idesc, acc); acc = 1u; continue; }      // colour head: hi*hi only
-                    // hi*hi and hi*lo back to back with A(hi) held in the collector buffer (one TMEM operand fetch for two MMAs), then lo*hi
-                    mma_ts_c(d_addr, a_hi, bh[u], idesc, acc, 1); acc = 1u;
-                    mma_ts_c(d_addr, a_hi, bl[u], idesc, 1u, 2);
-                    mma_ts(d_addr, a_lo, bh[u], idesc | (1u << 13), 1u);      // negate A: TMEM holds -lo (split2_neg)
+                    for (int u = 0; u < 4; ++u) { mma_ts(d_addr, a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), bh[u], idesc, acc); acc = 1u; }
+                  } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const uint32_t a_hi = a0 + (uint32_t)((u >> 1) * 32 + (u & 1) * 8), a_lo = a_hi + 16u;
+                      // hi*hi and hi*lo back to back with A(hi) held in the collector buffer (one TMEM operand fetch for two MMAs), then lo*hi
+                      mma_ts_c(d_addr, a_hi, bh[u], idesc, acc, 1); acc = 1u;
+                      mma_ts_c(d_addr, a_hi, bl[u], idesc, 1u, 2);
+                      mma_ts(d_addr, a_lo, bh[u], idesc | (1u << 13), 1u);      // negate A: TMEM holds -lo (split2_neg)
+                    }
                   }
                   tc_commit(&S.empty[stage]);
                 }
@@ -835,7 +844,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       const int n_slices = a.kind == AVC_KIND_RECON ? 3 : 5;
       float px, py, pz;
       if (tl == 0 || !gathers) {                                      // template-only programs have no prefetch: load every tile's points here
-        fetch_point(a, g, px, py, pz);
+        fetch_point<GRID>(a, g, px, py, pz);
         if (gathers) {
           const Taps t = make_taps(px - a.cx, -(py - a.cy), a.mH, a.mW);
           for (int sl = 0; sl < n_slices; ++sl) input_slice(a, skip, row, grp, sl, t, px, py, pz);
@@ -854,7 +863,7 @@ __global__ void __launch_bounds__(NT, 1) field_tc2_kernel(const __grid_constant_
       auto prefetch_step = [&]() {
         if (pf == 0) {
           const int64_t g2 = ((pair + pair_step) * 2 + rank) * TILE + row;
-          fetch_point(a, g2, nx_x, nx_y, nx_z);
+          fetch_point<GRID>(a, g2, nx_x, nx_y, nx_z);
           nt = make_taps(nx_x - a.cx, -(nx_y - a.cy), a.mH, a.mW);
         } else {
           input_slice(a, skip_nx, row, grp, pf - 1, nt, nx_x, nx_y, nx_z);
@@ -1001,7 +1010,10 @@ int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, c
   if (sb > SB_FLOATS_MAX) return avc_fail(ctx, AVC_EFORMAT, "tensor-core path: scale/bias table too large (%d floats)", sb);
   TcArgs a;
   a.pts = pts; a.n = n; a.cx = center[0]; a.cy = center[1]; a.cz = center[2];
-  for (int c = 0; c < 3; ++c) { a.gb[c] = grid ? grid->bmin[c] : 0.f; a.gl[c] = grid ? grid->len[c] : 0.f; a.gr[c] = grid ? grid->res[c] : 1; }
+  for (int c = 0; c < 3; ++c) {
+    a.gb[c] = grid ? grid->bmin[c] : 0.f; a.gl[c] = grid ? grid->len[c] : 0.f; a.gr[c] = grid ? grid->res[c] : 1;
+    a.gstep[c] = (grid && grid->res[c] > 1) ? 1.0f / (float)(grid->res[c] - 1) : 0.f;      // IEEE float division == __fdiv_rn of make_grid_kernel
+  }
   a.gx_first = grid ? grid->x_first : 0;
   if (grid) a.pts = nullptr;
   if (grid && n >= ((int64_t)1 << 31)) return avc_fail(ctx, AVC_EINVAL, "dense-grid entry: at most 2^31 - 1 points per call (split the slab)");
@@ -1010,7 +1022,7 @@ int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, c
   a.w16 = w.d_f16; a.f32 = w.d_f32; a.hdr = reinterpret_cast<const AvcBlobHeader*>(w.d_blob);
   a.trace = reinterpret_cast<long long*>(ctx->d_trace); a.dbg = ctx->dbg_flags;
   build_ops(a, &w.hdr, kind, mode, out_rgb != nullptr);
-  AVC_CUDA(ctx, cudaFuncSetAttribute(field_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  AVC_CUDA(ctx, cudaFuncSetAttribute(grid ? field_tc2_kernel<true> : field_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int64_t pairs = ((n + TILE - 1) / TILE + 1) / 2;
   const int max_clusters = ctx->sm_count / 2;
   const int n_ctas = 2 * (int)(pairs < (int64_t)max_clusters ? pairs : max_clusters);
@@ -1019,7 +1031,8 @@ int launch_tc2(avc_ctx* ctx, const AvcWeights& w, int kind, const AvcMap* map, c
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  AVC_CUDA(ctx, cudaLaunchKernelEx(&cfg, field_tc2_kernel, a));
+  if (grid) AVC_CUDA(ctx, cudaLaunchKernelEx(&cfg, field_tc2_kernel<true>, a));
+  else AVC_CUDA(ctx, cudaLaunchKernelEx(&cfg, field_tc2_kernel<false>, a));
   AVC_LAUNCH_CHECK(ctx, "field_tc2_kernel");
   return AVC_OK;
 }

@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(1024) grid_bounds_kernel(const float* __restri
       G[l] = g;
     }
   }
-  for (int i = threadIdx.x; i < GRID_MAX_CELLS + GRID1_MAX_CELLS; i += blockDim.x) cnt[i] = 0;
 }
 __global__ void grid_count_kernel(const float* __restrict__ ref, int m, const GridDesc* __restrict__ Gp, int* __restrict__ cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,25 +102,31 @@ __global__ void grid_count_kernel(const float* __restrict__ ref, int m, const Gr
   atomicAdd(&cnt[grid_cell(Gp[0], x, y, z, cx, cy, cz)], 1);
   atomicAdd(&cnt[GRID_MAX_CELLS + grid_cell(Gp[1], x, y, z, cx, cy, cz)], 1);
 }
-// one block per level
+// one block per level; a thread owns 16 consecutive cells per round (a 48 x 48 x 15 grid is 3 rounds instead of 34)
 __global__ void __launch_bounds__(1024) grid_scan_kernel(const GridDesc* __restrict__ Gp, int* __restrict__ cnt_all, int* __restrict__ start_all) {
   __shared__ int wsum[32]; __shared__ int carry;
+  constexpr int CPT = 16;
   const int level = blockIdx.x;
   int* cnt = cnt_all + level * GRID_MAX_CELLS; int* start = start_all + level * (GRID_MAX_CELLS + 4);
   const int cells = Gp[level].cells;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int base = 0; base < cells; base += 1024) {
-    const int c = base + threadIdx.x;
-    const int x = c < cells ? cnt[c] : 0;
-    int inc = x;
+  for (int base = 0; base < cells; base += 1024 * CPT) {
+    const int c0 = base + threadIdx.x * CPT;
+    int x[CPT]; int sum = 0;
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) { x[e] = c0 + e < cells ? cnt[c0 + e] : 0; sum += x[e]; }
+    int inc = sum;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
     int pre = 0, tot = 0;
     for (int w = 0; w < 32; ++w) { const int sw = wsum[w]; if (w < wid) pre += sw; tot += sw; }
-    if (c < cells) { start[c] = carry + pre + inc - x; cnt[c] = 0; }      // cnt becomes the fill cursor
+    int run = carry + pre + inc - sum;
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) { if (c0 + e < cells) { start[c0 + e] = run; cnt[c0 + e] = 0; } run += x[e]; }      // cnt becomes the fill cursor
     __syncthreads();
     if (threadIdx.x == 0) carry += tot;
     __syncthreads();
@@ -524,6 +529,7 @@ int build_grid(avc_ctx* ctx, const float* ref, int m, int64_t n_query, cudaStrea
   }
   const float h_min = [] { const char* e = getenv("AVC_KNN_CELL"); const float v = e ? (float)atof(e) : 0.f; return v >= 0.01f && v <= 1.f ? v : 0.04f; }();   // tuning knob (metres), read per call
   const int rmax = [] { const char* e = getenv("AVC_KNN_RMAX"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 12 ? v : GRID_RMAX; }();
+  AVC_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)2 * GRID_MAX_CELLS * sizeof(int), st));      // the copy engine zeroes the counters (was a 24 us single-block loop)
   grid_bounds_kernel<<<1, 1024, 0, st>>>(ref, m, h_min, rmax, G, cnt);
   AVC_LAUNCH_CHECK(ctx, "grid_bounds_kernel");
   grid_count_kernel<<<(m + 255) / 256, 256, 0, st>>>(ref, m, G, cnt);

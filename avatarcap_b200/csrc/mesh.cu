@@ -16,8 +16,11 @@
 namespace {
 
 constexpr int MC_NT = 256;
-constexpr int MC_VPT = 4;                  // voxels per thread (consecutive in z)
-constexpr int MC_VPB = MC_NT * MC_VPT;     // voxels per block
+constexpr int MC_VPT = 4;                  // voxels per quad (consecutive in z: one float4 of a z-row on the vector path)
+constexpr int MC_QPT = 4;                  // quads per thread: 16 consecutive voxels. A block's lifetime is a chain of latencies (loads, two
+                                           // barriers, the look-back round trip); 4 096 voxels per block instead of 1 024 means a quarter of the
+                                           // blocks pay it (launch list r2d: 235 us for 16 384 blocks of 1 024 voxels at 256^3)
+constexpr int MC_VPB = MC_NT * MC_VPT * MC_QPT;     // voxels per block
 
 struct McDims {
   int rx, ry, rz;        // local extents (including halo planes)
@@ -207,15 +210,16 @@ __global__ void __launch_bounds__(MC_NT) mc_scan_kernel(const float* __restrict_
   __shared__ unsigned char s_ntri[256];
   const int bid = lookback_ticket(L);
   stage_ntri(s_ntri);
-  const int64_t v0 = ((int64_t)bid * MC_NT + threadIdx.x) * MC_VPT;
-  int c[MC_VPT], cut[MC_VPT], ccase[MC_VPT]; int nv = 0, nvo = 0, nt = 0;
-  {
-    Vox4 r; classify_thread(vol, d, v0, r);
+  const int64_t t0 = ((int64_t)bid * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT);       // first of this thread's 16 consecutive voxels
+  int cut[MC_QPT][MC_VPT], ccase[MC_QPT][MC_VPT]; int nv = 0, nvo = 0, nt = 0;
+#pragma unroll
+  for (int s = 0; s < MC_QPT; ++s) {
+    Vox4 r; classify_thread(vol, d, t0 + s * MC_VPT, r);
 #pragma unroll
     for (int q = 0; q < MC_VPT; ++q) {
-      cut[q] = r.cut[q]; c[q] = __popc(cut[q]); nv += c[q];
-      if ((r.own_mask >> q) & 1) nvo += c[q];
-      ccase[q] = r.ccase[q]; if (ccase[q] >= 0) nt += s_ntri[ccase[q]];
+      cut[s][q] = r.cut[q]; const int c = __popc(r.cut[q]); nv += c;
+      if ((r.own_mask >> q) & 1) nvo += c;
+      ccase[s][q] = r.ccase[q]; if (r.ccase[q] >= 0) nt += s_ntri[r.ccase[q]];
     }
   }
   // owned-vertex total: an order-independent integer sum
@@ -233,30 +237,31 @@ __global__ void __launch_bounds__(MC_NT) mc_scan_kernel(const float* __restrict_
     counts[0] = (long long)(all >> 31); counts[2] = (long long)(all & 0x7fffffffull);
   }
   if (!vbase) return;
-  int p = (int)(pre >> 31);
-  if (d.vec4 && v0 < d.nvox) {
-    *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + c[0], p + c[0] + c[1], p + c[0] + c[1] + c[2]);
-  } else {
-    int pp = p;
+  int p = (int)(pre >> 31), tb = (int)(pre & 0x7fffffffull);
 #pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += c[q]; }
-  }
-  if (nv) {
+  for (int s = 0; s < MC_QPT; ++s) {
+    const int64_t v0 = t0 + s * MC_VPT;
+    const int c0 = __popc(cut[s][0]), c1 = __popc(cut[s][1]), c2 = __popc(cut[s][2]), c3 = __popc(cut[s][3]);
+    if (d.vec4 && v0 < d.nvox) {
+      *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + c0, p + c0 + c1, p + c0 + c1 + c2);
+    } else {
+      int pp = p;
 #pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) {
+      for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += __popc(cut[s][q]); }
+    }
+    if (c0 + c1 + c2 + c3) {
       int e = p;
 #pragma unroll
-      for (int ax = 0; ax < 3; ++ax) if ((cut[q] >> ax) & 1) { if (e < cap_e) edges[e] = (long long)(v0 + q) * 4 + ax; ++e; }
-      p += c[q];
+      for (int q = 0; q < MC_VPT; ++q)
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) if ((cut[s][q] >> ax) & 1) { if (e < cap_e) edges[e] = (long long)(v0 + q) * 4 + ax; ++e; }
     }
-  }
-  if (nt) {
-    int tb = (int)(pre & 0x7fffffffull);
+    p += c0 + c1 + c2 + c3;
 #pragma unroll
     for (int q = 0; q < MC_VPT; ++q) {
-      if (ccase[q] < 0) continue;
-      const int ntri = s_ntri[ccase[q]];
-      for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)ccase[q] << 3) | tix;
+      if (ccase[s][q] < 0) continue;
+      const int ntri = s_ntri[ccase[s][q]];
+      for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)ccase[s][q] << 3) | tix;
     }
   }
 }
@@ -407,24 +412,27 @@ __global__ void __launch_bounds__(MC_NT) scatter_fill_kernel(const uint8_t* __re
                                                              const float* __restrict__ vals, const float* __restrict__ fill,
                                                              float* __restrict__ out) {
   const int bid = lookback_ticket(L);
-  const int64_t v0 = ((int64_t)bid * MC_NT + threadIdx.x) * MC_VPT;
-  int c = 0; bool f[MC_VPT];
-  if (v0 + MC_VPT <= n && (reinterpret_cast<uintptr_t>(flag) & 3) == 0) {
-    const uchar4 f4 = *reinterpret_cast<const uchar4*>(flag + v0);
-    f[0] = f4.x != 0; f[1] = f4.y != 0; f[2] = f4.z != 0; f[3] = f4.w != 0;
-    c = (int)f[0] + (int)f[1] + (int)f[2] + (int)f[3];
+  constexpr int EPT = MC_VPT * MC_QPT;                         // 16 consecutive flags per thread: one 16-byte load
+  const int64_t v0 = ((int64_t)bid * MC_NT + threadIdx.x) * EPT;
+  int c = 0; unsigned int f = 0;
+  if (v0 + EPT <= n && (reinterpret_cast<uintptr_t>(flag) & 15) == 0) {
+    const uint4 w = *reinterpret_cast<const uint4*>(flag + v0);
+    const unsigned int ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) f |= ((ws[q >> 2] >> (8 * (q & 3))) & 0xffu) ? (1u << q) : 0u;
   } else {
 #pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) { f[q] = (v0 + q < n) && flag[v0 + q]; c += f[q]; }
+    for (int q = 0; q < EPT; ++q) f |= ((v0 + q < n) && flag[v0 + q]) ? (1u << q) : 0u;
   }
+  c = __popc(f);
   unsigned long long tot;
   const unsigned long long mine = block_excl_scan64((unsigned long long)c, &tot);
   int64_t p = (int64_t)(lookback_prefix(L, bid, tot) + mine);
 #pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) {
+  for (int q = 0; q < EPT; ++q) {
     const int64_t v = v0 + q;
     if (v >= n) break;
-    if (f[q]) { out[v] = vals[p]; ++p; } else { out[v] = fill[v - p]; }
+    if ((f >> q) & 1) { out[v] = vals[p]; ++p; } else { out[v] = fill[v - p]; }
   }
 }
 

@@ -173,10 +173,33 @@ def strided_sample(scene, res, count):
     return synth.volume_points(scene['frame']['cano_bounds'], sub)
 
 
+def run_reference_full(args):
+    """ONE full pass of the CPU port over the whole 256^3 grid (SURVEY.md 8d allows it once: ~2 minutes on 16 cores): what the
+    rate-extrapolated `cpu_baseline` / reference arm stand for, measured without extrapolation. Prints one JSON line."""
+    import torch
+    from oracle import field_oracle as fo
+    from avatarcap_b200 import synth
+    scene = build_scene()
+    res = GRIDS[1]
+    threads = host_cores()
+    torch.set_num_threads(threads)
+    pts = synth.volume_points(scene['frame']['cano_bounds'], res)
+    fo.occupancy_query(scene['avatar_sd'], pts[:65536], scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)     # warm-up chunk
+    t0 = time.perf_counter()
+    n = len(pts)
+    for s0 in range(0, n, 1 << 21):                         # 2 Mi-point slices bound the host memory of the activations
+        fo.occupancy_query(scene['avatar_sd'], pts[s0:s0 + (1 << 21)], scene['pose_map'], scene['frame']['cano_smpl_center'], with_texture=True)
+    dt = time.perf_counter() - t0
+    print(json.dumps({'impl': 'reference', 'full_pass': True, 'metric': 'Mpoints/s implicit-field eval @256^3 (occupancy+texture), CPU port, whole grid',
+                      'value': n / dt / 1e6, 'unit': 'Mpoints/s', 'seconds': dt, 'points': n, 'cores': threads, 'kind': 'port', 'dtype': 'f32'}))
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if args.cpu_full:
+        return run_reference_full(args)
     scene = build_scene()
     res = GRIDS[args.gpus]
     threads = host_cores()
@@ -636,6 +659,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-frame', action='store_true')
+    ap.add_argument('--cpu-full', action='store_true', help='with --impl reference: one un-extrapolated CPU pass over the whole 256^3 grid (~2 min)')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling block (one 256^3 frame split over the N GPUs)')
     ap.add_argument('--no-parity', action='store_true', help='skip the merged-mesh == single-GPU-mesh check on real ranks')
     ap.add_argument('--no-gpu-torch', action='store_true', help='skip the reference-on-GPU (PyTorch) baseline')
