@@ -443,6 +443,7 @@ __device__ __forceinline__ void hidden_pair(uint32_t t0, uint32_t t1, const floa
 // torch.linspace(0, 1, steps)[q] in float32 exactly as ATen computes it (and make_grid_kernel restates it); step = fl(1 / (steps - 1)) comes from
 // the host (an IEEE division there, no division subroutine in this kernel: its instruction footprint is on the critical path)
 __device__ __forceinline__ float lin_coord(int q, int steps, float step) {
+  if (steps <= 1) return 0.f;
   return q < steps / 2 ? __fmul_rn(step, (float)q) : __fsub_rn(1.f, __fmul_rn(step, (float)(steps - 1 - q)));
 }
 

@@ -128,3 +128,56 @@ def test_projection_matrices_equal_the_reference(ref_env):
             b = rr.gl_perspective_projection_matrix(551.3, 548.9, 255.2, 260.7, 512, 480, gl_space=gl_space)
             assert a.dtype == b.dtype and np.array_equal(a, b)
         assert np.array_equal(mod.gl_perspective_projection_matrix(500, 500, 256, 256, 512, 512, 50.0, 0.2), rr.gl_perspective_projection_matrix(500, 500, 256, 256, 512, 512, 50.0, 0.2))
+
+
+@pytest.mark.gpu
+def test_patched_real_reference_runs_on_the_library(ref_env):
+    """Where BOTH a B200 and a reference checkout are reachable (AVATARCAP_REFERENCE): the reference's own modules, moved to the
+    device and patched, must produce the reference's results through the library -- OccupancyNet.query, ReconNetwork.infer's
+    decoder, calculate_lbs / skinning, recon_mesh's vertex count -- and a train-mode twin must keep using PyTorch."""
+    from avatarcap_b200 import patch
+    from avatarcap_b200.engine import Engine
+    import network.arch_avatar as aa
+    import utils.smpl_util as su
+    import config
+    frame = ref_env['frame']; gg = ref_env['gg']
+    dev = torch.device('cuda', 0)
+    net = aa.GeoTexAvatar().eval()
+    net.load_state_dict(gg.to_torch_sd(synth.avatar_state_dict()), strict=False)
+    fmap = torch.from_numpy(synth.feature_map(64, 64, 64, synth.SEED + 2))[None]
+    net.warping_field.pose_feat_map = fmap
+    rs = np.random.RandomState(2)
+    bmin, bmax = frame['cano_bounds']
+    pts = torch.from_numpy((rs.uniform(0, 1, (5000, 3)) * (bmax - bmin) + bmin).astype(np.float32))[None]
+    batch = {'cano_pts': pts, 'cano_smpl_center': torch.from_numpy(frame['cano_smpl_center'])[None]}
+    su.smpl_util.set_cano_smpl_vertices(torch.from_numpy(frame['cano_smpl_v']))
+    with torch.no_grad():
+        want = aa.OccupancyNet(net).query(batch)                      # the reference, CPU f32
+        want_lbs = su.smpl_util.calculate_lbs(pts)
+    eng = Engine(dev)
+    old_dev = config.device
+    config.device = dev
+    patch.install(engine=eng, encoders=False, render=False)
+    try:
+        net_d = net.to(dev); net_d.warping_field.pose_feat_map = fmap.to(dev)
+        su.smpl_util.smpl_skinning_weights = su.smpl_util.smpl_skinning_weights.to(dev)
+        su.smpl_util.set_cano_smpl_vertices(torch.from_numpy(frame['cano_smpl_v']).to(dev))
+        batch_d = {k: v.to(dev) for k, v in batch.items()}
+        launches = eng.launch_count
+        with torch.no_grad():
+            got = aa.OccupancyNet(net_d).query(batch_d)
+            got_lbs = su.smpl_util.calculate_lbs(pts.to(dev))
+        assert eng.launch_count > launches                            # it did go through the library
+        assert float((got['cano_pts_ov'].cpu() - want['cano_pts_ov']).abs().max()) < 1e-4
+        assert float((got['nonrigid_offset'].cpu() - want['nonrigid_offset']).abs().max()) < 2e-6
+        assert float((got_lbs.cpu() - want_lbs).abs().max()) < 2e-6
+        twin = aa.GeoTexAvatar().to(dev)                               # train mode, like finetune_tex's network_init
+        twin.load_state_dict(net_d.state_dict()); twin.warping_field.pose_feat_map = fmap.to(dev)
+        launches = eng.launch_count
+        with torch.no_grad():
+            aa.OccupancyNet(twin).query(batch_d)
+        assert eng.launch_count == launches                           # batch-statistics BatchNorm: the reference's own path
+    finally:
+        patch.uninstall(); config.device = old_dev
+        su.smpl_util.smpl_skinning_weights = su.smpl_util.smpl_skinning_weights.cpu()
+        eng.close()
