@@ -204,66 +204,82 @@ __device__ __forceinline__ unsigned long long lookback_prefix(const LookbackStat
 // index, then axis), the compact list of sign-changing EDGES (edges[vid] = voxel*4 + axis: the vertex kernel runs one thread per
 // vertex) and of TRIANGLES (tris[t] = voxel << 11 | case << 3 | triangle number: one thread per triangle). vbase == NULL: count only.
 // Entries beyond the capacities cap_e / cap_t are dropped (the totals stay exact, the caller sees the overflow).
-__global__ void __launch_bounds__(MC_NT) mc_scan_kernel(const float* __restrict__ vol, McDims d, LookbackState L, int nblk, long long* __restrict__ counts,
-                                                        int* __restrict__ vbase, long long* __restrict__ edges, long long* __restrict__ tris,
-                                                        long long cap_e, long long cap_t) {
+__global__ void __launch_bounds__(MC_NT, 4) mc_scan_kernel(const float* __restrict__ vol, McDims d, LookbackState L, int nblk, long long* __restrict__ counts,
+                                                           int* __restrict__ vbase, long long* __restrict__ edges, long long* __restrict__ tris,
+                                                           long long cap_e, long long cap_t) {
+  // PERSISTENT blocks: a chunk (4 096 voxels) is a chain of latencies -- ticket, loads, block scan, look-back round trip -- and with one
+  // chunk per block the kernel ran at the pace of (waves x chunk latency): 230-300 us at 256^3 whatever the chunk size (launch lists
+  // r2d / r2e). Here each resident block loops over chunks, fetches its NEXT ticket while it works on the current chunk and keeps the
+  // case table staged; per-voxel results are packed (12 bits each) so that 4 blocks stay resident per SM.
   __shared__ unsigned char s_ntri[256];
-  const int bid = lookback_ticket(L);
+  __shared__ int s_next[2];
   stage_ntri(s_ntri);
-  const int64_t t0 = ((int64_t)bid * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT);       // first of this thread's 16 consecutive voxels
-  int cut[MC_QPT][MC_VPT], ccase[MC_QPT][MC_VPT]; int nv = 0, nvo = 0, nt = 0;
+  if (threadIdx.x == 0) s_next[0] = (int)atomicAdd(L.ticket, 1u);
+  __syncthreads();
+  int bid = s_next[0];
+  long long n_owned = 0;                                       // this thread's owned vertices over all its chunks
+  for (int it = 0; bid < nblk; ++it) {
+    if (threadIdx.x == 0) s_next[(it + 1) & 1] = (int)atomicAdd(L.ticket, 1u);      // consumed after the barriers below
+    const int64_t t0 = ((int64_t)bid * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT);     // first of this thread's 16 consecutive voxels
+    unsigned long long info[MC_QPT];                             // per voxel q of quad s: bits [12q, 12q+3) cut flags, [12q+3, 12q+12) case + 1
+    int nv = 0, nt = 0;
 #pragma unroll
-  for (int s = 0; s < MC_QPT; ++s) {
-    Vox4 r; classify_thread(vol, d, t0 + s * MC_VPT, r);
+    for (int s = 0; s < MC_QPT; ++s) {
+      Vox4 r; classify_thread(vol, d, t0 + s * MC_VPT, r);
+      unsigned long long w = 0;
 #pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) {
-      cut[s][q] = r.cut[q]; const int c = __popc(r.cut[q]); nv += c;
-      if ((r.own_mask >> q) & 1) nvo += c;
-      ccase[s][q] = r.ccase[q]; if (r.ccase[q] >= 0) nt += s_ntri[r.ccase[q]];
+      for (int q = 0; q < MC_VPT; ++q) {
+        const int c = __popc(r.cut[q]); nv += c;
+        if ((r.own_mask >> q) & 1) n_owned += c;
+        if (r.ccase[q] >= 0) nt += s_ntri[r.ccase[q]];
+        w |= (unsigned long long)((unsigned int)r.cut[q] | ((unsigned int)(r.ccase[q] + 1) << 3)) << (12 * q);
+      }
+      info[s] = w;
     }
-  }
-  // owned-vertex total: an order-independent integer sum
-  {
-    int w = nvo;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-    if ((threadIdx.x & 31) == 0 && w) atomicAdd(reinterpret_cast<unsigned long long*>(counts + 1), (unsigned long long)w);
-  }
-  unsigned long long tot;
-  const unsigned long long mine = block_excl_scan64(((unsigned long long)nv << 31) | (unsigned long long)nt, &tot);
-  const unsigned long long pre = lookback_prefix(L, bid, tot) + mine;
-  if (bid == nblk - 1 && threadIdx.x == MC_NT - 1) {
-    const unsigned long long all = pre + (((unsigned long long)nv << 31) | (unsigned long long)nt);
-    counts[0] = (long long)(all >> 31); counts[2] = (long long)(all & 0x7fffffffull);
-  }
-  if (!vbase) return;
-  int p = (int)(pre >> 31), tb = (int)(pre & 0x7fffffffull);
-#pragma unroll
-  for (int s = 0; s < MC_QPT; ++s) {
-    const int64_t v0 = t0 + s * MC_VPT;
-    const int c0 = __popc(cut[s][0]), c1 = __popc(cut[s][1]), c2 = __popc(cut[s][2]), c3 = __popc(cut[s][3]);
-    if (d.vec4 && v0 < d.nvox) {
-      *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + c0, p + c0 + c1, p + c0 + c1 + c2);
-    } else {
-      int pp = p;
-#pragma unroll
-      for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += __popc(cut[s][q]); }
+    unsigned long long tot;
+    const unsigned long long mine = block_excl_scan64(((unsigned long long)nv << 31) | (unsigned long long)nt, &tot);
+    const unsigned long long pre = lookback_prefix(L, bid, tot) + mine;
+    if (bid == nblk - 1 && threadIdx.x == MC_NT - 1) {
+      const unsigned long long all = pre + (((unsigned long long)nv << 31) | (unsigned long long)nt);
+      counts[0] = (long long)(all >> 31); counts[2] = (long long)(all & 0x7fffffffull);
     }
-    if (c0 + c1 + c2 + c3) {
-      int e = p;
+    if (vbase) {
+      int p = (int)(pre >> 31), tb = (int)(pre & 0x7fffffffull);
 #pragma unroll
-      for (int q = 0; q < MC_VPT; ++q)
+      for (int s = 0; s < MC_QPT; ++s) {
+        const int64_t v0 = t0 + s * MC_VPT;
+        int cq[MC_VPT];
 #pragma unroll
-        for (int ax = 0; ax < 3; ++ax) if ((cut[s][q] >> ax) & 1) { if (e < cap_e) edges[e] = (long long)(v0 + q) * 4 + ax; ++e; }
+        for (int q = 0; q < MC_VPT; ++q) cq[q] = __popc((unsigned int)(info[s] >> (12 * q)) & 7u);
+        if (d.vec4 && v0 < d.nvox) {
+          *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + cq[0], p + cq[0] + cq[1], p + cq[0] + cq[1] + cq[2]);
+        } else {
+          int pp = p;
+#pragma unroll
+          for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += cq[q]; }
+        }
+        if (info[s]) {
+#pragma unroll
+          for (int q = 0; q < MC_VPT; ++q) {
+            const unsigned int wq = (unsigned int)(info[s] >> (12 * q)) & 0xfffu;
+            const int cut = (int)(wq & 7u), cc = (int)(wq >> 3) - 1;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) if ((cut >> ax) & 1) { if (p < cap_e) edges[p] = (long long)(v0 + q) * 4 + ax; ++p; }
+            if (cc >= 0) {
+              const int ntri = s_ntri[cc];
+              for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)cc << 3) | tix;
+            }
+          }
+        }
+      }
     }
-    p += c0 + c1 + c2 + c3;
-#pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) {
-      if (ccase[s][q] < 0) continue;
-      const int ntri = s_ntri[ccase[s][q]];
-      for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)ccase[s][q] << 3) | tix;
-    }
+    __syncthreads();                                             // s_next[(it + 1) & 1] is visible; s_next[it & 1] may be rewritten next round
+    bid = s_next[(it + 1) & 1];
   }
+  // owned-vertex total: an order-independent integer sum, one atomic per warp for the whole kernel
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_owned += __shfl_xor_sync(0xffffffffu, n_owned, o);
+  if ((threadIdx.x & 31) == 0 && n_owned) atomicAdd(reinterpret_cast<unsigned long long*>(counts + 1), (unsigned long long)n_owned);
 }
 
 struct McEmit {
@@ -507,7 +523,7 @@ extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], fl
   if (rc) return rc;
   d.vec4 = mc_vec4_ok(vol, res);
   AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, S.zero_bytes, st));
-  mc_scan_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, nullptr, nullptr, nullptr, 0, 0);
+  mc_scan_kernel<<<nblk < ctx->sm_count * 4 ? nblk : ctx->sm_count * 4, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, nullptr, nullptr, nullptr, 0, 0);
   AVC_LAUNCH_CHECK(ctx, "mc_scan_kernel(count)");
   AVC_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, S.counts, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   AVC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -542,7 +558,8 @@ static int mc_extract_async(avc_ctx* ctx, const float* vol, const int res[3], co
   long long* d_edges = reinterpret_cast<long long*>(ctx->d_scratch2);
   long long* d_tris = d_edges + cap_v + 1;
   AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, S.zero_bytes, st));
-  mc_scan_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, S.vbase, d_edges, d_tris, (long long)cap_v, (long long)cap_f);
+  mc_scan_kernel<<<nblk < ctx->sm_count * 4 ? nblk : ctx->sm_count * 4, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, S.vbase, d_edges, d_tris,
+                                                                                        (long long)cap_v, (long long)cap_f);
   AVC_LAUNCH_CHECK(ctx, "mc_scan_kernel");
   McEmit e;
   const int gres[3] = {gres_x, res[1], res[2]};
