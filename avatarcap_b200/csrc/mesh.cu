@@ -147,139 +147,121 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
   return wprefix + inc - val;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Single-pass chained scan across blocks (decoupled look-back). One 64-bit state word per block: bits 63..62 = flag
-// (0 empty, 1 = the block's own aggregate, 2 = inclusive prefix of everything up to and including the block), bits 61..0 = payload
-// (for marching cubes two 31-bit counters: vertices << 31 | triangles). Blocks take their logical index from an atomic ticket,
-// so every predecessor of a running block has itself started -- the spin below always makes progress. Replaces the
-// count kernel + single-CTA scan kernel + second classification pass of round 1 (3 launches, the volume read twice).
-constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = (1ull << 62) - 1;
-struct LookbackState { unsigned long long* state; unsigned int* ticket; };
-
-__device__ __forceinline__ int lookback_ticket(const LookbackState& L) {
-  __shared__ int s_bid;
-  if (threadIdx.x == 0) s_bid = (int)atomicAdd(L.ticket, 1u);
-  __syncthreads();
-  return s_bid;
-}
-// called by ALL threads of the block; returns the exclusive prefix (payload sum of the blocks 0..bid-1) to every thread
-__device__ __forceinline__ unsigned long long lookback_prefix(const LookbackState& L, int bid, unsigned long long agg) {
-  __shared__ unsigned long long s_excl;
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    volatile unsigned long long* st = L.state;
-    if (lane == 0) { st[bid] = (bid == 0 ? LB_PREFIX : LB_AGG) | agg; }
-    unsigned long long excl = 0;
-    if (bid > 0) {
-      int base = bid - 1;
-      for (;;) {
-        const int idx = base - lane;
-        unsigned long long w = LB_PREFIX;                  // before block 0: an inclusive prefix of zero
-        if (idx >= 0) {
-          unsigned int spins = 0;
-          while (((w = st[idx]) >> 62) == 0) {
-            if (++spins > (1u << 26)) { printf("avatarcap_b200: look-back scan stalled (block %d waits for %d)\n", bid, idx); __trap(); }
-            __nanosleep(32);
-          }
-        }
-        const unsigned int m = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-        const int first = m ? __ffs((int)m) - 1 : 32;        // nearest predecessor whose inclusive prefix is known
-        unsigned long long c = lane <= first ? (w & LB_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        excl += c;
-        if (m) break;
-        base -= 32;
-      }
-      if (lane == 0) st[bid] = LB_PREFIX | (excl + agg);
-    }
-    if (lane == 0) s_excl = excl;
-  }
-  __syncthreads();
-  return s_excl;
-}
-
 // mc counters (device, int64): [0] vertices in the scan range, [1] owned vertices, [2] triangles, [3] reserved
-// Fused pass: classify -> block scan -> look-back -> vbase[v] = exclusive vertex prefix of voxel v (canonical order: voxel linear
-// index, then axis), the compact list of sign-changing EDGES (edges[vid] = voxel*4 + axis: the vertex kernel runs one thread per
-// vertex) and of TRIANGLES (tris[t] = voxel << 11 | case << 3 | triangle number: one thread per triangle). vbase == NULL: count only.
-// Entries beyond the capacities cap_e / cap_t are dropped (the totals stay exact, the caller sees the overflow).
-__global__ void __launch_bounds__(MC_NT, 4) mc_scan_kernel(const float* __restrict__ vol, McDims d, LookbackState L, int nblk, long long* __restrict__ counts,
-                                                           int* __restrict__ vbase, long long* __restrict__ edges, long long* __restrict__ tris,
-                                                           long long cap_e, long long cap_t) {
-  // PERSISTENT blocks: a chunk (4 096 voxels) is a chain of latencies -- ticket, loads, block scan, look-back round trip -- and with one
-  // chunk per block the kernel ran at the pace of (waves x chunk latency): 230-300 us at 256^3 whatever the chunk size (launch lists
-  // r2d / r2e). Here each resident block loops over chunks, fetches its NEXT ticket while it works on the current chunk and keeps the
-  // case table staged; per-voxel results are packed (12 bits each) so that 4 blocks stay resident per SM.
-  __shared__ unsigned char s_ntri[256];
-  __shared__ int s_next[2];
-  stage_ntri(s_ntri);
-  if (threadIdx.x == 0) s_next[0] = (int)atomicAdd(L.ticket, 1u);
-  __syncthreads();
-  int bid = s_next[0];
-  long long n_owned = 0;                                       // this thread's owned vertices over all its chunks
-  for (int it = 0; bid < nblk; ++it) {
-    if (threadIdx.x == 0) s_next[(it + 1) & 1] = (int)atomicAdd(L.ticket, 1u);      // consumed after the barriers below
-    const int64_t t0 = ((int64_t)bid * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT);     // first of this thread's 16 consecutive voxels
-    unsigned long long info[MC_QPT];                             // per voxel q of quad s: bits [12q, 12q+3) cut flags, [12q+3, 12q+12) case + 1
-    int nv = 0, nt = 0;
+//
+// Two passes over the volume, NO chained scan: (1) mc_count_kernel writes one record per 4 096-voxel chunk {vertices << 31 | triangles,
+// owned vertices}; (2) every block of mc_emit_kernel gets its exclusive prefix by SUMMING the records of the chunks before it (a
+// coalesced read of at most 64 KB that sits in L2, 256 threads, fixed order), classifies its chunk again (the 67 MB volume is L2
+// resident on a B200) and writes vbase[v] = exclusive vertex prefix of voxel v (canonical order: voxel linear index, then axis), the
+// compact list of sign-changing EDGES (edges[vid] = voxel*4 + axis: the vertex kernel runs one thread per vertex) and of TRIANGLES
+// (tris[t] = voxel << 11 | case << 3 | triangle number: one thread per triangle). Entries beyond the capacities cap_e / cap_t are
+// dropped (the totals stay exact, the caller sees the overflow).
+// History of this pass at 256^3 (launch lists in profiles/): round 1 count 103 us + single-CTA scan 66 us + second classification 89 us;
+// a single fused pass with a decoupled look-back scan ran 190-300 us, persistent or not, 1 024 or 4 096 voxels per block -- top stall
+// `barrier`: with ~600 chunks in flight none of the predecessors inside a chunk's look-back window has its inclusive prefix yet, so
+// every chunk walks back through all of them, one L2 round trip per 32. Independent blocks + a redundant 64 KB sum have no chain at all.
+struct ThreadCls { unsigned long long info[MC_QPT]; int nv, nvo, nt; };     // per voxel q of quad s: bits [12q, 12q+3) cut flags, [12q+3, 12q+12) case + 1
+
+__device__ __forceinline__ void classify16(const float* __restrict__ vol, const McDims& d, int64_t t0, const unsigned char* s_ntri, ThreadCls& T) {
+  T.nv = T.nvo = T.nt = 0;
 #pragma unroll
-    for (int s = 0; s < MC_QPT; ++s) {
-      Vox4 r; classify_thread(vol, d, t0 + s * MC_VPT, r);
-      unsigned long long w = 0;
+  for (int s = 0; s < MC_QPT; ++s) {
+    Vox4 r; classify_thread(vol, d, t0 + s * MC_VPT, r);
+    unsigned long long w = 0;
+#pragma unroll
+    for (int q = 0; q < MC_VPT; ++q) {
+      const int c = __popc(r.cut[q]); T.nv += c;
+      if ((r.own_mask >> q) & 1) T.nvo += c;
+      if (r.ccase[q] >= 0) T.nt += s_ntri[r.ccase[q]];
+      w |= (unsigned long long)((unsigned int)r.cut[q] | ((unsigned int)(r.ccase[q] + 1) << 3)) << (12 * q);
+    }
+    T.info[s] = w;
+  }
+}
+
+__global__ void __launch_bounds__(MC_NT, 4) mc_count_kernel(const float* __restrict__ vol, McDims d, unsigned long long* __restrict__ chunk) {
+  __shared__ unsigned char s_ntri[256];
+  __shared__ unsigned long long s_a[MC_NT / 32], s_b[MC_NT / 32];
+  stage_ntri(s_ntri);
+  ThreadCls T; classify16(vol, d, ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT), s_ntri, T);
+  unsigned long long a = ((unsigned long long)T.nv << 31) | (unsigned long long)T.nt, b = (unsigned long long)T.nvo;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < MC_NT / 32; ++w) { a += s_a[w]; b += s_b[w]; }
+    chunk[2 * blockIdx.x] = a; chunk[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// sum of the chunk records [0, n): every thread of the block gets {vertices << 31 | triangles, owned}
+__device__ __forceinline__ void sum_chunks(const unsigned long long* __restrict__ chunk, int n, unsigned long long& a, unsigned long long& b) {
+  __shared__ unsigned long long s_a[MC_NT / 32], s_b[MC_NT / 32];
+  a = 0; b = 0;
+  for (int c = threadIdx.x; c < n; c += MC_NT) { const ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2*>(chunk) + c); a += r.x; b += r.y; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  a = 0; b = 0;
+#pragma unroll
+  for (int w = 0; w < MC_NT / 32; ++w) { a += s_a[w]; b += s_b[w]; }
+}
+
+// totals only (avc_mc_count): one block
+__global__ void __launch_bounds__(MC_NT) mc_total_kernel(const unsigned long long* __restrict__ chunk, int nblk, long long* __restrict__ counts) {
+  unsigned long long a, b; sum_chunks(chunk, nblk, a, b);
+  if (threadIdx.x == 0) { counts[0] = (long long)(a >> 31); counts[1] = (long long)b; counts[2] = (long long)(a & 0x7fffffffull); }
+}
+
+__global__ void __launch_bounds__(MC_NT, 4) mc_emit_kernel(const float* __restrict__ vol, McDims d, const unsigned long long* __restrict__ chunk, int nblk,
+                                                           long long* __restrict__ counts, int* __restrict__ vbase, long long* __restrict__ edges,
+                                                           long long* __restrict__ tris, long long cap_e, long long cap_t) {
+  __shared__ unsigned char s_ntri[256];
+  stage_ntri(s_ntri);
+  const int bid = blockIdx.x;
+  unsigned long long base, owned_before; sum_chunks(chunk, bid, base, owned_before);
+  const int64_t t0 = ((int64_t)bid * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT);     // first of this thread's 16 consecutive voxels
+  ThreadCls T; classify16(vol, d, t0, s_ntri, T);
+  unsigned long long tot;
+  const unsigned long long mine = block_excl_scan64(((unsigned long long)T.nv << 31) | (unsigned long long)T.nt, &tot);
+  const unsigned long long pre = base + mine;
+  if (bid == nblk - 1 && threadIdx.x == 0) {                    // the last chunk publishes the totals
+    const unsigned long long all = base + tot;
+    const ulonglong2 last = __ldg(reinterpret_cast<const ulonglong2*>(chunk) + bid);
+    counts[0] = (long long)(all >> 31); counts[1] = (long long)(owned_before + last.y); counts[2] = (long long)(all & 0x7fffffffull);
+  }
+  int p = (int)(pre >> 31), tb = (int)(pre & 0x7fffffffull);
+#pragma unroll
+  for (int s = 0; s < MC_QPT; ++s) {
+    const int64_t v0 = t0 + s * MC_VPT;
+    int cq[MC_VPT];
+#pragma unroll
+    for (int q = 0; q < MC_VPT; ++q) cq[q] = __popc((unsigned int)(T.info[s] >> (12 * q)) & 7u);
+    if (d.vec4 && v0 < d.nvox) {
+      *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + cq[0], p + cq[0] + cq[1], p + cq[0] + cq[1] + cq[2]);
+    } else {
+      int pp = p;
+#pragma unroll
+      for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += cq[q]; }
+    }
+    if (T.info[s]) {
 #pragma unroll
       for (int q = 0; q < MC_VPT; ++q) {
-        const int c = __popc(r.cut[q]); nv += c;
-        if ((r.own_mask >> q) & 1) n_owned += c;
-        if (r.ccase[q] >= 0) nt += s_ntri[r.ccase[q]];
-        w |= (unsigned long long)((unsigned int)r.cut[q] | ((unsigned int)(r.ccase[q] + 1) << 3)) << (12 * q);
-      }
-      info[s] = w;
-    }
-    unsigned long long tot;
-    const unsigned long long mine = block_excl_scan64(((unsigned long long)nv << 31) | (unsigned long long)nt, &tot);
-    const unsigned long long pre = lookback_prefix(L, bid, tot) + mine;
-    if (bid == nblk - 1 && threadIdx.x == MC_NT - 1) {
-      const unsigned long long all = pre + (((unsigned long long)nv << 31) | (unsigned long long)nt);
-      counts[0] = (long long)(all >> 31); counts[2] = (long long)(all & 0x7fffffffull);
-    }
-    if (vbase) {
-      int p = (int)(pre >> 31), tb = (int)(pre & 0x7fffffffull);
+        const unsigned int wq = (unsigned int)(T.info[s] >> (12 * q)) & 0xfffu;
+        const int cut = (int)(wq & 7u), cc = (int)(wq >> 3) - 1;
 #pragma unroll
-      for (int s = 0; s < MC_QPT; ++s) {
-        const int64_t v0 = t0 + s * MC_VPT;
-        int cq[MC_VPT];
-#pragma unroll
-        for (int q = 0; q < MC_VPT; ++q) cq[q] = __popc((unsigned int)(info[s] >> (12 * q)) & 7u);
-        if (d.vec4 && v0 < d.nvox) {
-          *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + cq[0], p + cq[0] + cq[1], p + cq[0] + cq[1] + cq[2]);
-        } else {
-          int pp = p;
-#pragma unroll
-          for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += cq[q]; }
-        }
-        if (info[s]) {
-#pragma unroll
-          for (int q = 0; q < MC_VPT; ++q) {
-            const unsigned int wq = (unsigned int)(info[s] >> (12 * q)) & 0xfffu;
-            const int cut = (int)(wq & 7u), cc = (int)(wq >> 3) - 1;
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax) if ((cut >> ax) & 1) { if (p < cap_e) edges[p] = (long long)(v0 + q) * 4 + ax; ++p; }
-            if (cc >= 0) {
-              const int ntri = s_ntri[cc];
-              for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)cc << 3) | tix;
-            }
-          }
+        for (int ax = 0; ax < 3; ++ax) if ((cut >> ax) & 1) { if (p < cap_e) edges[p] = (long long)(v0 + q) * 4 + ax; ++p; }
+        if (cc >= 0) {
+          const int ntri = s_ntri[cc];
+          for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)cc << 3) | tix;
         }
       }
     }
-    __syncthreads();                                             // s_next[(it + 1) & 1] is visible; s_next[it & 1] may be rewritten next round
-    bid = s_next[(it + 1) & 1];
   }
-  // owned-vertex total: an order-independent integer sum, one atomic per warp for the whole kernel
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) n_owned += __shfl_xor_sync(0xffffffffu, n_owned, o);
-  if ((threadIdx.x & 31) == 0 && n_owned) atomicAdd(reinterpret_cast<unsigned long long*>(counts + 1), (unsigned long long)n_owned);
 }
 
 struct McEmit {
@@ -422,39 +404,55 @@ __global__ void make_grid_kernel(float* __restrict__ out, float bx, float by, fl
   out[idx * 3 + 2] = __fadd_rn(__fmul_rn(lin(k, rz), lz), bz);
 }
 
-// vol[flag] = vals (in order); vol[~flag] = fill (in order)   main.py:357,362-364. One pass: the flag count of each block is
-// chained through the look-back scan, so the flags are read once and there is no separate count / scan launch.
-__global__ void __launch_bounds__(MC_NT) scatter_fill_kernel(const uint8_t* __restrict__ flag, int64_t n, LookbackState L,
-                                                             const float* __restrict__ vals, const float* __restrict__ fill,
-                                                             float* __restrict__ out) {
-  const int bid = lookback_ticket(L);
-  constexpr int EPT = MC_VPT * MC_QPT;                         // 16 consecutive flags per thread: one 16-byte load
-  const int64_t v0 = ((int64_t)bid * MC_NT + threadIdx.x) * EPT;
-  int c = 0; unsigned int f = 0;
-  if (v0 + EPT <= n && (reinterpret_cast<uintptr_t>(flag) & 15) == 0) {
-    const uint4 w = *reinterpret_cast<const uint4*>(flag + v0);
+// vol[flag] = vals (in order); vol[~flag] = fill (in order)   main.py:357,362-364. Same scheme as marching cubes: per-chunk flag counts,
+// then every block sums the counts of the chunks before it (no chained scan) and scatters; 16 flags per thread from one 16-byte load.
+constexpr int SC_EPT = MC_VPT * MC_QPT;
+__device__ __forceinline__ unsigned int load_flags16(const uint8_t* __restrict__ flag, int64_t v0, int64_t n) {
+  unsigned int f = 0;
+  if (v0 + SC_EPT <= n && (reinterpret_cast<uintptr_t>(flag) & 15) == 0) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(flag + v0));
     const unsigned int ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-    for (int q = 0; q < EPT; ++q) f |= ((ws[q >> 2] >> (8 * (q & 3))) & 0xffu) ? (1u << q) : 0u;
+    for (int q = 0; q < SC_EPT; ++q) f |= ((ws[q >> 2] >> (8 * (q & 3))) & 0xffu) ? (1u << q) : 0u;
   } else {
 #pragma unroll
-    for (int q = 0; q < EPT; ++q) f |= ((v0 + q < n) && flag[v0 + q]) ? (1u << q) : 0u;
+    for (int q = 0; q < SC_EPT; ++q) f |= ((v0 + q < n) && flag[v0 + q]) ? (1u << q) : 0u;
   }
-  c = __popc(f);
-  unsigned long long tot;
-  const unsigned long long mine = block_excl_scan64((unsigned long long)c, &tot);
-  int64_t p = (int64_t)(lookback_prefix(L, bid, tot) + mine);
+  return f;
+}
+__global__ void __launch_bounds__(MC_NT) flag_count_kernel(const uint8_t* __restrict__ flag, int64_t n, unsigned long long* __restrict__ chunk) {
+  __shared__ int s_c[MC_NT / 32];
+  int c = __popc(load_flags16(flag, ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * SC_EPT, n));
 #pragma unroll
-  for (int q = 0; q < EPT; ++q) {
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < MC_NT / 32; ++w) c += s_c[w];
+    chunk[2 * blockIdx.x] = (unsigned long long)c; chunk[2 * blockIdx.x + 1] = 0ull;
+  }
+}
+__global__ void __launch_bounds__(MC_NT) scatter_fill_kernel(const uint8_t* __restrict__ flag, int64_t n, const unsigned long long* __restrict__ chunk,
+                                                             const float* __restrict__ vals, const float* __restrict__ fill,
+                                                             float* __restrict__ out) {
+  unsigned long long base, unused; sum_chunks(chunk, blockIdx.x, base, unused);
+  const int64_t v0 = ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * SC_EPT;
+  const unsigned int f = load_flags16(flag, v0, n);
+  unsigned long long tot;
+  const unsigned long long mine = block_excl_scan64((unsigned long long)__popc(f), &tot);
+  int64_t p = (int64_t)(base + mine);
+#pragma unroll
+  for (int q = 0; q < SC_EPT; ++q) {
     const int64_t v = v0 + q;
     if (v >= n) break;
     if ((f >> q) & 1) { out[v] = vals[p]; ++p; } else { out[v] = fill[v - p]; }
   }
 }
 
-// scratch layout of one scan: [0,64) counters (int64 x 4: scan vertices, owned vertices, triangles, -) | [64,128) ticket |
-// [128, 128 + 8*nblk) look-back state words | (256-aligned) vbase, 4 B per voxel
-struct McScratch { long long* counts; LookbackState L; int* vbase; size_t zero_bytes; };
+// scratch layout of one extraction: [0,64) counters (int64 x 4: scan vertices, owned vertices, triangles, -) | [64,128) unused |
+// [128, 128 + 16*nblk) chunk records | (256-aligned) vbase, 4 B per voxel
+struct McScratch { long long* counts; unsigned long long* chunk; int* vbase; };
 
 int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi, bool with_vbase, McDims* d, int* nblk, McScratch* S) {
   if (res[0] < 2 || res[1] < 2 || res[2] < 2) return avc_fail(ctx, AVC_EINVAL, "marching cubes needs res >= 2 per axis");
@@ -465,16 +463,14 @@ int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi
   // vertex / triangle prefixes travel as 31-bit fields of one look-back word: 3 edges and at most 5 triangles per voxel
   if (d->nvox * 5 >= ((int64_t)1 << 31)) return avc_fail(ctx, AVC_EINVAL, "volume too large for int32 mesh indices (%lld voxels)", (long long)d->nvox);
   *nblk = (int)((d->nvox + MC_VPB - 1) / MC_VPB);
-  size_t off = 128 + (size_t)*nblk * sizeof(unsigned long long); off = (off + 255) & ~(size_t)255;
+  size_t off = 128 + (size_t)*nblk * 2 * sizeof(unsigned long long); off = (off + 255) & ~(size_t)255;
   const size_t need = off + (with_vbase ? (size_t)d->nvox * sizeof(int) : 0) + 256;
   int rc = avc_ensure_scratch(ctx, need);
   if (rc) return rc;
   char* base = (char*)ctx->d_scratch;
   S->counts = (long long*)base;
-  S->L.ticket = (unsigned int*)(base + 64);
-  S->L.state = (unsigned long long*)(base + 128);
+  S->chunk = (unsigned long long*)(base + 128);
   S->vbase = with_vbase ? (int*)(base + off) : nullptr;
-  S->zero_bytes = 128 + (size_t)*nblk * sizeof(unsigned long long);
   return AVC_OK;
 }
 
@@ -499,12 +495,12 @@ extern "C" int avc_scatter_fill(avc_ctx* ctx, const uint8_t* flag, int64_t n_tot
   if (n_total == 0) return AVC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((n_total + MC_VPB - 1) / MC_VPB);
-  const size_t zero = 128 + (size_t)nblk * sizeof(unsigned long long);
-  int rc = avc_ensure_scratch(ctx, zero);
+  int rc = avc_ensure_scratch(ctx, 128 + (size_t)nblk * 2 * sizeof(unsigned long long));
   if (rc) return rc;
-  AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, zero, st));
-  LookbackState L; L.ticket = (unsigned int*)((char*)ctx->d_scratch + 64); L.state = (unsigned long long*)((char*)ctx->d_scratch + 128);
-  scatter_fill_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, L, vals, fill, out_vol);
+  unsigned long long* chunk = (unsigned long long*)((char*)ctx->d_scratch + 128);
+  flag_count_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, chunk);
+  AVC_LAUNCH_CHECK(ctx, "flag_count_kernel");
+  scatter_fill_kernel<<<nblk, MC_NT, 0, st>>>(flag, n_total, chunk, vals, fill, out_vol);
   AVC_LAUNCH_CHECK(ctx, "scatter_fill_kernel");
   return AVC_OK;
 }
@@ -522,9 +518,10 @@ extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], fl
   int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, false, &d, &nblk, &S);
   if (rc) return rc;
   d.vec4 = mc_vec4_ok(vol, res);
-  AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, S.zero_bytes, st));
-  mc_scan_kernel<<<nblk < ctx->sm_count * 4 ? nblk : ctx->sm_count * 4, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, nullptr, nullptr, nullptr, 0, 0);
-  AVC_LAUNCH_CHECK(ctx, "mc_scan_kernel(count)");
+  mc_count_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk);
+  AVC_LAUNCH_CHECK(ctx, "mc_count_kernel");
+  mc_total_kernel<<<1, MC_NT, 0, st>>>(S.chunk, nblk, S.counts);
+  AVC_LAUNCH_CHECK(ctx, "mc_total_kernel");
   AVC_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, S.counts, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   AVC_CUDA(ctx, cudaStreamSynchronize(st));
   *n_verts = ctx->h_counts[1]; *n_faces = ctx->h_counts[2];
@@ -557,10 +554,10 @@ static int mc_extract_async(avc_ctx* ctx, const float* vol, const int res[3], co
   }
   long long* d_edges = reinterpret_cast<long long*>(ctx->d_scratch2);
   long long* d_tris = d_edges + cap_v + 1;
-  AVC_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, S.zero_bytes, st));
-  mc_scan_kernel<<<nblk < ctx->sm_count * 4 ? nblk : ctx->sm_count * 4, MC_NT, 0, st>>>(vol, d, S.L, nblk, S.counts, S.vbase, d_edges, d_tris,
-                                                                                        (long long)cap_v, (long long)cap_f);
-  AVC_LAUNCH_CHECK(ctx, "mc_scan_kernel");
+  mc_count_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk);
+  AVC_LAUNCH_CHECK(ctx, "mc_count_kernel");
+  mc_emit_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk, nblk, S.counts, S.vbase, d_edges, d_tris, (long long)cap_v, (long long)cap_f);
+  AVC_LAUNCH_CHECK(ctx, "mc_emit_kernel");
   McEmit e;
   const int gres[3] = {gres_x, res[1], res[2]};
   for (int c = 0; c < 3; ++c) {

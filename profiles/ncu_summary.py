@@ -29,7 +29,7 @@ def main():
         st = sorted(((float(v[1] or 0), h[len(STALLS):].replace('_per_issue_active.ratio', '')) for h, v in d.items() if h.startswith(STALLS) and h.endswith('per_issue_active.ratio')), reverse=True)[:6]
         out.append('- top stalls (warps per issue): ' + ', '.join('%s %.2f' % (n, x) for x, n in st))
         if entry and 'dram__bytes_read.sum' in d:
-            name = d['Kernel Name'][1].split('(')[0].split('<')[0].split('::')[-1]
+            name = d['Kernel Name'][1].replace('void ', '').replace('<unnamed>::', '').split('(')[0].split('<')[0]
             rec = {'kernel': name, 'entry': entry, 'dram_bytes': int(to_bytes(d['dram__bytes_read.sum'][1], d['dram__bytes_read.sum'][0]) + to_bytes(d['dram__bytes_write.sum'][1], d['dram__bytes_write.sum'][0])),
                    'dram_read_bytes': int(to_bytes(d['dram__bytes_read.sum'][1], d['dram__bytes_read.sum'][0])), 'dram_write_bytes': int(to_bytes(d['dram__bytes_write.sum'][1], d['dram__bytes_write.sum'][0])),
                    'source': 'ncu --set full, ' + os.path.basename(rep)}
