@@ -243,20 +243,27 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const __grid_con
 constexpr int GN_PX = 128;
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int P, int C, int ld, int c_off, double* __restrict__ partial,
                                                        unsigned int* __restrict__ ticket, float* __restrict__ stats /*32 x {mean, rstd}*/) {
-  __shared__ float s_sum[256], s_sq[256];
+  __shared__ float s_sum[1024], s_sq[1024];           // [thread][j]: the 4 channels a thread owns
   __shared__ bool s_last;
-  const int tid = threadIdx.x, c = tid % C, per_px = 256 / C;      // threads per pixel row chunk
+  const int tid = threadIdx.x, C4 = C / 4, c4 = tid % C4, rows = 256 / C4;    // a pixel's C channels are C/4 float4 loads; `rows` pixels per sweep
   const int p0 = blockIdx.x * GN_PX, p1 = min(P, p0 + GN_PX);
-  float sum = 0.f, sq = 0.f;
-  for (int p = p0 + tid / C; p < p1; p += per_px) { const float v = x[(size_t)p * ld + c_off + c]; sum += v; sq = fmaf(v, v, sq); }
-  s_sum[tid] = sum; s_sq[tid] = sq;
+  float sum[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* base = x + c_off + 4 * c4;
+#pragma unroll 4
+  for (int p = p0 + tid / C4; p < p1; p += rows) {       // independent 16-byte loads, four in flight per thread
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * ld));
+    sum[0] += v.x; sum[1] += v.y; sum[2] += v.z; sum[3] += v.w;
+    sq[0] = fmaf(v.x, v.x, sq[0]); sq[1] = fmaf(v.y, v.y, sq[1]); sq[2] = fmaf(v.z, v.z, sq[2]); sq[3] = fmaf(v.w, v.w, sq[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { s_sum[4 * tid + j] = sum[j]; s_sq[4 * tid + j] = sq[j]; }
   __syncthreads();
   if (tid < 32) {
-    // group g = channels [g*cg, (g+1)*cg); the threads holding them: t with (t % C) / cg == g
+    // group g = channels [g*cg, (g+1)*cg); entry (t, j) holds channel 4*(t % C4) + j: fold the 32 entries of the group in a fixed order
     const int cg = C / 32;
     double a = 0.0, b = 0.0;
-    for (int r = 0; r < per_px; ++r)
-      for (int j = 0; j < cg; ++j) { const int t = r * C + tid * cg + j; a += (double)s_sum[t]; b += (double)s_sq[t]; }
+    for (int r = 0; r < rows; ++r)
+      for (int k = 0; k < cg; ++k) { const int ch = tid * cg + k; const int e = 4 * (r * C4 + ch / 4) + (ch & 3); a += (double)s_sum[e]; b += (double)s_sq[e]; }
     partial[((size_t)blockIdx.x * 32 + tid) * 2] = a; partial[((size_t)blockIdx.x * 32 + tid) * 2 + 1] = b;
   }
   __threadfence();
@@ -265,12 +272,21 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (tid < 32) {
+  {
+    // the last block folds the per-block partials: 8 threads per group take interleaved blocks, then a fixed-order fold of the 8
+    __shared__ double s_a[256], s_b[256];
+    const int g = tid & 31, part = tid >> 5;
     double a = 0.0, b = 0.0;
-    for (unsigned int blk = 0; blk < gridDim.x; ++blk) { a += partial[((size_t)blk * 32 + tid) * 2]; b += partial[((size_t)blk * 32 + tid) * 2 + 1]; }
-    const double cnt = (double)P * (double)(C / 32);
-    const double mean = a / cnt, var = fmax(b / cnt - mean * mean, 0.0);
-    stats[2 * tid] = (float)mean; stats[2 * tid + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    for (unsigned int blk = part; blk < gridDim.x; blk += 8) { a += partial[((size_t)blk * 32 + g) * 2]; b += partial[((size_t)blk * 32 + g) * 2 + 1]; }
+    s_a[tid] = a; s_b[tid] = b;
+    __syncthreads();
+    if (tid < 32) {
+      a = 0.0; b = 0.0;
+      for (int q = 0; q < 8; ++q) { a += s_a[q * 32 + tid]; b += s_b[q * 32 + tid]; }
+      const double cnt = (double)P * (double)(C / 32);
+      const double mean = a / cnt, var = fmax(b / cnt - mean * mean, 0.0);
+      stats[2 * tid] = (float)mean; stats[2 * tid + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
   }
   if (tid == 0) *ticket = 0;
 }
@@ -375,7 +391,7 @@ __global__ void __launch_bounds__(256) bicubic_up2_add_kernel(const float* __res
 __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ in, const float* __restrict__ w /*(64,6,7,7)*/, const float* __restrict__ bias,
                                                       float* __restrict__ out, int Hin, int Win) {
   __shared__ float s_in[6][37][38];          // 16*2 + 5 = 37 input rows / columns per block
-  __shared__ float s_w[8][6 * 49];
+  __shared__ float4 s_w[6 * 49][2];         // [tap][8 output channels]: two 16-byte broadcast loads per tap
   const int Ho = Hin / 2, Wo = Win / 2;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int ox0 = blockIdx.x * 16, oy0 = blockIdx.y * 16;
@@ -387,7 +403,7 @@ __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ 
   const int ox = ox0 + tx, oy = oy0 + ty;
   for (int cg = 0; cg < 8; ++cg) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 8 * 294; i += 256) s_w[i / 294][i % 294] = w[(size_t)(cg * 8 + i / 294) * 294 + i % 294];
+    for (int i = threadIdx.x; i < 8 * 294; i += 256) reinterpret_cast<float*>(s_w)[(i % 294) * 8 + i / 294] = w[(size_t)(cg * 8 + i / 294) * 294 + i % 294];
     __syncthreads();
     float acc[8];
 #pragma unroll
@@ -398,8 +414,9 @@ __global__ void __launch_bounds__(256) stem7x7_kernel(const float* __restrict__ 
         for (int kx = 0; kx < 7; ++kx) {
           const float v = s_in[ci][2 * ty + ky][2 * tx + kx];
           const int wi = ci * 49 + ky * 7 + kx;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, s_w[j][wi], acc[j]);
+          const float4 w0 = s_w[wi][0], w1 = s_w[wi][1];
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
         }
     if (ox < Wo && oy < Ho) {
       float* d = out + ((size_t)oy * Wo + ox) * 64 + cg * 8;

@@ -109,10 +109,11 @@ __device__ __forceinline__ void classify4(const float* __restrict__ vol, const M
                    ((int)C[q + 1] << 6) | ((int)E[q + 1] << 7);
   }
 }
-// classification of a thread's 4 voxels by either path
+// classification of a thread's 4 voxels by either path (a compile-time choice: both inlined four times made the kernels instruction-fetch bound)
+template <bool VEC4>
 __device__ __forceinline__ void classify_thread(const float* __restrict__ vol, const McDims& d, int64_t v0, Vox4& r) {
   Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
-  if (d.vec4) { classify4(vol, d, v0, c, r); return; }
+  if (VEC4) { classify4(vol, d, v0, c, r); return; }
   r.in_scan = false; r.owned = false; r.own_mask = 0;
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
@@ -160,31 +161,49 @@ __device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long lo
 // a single fused pass with a decoupled look-back scan ran 190-300 us, persistent or not, 1 024 or 4 096 voxels per block -- top stall
 // `barrier`: with ~600 chunks in flight none of the predecessors inside a chunk's look-back window has its inclusive prefix yet, so
 // every chunk walks back through all of them, one L2 round trip per 32. Independent blocks + a redundant 64 KB sum have no chain at all.
-struct ThreadCls { unsigned long long info[MC_QPT]; int nv, nvo, nt; };     // per voxel q of quad s: bits [12q, 12q+3) cut flags, [12q+3, 12q+12) case + 1
+// Voxel assignment inside a chunk: quad (s, t) = 4 consecutive voxels starting at ((chunk*4 + s)*256 + t)*4 -- for a fixed s the 256
+// threads of the block cover 4 KB contiguously, so every load instruction of a warp is one 512-byte segment (the first version gave a
+// thread 16 consecutive voxels: 64-byte lane stride, 16 cache lines per load instruction, and the pass was L1-wavefront bound).
+// The canonical vertex order (voxel linear index) is therefore (s, t) lexicographic.
+struct ThreadCls { unsigned long long info[MC_QPT]; };     // per voxel q of quad s: bits [12q, 12q+3) cut flags, [12q+3, 12q+12) case + 1
 
-__device__ __forceinline__ void classify16(const float* __restrict__ vol, const McDims& d, int64_t t0, const unsigned char* s_ntri, ThreadCls& T) {
-  T.nv = T.nvo = T.nt = 0;
+__device__ __forceinline__ int64_t quad_start(int bid, int s) { return (((int64_t)bid * MC_QPT + s) * MC_NT + threadIdx.x) * MC_VPT; }
+
+template <bool VEC4>
+__device__ __forceinline__ void classify16(const float* __restrict__ vol, const McDims& d, int bid, ThreadCls& T, int& nvo) {
+  nvo = 0;
 #pragma unroll
   for (int s = 0; s < MC_QPT; ++s) {
-    Vox4 r; classify_thread(vol, d, t0 + s * MC_VPT, r);
+    Vox4 r; classify_thread<VEC4>(vol, d, quad_start(bid, s), r);
     unsigned long long w = 0;
 #pragma unroll
     for (int q = 0; q < MC_VPT; ++q) {
-      const int c = __popc(r.cut[q]); T.nv += c;
-      if ((r.own_mask >> q) & 1) T.nvo += c;
-      if (r.ccase[q] >= 0) T.nt += s_ntri[r.ccase[q]];
+      if ((r.own_mask >> q) & 1) nvo += __popc(r.cut[q]);
       w |= (unsigned long long)((unsigned int)r.cut[q] | ((unsigned int)(r.ccase[q] + 1) << 3)) << (12 * q);
     }
     T.info[s] = w;
   }
 }
+// vertices << 31 | triangles of one quad (a rolled loop over the 4 voxels: this code is on the instruction-fetch path of 4 096 blocks)
+__device__ __forceinline__ unsigned long long quad_counts(unsigned long long info, const unsigned char* s_ntri) {
+  unsigned long long c = 0;
+#pragma unroll 1
+  for (int q = 0; q < MC_VPT; ++q) {
+    const unsigned int wq = (unsigned int)(info >> (12 * q)) & 0xfffu;
+    c += ((unsigned long long)__popc(wq & 7u) << 31) + (unsigned long long)((wq >> 3) ? s_ntri[(wq >> 3) - 1] : 0);
+  }
+  return c;
+}
 
+template <bool VEC4>
 __global__ void __launch_bounds__(MC_NT, 4) mc_count_kernel(const float* __restrict__ vol, McDims d, unsigned long long* __restrict__ chunk) {
   __shared__ unsigned char s_ntri[256];
   __shared__ unsigned long long s_a[MC_NT / 32], s_b[MC_NT / 32];
   stage_ntri(s_ntri);
-  ThreadCls T; classify16(vol, d, ((int64_t)blockIdx.x * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT), s_ntri, T);
-  unsigned long long a = ((unsigned long long)T.nv << 31) | (unsigned long long)T.nt, b = (unsigned long long)T.nvo;
+  ThreadCls T; int nvo; classify16<VEC4>(vol, d, blockIdx.x, T, nvo);
+  unsigned long long a = 0, b = (unsigned long long)nvo;
+#pragma unroll 1
+  for (int s = 0; s < MC_QPT; ++s) if (T.info[s]) a += quad_counts(T.info[s], s_ntri);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
   if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
@@ -217,48 +236,66 @@ __global__ void __launch_bounds__(MC_NT) mc_total_kernel(const unsigned long lon
   if (threadIdx.x == 0) { counts[0] = (long long)(a >> 31); counts[1] = (long long)b; counts[2] = (long long)(a & 0x7fffffffull); }
 }
 
+template <bool VEC4>
 __global__ void __launch_bounds__(MC_NT, 4) mc_emit_kernel(const float* __restrict__ vol, McDims d, const unsigned long long* __restrict__ chunk, int nblk,
                                                            long long* __restrict__ counts, int* __restrict__ vbase, long long* __restrict__ edges,
                                                            long long* __restrict__ tris, long long cap_e, long long cap_t) {
   __shared__ unsigned char s_ntri[256];
+  __shared__ unsigned long long s_w[MC_QPT][MC_NT / 32];        // warp totals per sub-chunk
   stage_ntri(s_ntri);
-  const int bid = blockIdx.x;
+  const int bid = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned long long base, owned_before; sum_chunks(chunk, bid, base, owned_before);
-  const int64_t t0 = ((int64_t)bid * MC_NT + threadIdx.x) * (MC_VPT * MC_QPT);     // first of this thread's 16 consecutive voxels
-  ThreadCls T; classify16(vol, d, t0, s_ntri, T);
-  unsigned long long tot;
-  const unsigned long long mine = block_excl_scan64(((unsigned long long)T.nv << 31) | (unsigned long long)T.nt, &tot);
-  const unsigned long long pre = base + mine;
-  if (bid == nblk - 1 && threadIdx.x == 0) {                    // the last chunk publishes the totals
-    const unsigned long long all = base + tot;
-    const ulonglong2 last = __ldg(reinterpret_cast<const ulonglong2*>(chunk) + bid);
-    counts[0] = (long long)(all >> 31); counts[1] = (long long)(owned_before + last.y); counts[2] = (long long)(all & 0x7fffffffull);
-  }
-  int p = (int)(pre >> 31), tb = (int)(pre & 0x7fffffffull);
+  ThreadCls T; int nvo; classify16<VEC4>(vol, d, bid, T, nvo);
+  // exclusive prefix of quad (s, t) in (s, t) order: warp scans per sub-chunk + one exchange of the warp totals
+  unsigned long long cnt[MC_QPT], pre[MC_QPT];
 #pragma unroll
   for (int s = 0; s < MC_QPT; ++s) {
-    const int64_t v0 = t0 + s * MC_VPT;
+    cnt[s] = T.info[s] ? quad_counts(T.info[s], s_ntri) : 0ull;
+    unsigned long long inc = cnt[s];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    pre[s] = inc - cnt[s];
+    if (lane == 31) s_w[s][wid] = inc;
+  }
+  __syncthreads();
+  unsigned long long run = base;
+#pragma unroll
+  for (int s = 0; s < MC_QPT; ++s) {
+    unsigned long long below = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < MC_NT / 32; ++w) { const unsigned long long x = s_w[s][w]; if (w < wid) below += x; tot += x; }
+    pre[s] += run + below;
+    run += tot;
+  }
+  if (bid == nblk - 1 && threadIdx.x == 0) {                    // the last chunk publishes the totals
+    const ulonglong2 last = __ldg(reinterpret_cast<const ulonglong2*>(chunk) + bid);
+    counts[0] = (long long)(run >> 31); counts[1] = (long long)(owned_before + last.y); counts[2] = (long long)(run & 0x7fffffffull);
+  }
+#pragma unroll 1
+  for (int s = 0; s < MC_QPT; ++s) {
+    const int64_t v0 = quad_start(bid, s);
+    const unsigned long long info = T.info[s];
+    int p = (int)(pre[s] >> 31), tb = (int)(pre[s] & 0x7fffffffull);
     int cq[MC_VPT];
 #pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) cq[q] = __popc((unsigned int)(T.info[s] >> (12 * q)) & 7u);
-    if (d.vec4 && v0 < d.nvox) {
-      *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + cq[0], p + cq[0] + cq[1], p + cq[0] + cq[1] + cq[2]);
+    for (int q = 0; q < MC_VPT; ++q) cq[q] = __popc((unsigned int)(info >> (12 * q)) & 7u);
+    if (VEC4) {
+      if (v0 < d.nvox) *reinterpret_cast<int4*>(vbase + v0) = make_int4(p, p + cq[0], p + cq[0] + cq[1], p + cq[0] + cq[1] + cq[2]);
     } else {
       int pp = p;
 #pragma unroll
       for (int q = 0; q < MC_VPT; ++q) { if (v0 + q < d.nvox) vbase[v0 + q] = pp; pp += cq[q]; }
     }
-    if (T.info[s]) {
+    if (!info) continue;
+#pragma unroll 1
+    for (int q = 0; q < MC_VPT; ++q) {
+      const unsigned int wq = (unsigned int)(info >> (12 * q)) & 0xfffu;
+      const int cut = (int)(wq & 7u), cc = (int)(wq >> 3) - 1;
 #pragma unroll
-      for (int q = 0; q < MC_VPT; ++q) {
-        const unsigned int wq = (unsigned int)(T.info[s] >> (12 * q)) & 0xfffu;
-        const int cut = (int)(wq & 7u), cc = (int)(wq >> 3) - 1;
-#pragma unroll
-        for (int ax = 0; ax < 3; ++ax) if ((cut >> ax) & 1) { if (p < cap_e) edges[p] = (long long)(v0 + q) * 4 + ax; ++p; }
-        if (cc >= 0) {
-          const int ntri = s_ntri[cc];
-          for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)cc << 3) | tix;
-        }
+      for (int ax = 0; ax < 3; ++ax) if ((cut >> ax) & 1) { if (p < cap_e) edges[p] = (long long)(v0 + q) * 4 + ax; ++p; }
+      if (cc >= 0) {
+        const int ntri = s_ntri[cc];
+        for (int tix = 0; tix < ntri; ++tix, ++tb) if (tb < cap_t) tris[tb] = ((long long)(v0 + q) << 11) | ((long long)cc << 3) | tix;
       }
     }
   }
@@ -518,7 +555,7 @@ extern "C" int avc_mc_count(avc_ctx* ctx, const float* vol, const int res[3], fl
   int rc = mc_setup(ctx, res, iso, x_halo_lo, x_halo_hi, false, &d, &nblk, &S);
   if (rc) return rc;
   d.vec4 = mc_vec4_ok(vol, res);
-  mc_count_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk);
+  if (d.vec4) mc_count_kernel<true><<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk); else mc_count_kernel<false><<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk);
   AVC_LAUNCH_CHECK(ctx, "mc_count_kernel");
   mc_total_kernel<<<1, MC_NT, 0, st>>>(S.chunk, nblk, S.counts);
   AVC_LAUNCH_CHECK(ctx, "mc_total_kernel");
@@ -554,9 +591,10 @@ static int mc_extract_async(avc_ctx* ctx, const float* vol, const int res[3], co
   }
   long long* d_edges = reinterpret_cast<long long*>(ctx->d_scratch2);
   long long* d_tris = d_edges + cap_v + 1;
-  mc_count_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk);
+  if (d.vec4) mc_count_kernel<true><<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk); else mc_count_kernel<false><<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk);
   AVC_LAUNCH_CHECK(ctx, "mc_count_kernel");
-  mc_emit_kernel<<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk, nblk, S.counts, S.vbase, d_edges, d_tris, (long long)cap_v, (long long)cap_f);
+  if (d.vec4) mc_emit_kernel<true><<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk, nblk, S.counts, S.vbase, d_edges, d_tris, (long long)cap_v, (long long)cap_f);
+  else mc_emit_kernel<false><<<nblk, MC_NT, 0, st>>>(vol, d, S.chunk, nblk, S.counts, S.vbase, d_edges, d_tris, (long long)cap_v, (long long)cap_f);
   AVC_LAUNCH_CHECK(ctx, "mc_emit_kernel");
   McEmit e;
   const int gres[3] = {gres_x, res[1], res[2]};
