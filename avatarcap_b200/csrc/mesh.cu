@@ -78,35 +78,35 @@ __device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const
 // the same for a thread's MC_VPT = 4 consecutive voxels when they are one aligned float4 of a single z-row (d.vec4): 4 rows x
 // (float4 + the next element) instead of up to 8 scalar loads per voxel
 struct Vox4 { int cut[MC_VPT]; int ccase[MC_VPT]; bool in_scan, owned; int own_mask; /* bit q: voxel q lies in an owned plane */ };
-__device__ __forceinline__ void load_row5(const float* __restrict__ p, bool more, float iso, bool b[5]) {
-  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-  b[0] = v.x > iso; b[1] = v.y > iso; b[2] = v.z > iso; b[3] = v.w > iso;
-  b[4] = more ? (__ldg(p + 4) > iso) : false;
-}
+// BRANCH-FREE: the eight loads of a quad are issued back to back from clamped addresses (a missing neighbour re-reads the quad itself
+// and its bits are masked out), so that the compiler can hoist the loads of all of a thread's quads above the first compare. The first
+// version guarded every row with an `if` and compared right behind each load: 32 dependent memory round trips per thread, and the
+// count / emit passes sat at 80 / 158 us (long_scoreboard) whatever the launch geometry.
 __device__ __forceinline__ void classify4(const float* __restrict__ vol, const McDims& d, int64_t v0, const Vox3& c, Vox4& r) {
-  r.in_scan = false; r.owned = false; r.own_mask = 0;
-#pragma unroll
-  for (int q = 0; q < MC_VPT; ++q) { r.cut[q] = 0; r.ccase[q] = -1; }
-  if (v0 >= d.nvox) return;
-  if (c.i < d.lo || c.i >= d.scan_end) return;
-  r.in_scan = true; r.owned = c.i < d.hi_excl; r.own_mask = r.owned ? 15 : 0;
+  const bool live = v0 < d.nvox && c.i >= d.lo && c.i < d.scan_end;
+  r.in_scan = live; r.owned = live && c.i < d.hi_excl; r.own_mask = r.owned ? 15 : 0;
   const int64_t sx = (int64_t)d.ry * d.rz, sy = d.rz;
-  const bool hx = c.i + 1 < d.rx, hy = c.j + 1 < d.ry, hz3 = c.k + 4 < d.rz;       // voxels q < 3 always have a +z neighbour in the row
-  bool A[5], B[5], C[5], E[5];
-  load_row5(vol + v0, hz3, d.iso, A);
-#pragma unroll
-  for (int q = 0; q < 5; ++q) { B[q] = false; C[q] = false; E[q] = false; }
-  if (hx) load_row5(vol + v0 + sx, hz3, d.iso, B);
-  if (hy) load_row5(vol + v0 + sy, hz3, d.iso, C);
+  const bool hx = live && c.i + 1 < d.rx, hy = live && c.j + 1 < d.ry, hz3 = c.k + 4 < d.rz;       // voxels q < 3 always have a +z neighbour in the row
+  const float* pa = vol + (v0 < d.nvox ? v0 : 0);
+  const float* pb = hx ? pa + sx : pa; const float* pc = hy ? pa + sy : pa; const float* pe = (hx && hy) ? pa + sx + sy : pa;
+  const int o4 = hz3 ? 4 : 0;
+  const float4 A = __ldg(reinterpret_cast<const float4*>(pa)), B = __ldg(reinterpret_cast<const float4*>(pb));
+  const float4 C = __ldg(reinterpret_cast<const float4*>(pc)), E = __ldg(reinterpret_cast<const float4*>(pe));
+  const float a4 = __ldg(pa + o4), b4 = __ldg(pb + o4), c4 = __ldg(pc + o4), e4 = __ldg(pe + o4);
+  const float iso = d.iso;
+  // 5-bit inside masks of the four rows (bit q = value q of the row > iso)
+  const unsigned int mA = (A.x > iso) | ((A.y > iso) << 1) | ((A.z > iso) << 2) | ((A.w > iso) << 3) | ((a4 > iso) << 4);
+  const unsigned int mB = (B.x > iso) | ((B.y > iso) << 1) | ((B.z > iso) << 2) | ((B.w > iso) << 3) | ((b4 > iso) << 4);
+  const unsigned int mC = (C.x > iso) | ((C.y > iso) << 1) | ((C.z > iso) << 2) | ((C.w > iso) << 3) | ((c4 > iso) << 4);
+  const unsigned int mE = (E.x > iso) | ((E.y > iso) << 1) | ((E.z > iso) << 2) | ((E.w > iso) << 3) | ((e4 > iso) << 4);
+  const unsigned int cx = hx ? (mA ^ mB) : 0u, cy = hy ? (mA ^ mC) : 0u, cz = live ? (mA ^ (mA >> 1)) & (hz3 ? 15u : 7u) : 0u;
   const bool cells = r.owned && hx && hy;
-  if (cells) load_row5(vol + v0 + sx + sy, hz3, d.iso, E);
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
-    const bool hz = q < 3 || hz3;
-    r.cut[q] = ((hx && B[q] != A[q]) ? 1 : 0) | ((hy && C[q] != A[q]) ? 2 : 0) | ((hz && A[q + 1] != A[q]) ? 4 : 0);
-    if (cells && hz)
-      r.ccase[q] = (int)A[q] | ((int)B[q] << 1) | ((int)C[q] << 2) | ((int)E[q] << 3) | ((int)A[q + 1] << 4) | ((int)B[q + 1] << 5) |
-                   ((int)C[q + 1] << 6) | ((int)E[q + 1] << 7);
+    r.cut[q] = (int)(((cx >> q) & 1u) | (((cy >> q) & 1u) << 1) | (((cz >> q) & 1u) << 2));
+    const unsigned int a = (mA >> q) & 3u, b = (mB >> q) & 3u, cc = (mC >> q) & 3u, e = (mE >> q) & 3u;
+    const int cs = (int)((a & 1u) | ((b & 1u) << 1) | ((cc & 1u) << 2) | ((e & 1u) << 3) | ((a >> 1) << 4) | ((b >> 1) << 5) | ((cc >> 1) << 6) | ((e >> 1) << 7));
+    r.ccase[q] = (cells && (q < 3 || hz3)) ? cs : -1;
   }
 }
 // classification of a thread's 4 voxels by either path (a compile-time choice: both inlined four times made the kernels instruction-fetch bound)
