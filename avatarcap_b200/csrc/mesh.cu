@@ -77,7 +77,8 @@ __device__ __forceinline__ VoxInfo classify(const float* __restrict__ vol, const
 
 // the same for a thread's MC_VPT = 4 consecutive voxels when they are one aligned float4 of a single z-row (d.vec4): 4 rows x
 // (float4 + the next element) instead of up to 8 scalar loads per voxel
-struct Vox4 { int cut[MC_VPT]; int ccase[MC_VPT]; bool in_scan, owned; int own_mask; /* bit q: voxel q lies in an owned plane */ };
+struct Vox4 { int cut[MC_VPT]; int ccase[MC_VPT]; bool in_scan, owned; int own_mask; /* bit q: voxel q lies in an owned plane */
+              bool any; /* false: no cut edge and no triangle in the quad (the common case away from the surface): cut = 0, ccase = -1 */ };
 // BRANCH-FREE: the eight loads of a quad are issued back to back from clamped addresses (a missing neighbour re-reads the quad itself
 // and its bits are masked out), so that the compiler can hoist the loads of all of a thread's quads above the first compare. The first
 // version guarded every row with an `if` and compared right behind each load: 32 dependent memory round trips per thread, and the
@@ -99,6 +100,14 @@ __device__ __forceinline__ void classify4(const float* __restrict__ vol, const M
   const unsigned int mB = (B.x > iso) | ((B.y > iso) << 1) | ((B.z > iso) << 2) | ((B.w > iso) << 3) | ((b4 > iso) << 4);
   const unsigned int mC = (C.x > iso) | ((C.y > iso) << 1) | ((C.z > iso) << 2) | ((C.w > iso) << 3) | ((c4 > iso) << 4);
   const unsigned int mE = (E.x > iso) | ((E.y > iso) << 1) | ((E.z > iso) << 2) | ((E.w > iso) << 3) | ((e4 > iso) << 4);
+  // all 20 values on one side of the iso level (19 of 20 quads of a body volume): nothing to emit, skip the per-voxel work --
+  // after the loads had been un-chained these passes were issue bound (top stall not_selected)
+  r.any = live && !(((mA | mB | mC | mE) == 0u) || ((mA & mB & mC & mE) == 31u));
+  if (!r.any) {
+#pragma unroll
+    for (int q = 0; q < MC_VPT; ++q) { r.cut[q] = 0; r.ccase[q] = -1; }
+    return;
+  }
   const unsigned int cx = hx ? (mA ^ mB) : 0u, cy = hy ? (mA ^ mC) : 0u, cz = live ? (mA ^ (mA >> 1)) & (hz3 ? 15u : 7u) : 0u;
   const bool cells = r.owned && hx && hy;
 #pragma unroll
@@ -114,7 +123,7 @@ template <bool VEC4>
 __device__ __forceinline__ void classify_thread(const float* __restrict__ vol, const McDims& d, int64_t v0, Vox4& r) {
   Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
   if (VEC4) { classify4(vol, d, v0, c, r); return; }
-  r.in_scan = false; r.owned = false; r.own_mask = 0;
+  r.in_scan = false; r.owned = false; r.own_mask = 0; r.any = true;
 #pragma unroll
   for (int q = 0; q < MC_VPT; ++q) {
     const VoxInfo x = classify(vol, d, v0 + q, c);
@@ -176,10 +185,12 @@ __device__ __forceinline__ void classify16(const float* __restrict__ vol, const 
   for (int s = 0; s < MC_QPT; ++s) {
     Vox4 r; classify_thread<VEC4>(vol, d, quad_start(bid, s), r);
     unsigned long long w = 0;
+    if (r.any) {
 #pragma unroll
-    for (int q = 0; q < MC_VPT; ++q) {
-      if ((r.own_mask >> q) & 1) nvo += __popc(r.cut[q]);
-      w |= (unsigned long long)((unsigned int)r.cut[q] | ((unsigned int)(r.ccase[q] + 1) << 3)) << (12 * q);
+      for (int q = 0; q < MC_VPT; ++q) {
+        if ((r.own_mask >> q) & 1) nvo += __popc(r.cut[q]);
+        w |= (unsigned long long)((unsigned int)r.cut[q] | ((unsigned int)(r.ccase[q] + 1) << 3)) << (12 * q);
+      }
     }
     T.info[s] = w;
   }
