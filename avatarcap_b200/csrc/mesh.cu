@@ -363,39 +363,42 @@ __global__ void __launch_bounds__(128) mc_verts_kernel(const float* __restrict__
   }
   e.verts[vid * 3 + 0] = p[0]; e.verts[vid * 3 + 1] = p[1]; e.verts[vid * 3 + 2] = p[2];
   if (!e.normals) continue;
-  // trilinear sample of the Sobel gradient volume: 8 corners, each a 3x3x3 stencil -> a 4x4x4 block of voxels
+  // Trilinear sample of the Sobel gradient volume (recon_util.py:9-48): 8 corners x a 3x3x3 stencil = a 4x4x4 block of voxels. Both the
+  // interpolation and the Sobel kernels are separable, so the 8 x 27 taps collapse into per-axis 4-tap filters: with the interpolation
+  // weights u = (1 - f, f) (the +1 tap weighs 0 beyond the last plane: border clip), smoothing taps S = u * [1 2 1] and derivative
+  // taps D = u * [-1 0 1],   grad_x = sum blk[a][b][c] Dx[a] Sy[b] Sz[c]   (and cyclically) -- 188 FMAs instead of ~650, and the 64
+  // loads are consumed row by row instead of living in registers. (The summation order differs from the reference's conv3d +
+  // grid_sample; the tests hold the normalised result to 2e-4 of the oracle and 5e-4 of the reference's golden.)
   const int x0 = (int)floorf(g[0]), y0 = (int)floorf(g[1]), z0 = (int)floorf(g[2]);
-  const float fx = g[0] - (float)x0, fy = g[1] - (float)y0, fz = g[2] - (float)z0;
-  float blk4[4][4][4];
+  float S[3][4], D[3][4];
+  {
+    const int i0[3] = {x0, y0, z0};
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int c = 0; c < 3; ++c) {
+      const float f = g[c] - (float)i0[c];
+      const float u0 = 1.f - f, u1 = (i0[c] + 1 <= e.gres[c] - 1) ? f : 0.f;
+      S[c][0] = u0; S[c][1] = 2.f * u0 + u1; S[c][2] = u0 + 2.f * u1; S[c][3] = u1;
+      D[c][0] = -u0; D[c][1] = -u1; D[c][2] = u0; D[c][3] = u1;
+    }
+  }
+  float gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+  for (int a = 0; a < 4; ++a) {
+    float uss = 0.f, uds = 0.f, usd = 0.f;                         // over (b, c): S_y S_z, D_y S_z, S_y D_z
 #pragma unroll
-      for (int c = 0; c < 4; ++c) blk4[a][b][c] = vol_at(vol, d, e, x0 - 1 + a - e.x_origin, y0 - 1 + b, z0 - 1 + c);
-  float n[3] = {0.f, 0.f, 0.f};
+    for (int b = 0; b < 4; ++b) {
+      float ts = 0.f, td = 0.f;
 #pragma unroll
-  for (int dx = 0; dx < 2; ++dx)
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dz = 0; dz < 2; ++dz) {
-        // corner (x0+dx, y0+dy, z0+dz); taps beyond the last plane have weight 0 (border clip)
-        const bool ok = (x0 + dx <= e.gres[0] - 1) && (y0 + dy <= e.gres[1] - 1) && (z0 + dz <= e.gres[2] - 1);
-        const float w = (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) * (dz ? fz : 1.f - fz);
-        if (!ok) continue;
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            const float sw = (float)((a == 1 ? 2 : 1) * (b == 1 ? 2 : 1));
-            gx += sw * (blk4[dx + 2][dy + a][dz + b] - blk4[dx][dy + a][dz + b]);
-            gy += sw * (blk4[dx + a][dy + 2][dz + b] - blk4[dx + a][dy][dz + b]);
-            gz += sw * (blk4[dx + a][dy + b][dz + 2] - blk4[dx + a][dy + b][dz]);
-          }
-        n[0] += w * (gx / (32.f * e.vox[0])); n[1] += w * (gy / (32.f * e.vox[1])); n[2] += w * (gz / (32.f * e.vox[2]));
+      for (int c = 0; c < 4; ++c) {
+        const float v = vol_at(vol, d, e, x0 - 1 + a - e.x_origin, y0 - 1 + b, z0 - 1 + c);
+        ts = fmaf(v, S[2][c], ts); td = fmaf(v, D[2][c], td);
       }
+      uss = fmaf(ts, S[1][b], uss); uds = fmaf(ts, D[1][b], uds); usd = fmaf(td, S[1][b], usd);
+    }
+    gx = fmaf(uss, D[0][a], gx); gy = fmaf(uds, S[0][a], gy); gz = fmaf(usd, S[0][a], gz);
+  }
+  float n[3];
+  n[0] = gx / (32.f * e.vox[0]); n[1] = gy / (32.f * e.vox[1]); n[2] = gz / (32.f * e.vox[2]);
   const float nn = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);   // no epsilon (recon_util.py:46-47)
   e.normals[vid * 3 + 0] = -(n[0] / nn);                              // negated (:68)
   e.normals[vid * 3 + 1] = -(n[1] / nn);
