@@ -512,9 +512,28 @@ def run_ours(args):
             ietc.close()
         except Exception as ex:
             enc_ms['encoder_hgfilter_tc_error'] = repr(ex)[:200]
+        # a SMOOTH body surface (the analytic capsule-body SDF on the same grid, evaluated with torch on the device -- synthetic input, not
+        # part of the path): what mesh extraction and skinning cost on a mesh like a trained avatar's (the noise field above is a stress case)
+        smooth = {}
+        try:
+            mats = synth.joint_affine_mats(synth.cano_pose())
+            pj = torch.from_numpy((np.einsum('jab,jb->ja', mats[:, :3, :3], synth._REST_JOINTS) + mats[:, :3, 3]).astype(np.float32)).to(dev)
+            sdf = torch.full((n,), -1e9, device=dev)
+            for j in range(1, synth.N_JOINTS):
+                a_, b_ = pj[int(synth.PARENTS[j])], pj[j]
+                ab = b_ - a_
+                tt_ = (((pts - a_) @ ab) / max(float(ab @ ab), 1e-12)).clamp_(0.0, 1.0)
+                sdf = torch.maximum(sdf, float(synth._BONE_RADIUS[j]) - (pts - (a_ + tt_[:, None] * ab)).norm(dim=1))
+            svol = sdf.reshape(res).contiguous(); del sdf
+            t_sm, (sv_, sf_, sn_) = timed(lambda: eng.extract_mesh(svol, frame['cano_bounds'], 0.0))
+            t_sl, _ = timed(lambda: eng.skin_mesh(sv_, sn_, cv, sw, jm))
+            smooth = {'smooth_body_vertices': int(sv_.shape[0]), 'smooth_body_mesh_extract_ms': t_sm, 'smooth_body_lbs_ms': t_sl}
+            del svol, sv_, sf_, sn_
+        except Exception as ex:
+            smooth = {'smooth_body_error': repr(ex)[:200]}
         frame_ms = {'vertex_colour_ms': t_col, 'vertex_colour_vertices': nvc, 'valid_fraction': float(flag.float().mean()), 'valid_points': int(vpts.shape[0]), 'field_ms': t_field, 'scatter_ms': t_scat,
                     'mesh_extract_ms': t_mesh, 'lbs_ms': t_lbs, 'whole_frame_ms': t_all, 'vertices': int(mv.shape[0]), 'faces': int(mf.shape[0])}
-        frame_ms.update(enc_ms); frame_ms.update(recon_ms)
+        frame_ms.update(enc_ms); frame_ms.update(recon_ms); frame_ms.update(smooth)
         # fusion stage ("next" row 4, main.py:369-428): avatar normal maps of the masked-frame mesh (2 orthographic 512^2 views), and
         # canonicalize_normal_map (perspective position pass + per-vertex canonicalisation + 2 views) -- the reference does these in OpenGL
         try:
