@@ -3,7 +3,7 @@
 // One CTA evaluates a tile of TP points through the WHOLE network with activations resident in shared memory
 // (the reference round-trips every 256-channel activation through HBM: network/mlp.py:56-72, 101-112).
 // It is the numerically closest path to the reference's fp32 math and the on-device cross-check for the
-// tcgen05 kernel (field_tc.cu).
+// tcgen05 kernel (field_tc2.cu).
 //
 // Reference call sites restated here:
 //   WarpingField.query      network/arch_avatar.py:113-140  (bilinear gather :133, OffsetDecoder mlp.py:101-112, out :138)

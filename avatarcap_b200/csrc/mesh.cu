@@ -17,9 +17,7 @@ namespace {
 
 constexpr int MC_NT = 256;
 constexpr int MC_VPT = 4;                  // voxels per quad (consecutive in z: one float4 of a z-row on the vector path)
-constexpr int MC_QPT = 4;                  // quads per thread: 16 consecutive voxels. A block's lifetime is a chain of latencies (loads, two
-                                           // barriers, the look-back round trip); 4 096 voxels per block instead of 1 024 means a quarter of the
-                                           // blocks pay it (launch list r2d: 235 us for 16 384 blocks of 1 024 voxels at 256^3)
+constexpr int MC_QPT = 4;                  // quads per thread (16 voxels, 4 096 per block): enough independent loads in flight per thread
 constexpr int MC_VPB = MC_NT * MC_VPT * MC_QPT;     // voxels per block
 
 struct McDims {
@@ -511,7 +509,7 @@ int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi
   d->rx = res[0]; d->ry = res[1]; d->rz = res[2];
   d->lo = halo_lo; d->hi_excl = res[0] - halo_hi; d->scan_end = halo_hi > 0 ? d->hi_excl + 1 : d->hi_excl;
   d->iso = iso; d->nvox = (int64_t)res[0] * res[1] * res[2]; d->vec4 = 0;
-  // vertex / triangle prefixes travel as 31-bit fields of one look-back word: 3 edges and at most 5 triangles per voxel
+  // vertex / triangle prefixes travel as 31-bit fields of one 64-bit word: 3 edges and at most 5 triangles per voxel
   if (d->nvox * 5 >= ((int64_t)1 << 31)) return avc_fail(ctx, AVC_EINVAL, "volume too large for int32 mesh indices (%lld voxels)", (long long)d->nvox);
   *nblk = (int)((d->nvox + MC_VPB - 1) / MC_VPB);
   size_t off = 128 + (size_t)*nblk * 2 * sizeof(unsigned long long); off = (off + 255) & ~(size_t)255;

@@ -128,12 +128,12 @@ def _slab(mat_nk16: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(mat_nk16.reshape(n // 8, 8, 2, 8).transpose(0, 2, 1, 3)).reshape(-1)
 
 
-STAGE_KSTEPS = 2      # k-steps per shared-memory ring stage (csrc/field_tc.cu)
+STAGE_KSTEPS = 2      # k-steps per shared-memory ring stage (csrc/field_tc2.cu)
 
 
 def tc_pieces(kind: int, layer: int, npad: int):
     """[(row_off, n_rows, [(first weight k-step, k-steps), ...] in issue order)] for one layer -- the op program of
-    csrc/field_tc.cu build_ops(): skip-input (shared-memory) k-steps are issued before the TMEM-fed ones."""
+    csrc/field_tc2.cu build_ops(): skip-input (shared-memory) k-steps are issued before the TMEM-fed ones."""
     if kind == KIND_AVATAR:
         segs = {0: [(0, 5)], 4: [(0, 5), (5, 16)], 8: [(0, 4)], 12: [(16, 4), (0, 16)], 16: [(0, 8)], 19: [(0, 8)]}.get(layer, [(0, 16)])
         return [(0, npad, segs)]
@@ -176,7 +176,7 @@ def pack(layers: List[_Layer], kind: int) -> bytes:
         hi, lo = split_hi_lo(Wp)
         # The tensor-core kernel consumes a layer as a STREAM: for each piece (row block of an op), each N-half of 128 rows,
         # each ring stage (<= 2 k-steps, in issue order: shared-memory segment first), the hi slab then the lo slab of those
-        # rows. One cp.async.bulk per stage moves it; tc_pieces() mirrors build_ops() in csrc/field_tc.cu.
+        # rows. One cp.async.bulk per stage moves it; tc_pieces() mirrors build_ops() in csrc/field_tc2.cu.
         tc_w_off = f16_bytes
         for row_off, n_piece, segs in tc_pieces(kind, len(descs), npad):
             halves = 2 if n_piece == 256 else 1

@@ -253,7 +253,7 @@ def test_mc_emit_counted_reuse_and_fallback(eng):
 
 def test_mc_extract_capacity_bounded_async(eng):
     """avc_mc_extract: no host round trip, device-side counts; too small a capacity sets the overflow flag, keeps the counts exact
-    and fills the first cap entries -- never a silent truncation. Many blocks (the chained look-back scan) and both iso values."""
+    and fills the first cap entries -- never a silent truncation. Many chunks (every block sums the chunk records before it) and both iso values."""
     rs = np.random.RandomState(21)
     bounds = np.array([[-1, -1, -0.4], [1, 1, 0.4]], np.float32)
     from oracle import mesh_oracle as mo
