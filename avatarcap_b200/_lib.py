@@ -96,10 +96,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get('AVC_LIB_PATH') or LIB_PATH          # A/B of two builds of the library (tests/diag_*): not a fallback, it must exist
+    if not os.path.exists(path):
         raise ImportError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` or '
-                          '`make -C avatarcap_b200/csrc` (needs nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+                          '`make -C avatarcap_b200/csrc` (needs nvcc, sm_100a). There is no CPU fallback.' % path)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch
         fn.restype = res

@@ -15,6 +15,9 @@
 namespace {
 
 constexpr int KNN_NT = 256;
+#ifndef KNN_MIN_BLOCKS_K4
+#define KNN_MIN_BLOCKS_K4 3
+#endif
 
 struct Top4 { float d[4]; int i[4]; };
 
@@ -341,7 +344,7 @@ struct EpiKnn {            // pytorch3d.ops.knn_points: squared distances ascend
 struct EpiLbs {            // SmplUtil.calculate_lbs   smpl_util.py:24-39
   const float* skin_w; float* out_lbs;
   static constexpr bool MATS = false;
-  static constexpr int MIN_BLOCKS = 3;       // 80 registers, no spills: the search is latency bound, occupancy pays
+  static constexpr int MIN_BLOCKS = KNN_MIN_BLOCKS_K4;       // 3 = 80 registers, no spills: the search is latency bound, occupancy pays
   __device__ __forceinline__ const float* mats() const { return nullptr; }
   __device__ __forceinline__ void operator()(int64_t g, float, float, float, const Top4& best, const float*) const {
     float w[4]; gauss_weights(best, w);
@@ -353,7 +356,7 @@ struct EpiLbs {            // SmplUtil.calculate_lbs   smpl_util.py:24-39
 struct EpiSkinMesh {       // calculate_lbs + skinning (+ skinning_normal)   main.py:385-389, smpl_util.py:58-81
   const float* skin_w; const float* jm; const float* normals; float* out_v; float* out_n;
   static constexpr bool MATS = true;
-  static constexpr int MIN_BLOCKS = 3;
+  static constexpr int MIN_BLOCKS = KNN_MIN_BLOCKS_K4;
   __device__ __forceinline__ const float* mats() const { return jm; }
   __device__ __forceinline__ void operator()(int64_t g, float x, float y, float z, const Top4& best, const float* s_m) const {
     float w[4]; gauss_weights(best, w);

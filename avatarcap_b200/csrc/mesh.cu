@@ -27,6 +27,7 @@ struct McDims {
   float iso;
   int64_t nvox;
   int vec4;              // rz % 4 == 0 and a 16-byte aligned volume: a thread's 4 voxels are one float4 of one z-row (classify4)
+  int q_di, q_dj, q_dk;  // (i, j, k) step between a thread's consecutive quads (MC_NT * MC_VPT voxels), so that only the first quad pays the divisions
 };
 
 __device__ __forceinline__ float ldv(const float* __restrict__ vol, int64_t idx) { return __ldg(vol + idx); }
@@ -118,8 +119,7 @@ __device__ __forceinline__ void classify4(const float* __restrict__ vol, const M
 }
 // classification of a thread's 4 voxels by either path (a compile-time choice: both inlined four times made the kernels instruction-fetch bound)
 template <bool VEC4>
-__device__ __forceinline__ void classify_thread(const float* __restrict__ vol, const McDims& d, int64_t v0, Vox4& r) {
-  Vox3 c = vox_of(d, v0 < d.nvox ? v0 : 0);
+__device__ __forceinline__ void classify_thread(const float* __restrict__ vol, const McDims& d, int64_t v0, Vox3 c, Vox4& r) {
   if (VEC4) { classify4(vol, d, v0, c, r); return; }
   r.in_scan = false; r.owned = false; r.own_mask = 0; r.any = true;
 #pragma unroll
@@ -179,9 +179,16 @@ __device__ __forceinline__ int64_t quad_start(int bid, int s) { return (((int64_
 template <bool VEC4>
 __device__ __forceinline__ void classify16(const float* __restrict__ vol, const McDims& d, int bid, ThreadCls& T, int& nvo) {
   nvo = 0;
+  const int64_t q0 = quad_start(bid, 0);
+  Vox3 c = vox_of(d, q0 < d.nvox ? q0 : 0);
 #pragma unroll
   for (int s = 0; s < MC_QPT; ++s) {
-    Vox4 r; classify_thread<VEC4>(vol, d, quad_start(bid, s), r);
+    if (s > 0) {                                               // + MC_NT * MC_VPT voxels: one carry per axis is enough (each step is < the extent)
+      c.k += d.q_dk; const int ck = c.k >= d.rz; c.k -= ck ? d.rz : 0;
+      c.j += d.q_dj + ck; const int cj = c.j >= d.ry; c.j -= cj ? d.ry : 0;
+      c.i += d.q_di + cj;
+    }
+    Vox4 r; classify_thread<VEC4>(vol, d, quad_start(bid, s), c, r);
     unsigned long long w = 0;
     if (r.any) {
 #pragma unroll
@@ -509,6 +516,7 @@ int mc_setup(avc_ctx* ctx, const int res[3], float iso, int halo_lo, int halo_hi
   d->rx = res[0]; d->ry = res[1]; d->rz = res[2];
   d->lo = halo_lo; d->hi_excl = res[0] - halo_hi; d->scan_end = halo_hi > 0 ? d->hi_excl + 1 : d->hi_excl;
   d->iso = iso; d->nvox = (int64_t)res[0] * res[1] * res[2]; d->vec4 = 0;
+  { const int step = MC_NT * MC_VPT; d->q_dk = step % res[2]; d->q_dj = (step / res[2]) % res[1]; d->q_di = step / (res[2] * res[1]); }
   // vertex / triangle prefixes travel as 31-bit fields of one 64-bit word: 3 edges and at most 5 triangles per voxel
   if (d->nvox * 5 >= ((int64_t)1 << 31)) return avc_fail(ctx, AVC_EINVAL, "volume too large for int32 mesh indices (%lld voxels)", (long long)d->nvox);
   *nblk = (int)((d->nvox + MC_VPB - 1) / MC_VPB);

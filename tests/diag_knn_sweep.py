@@ -42,8 +42,9 @@ def timed(fn, reps=5):
 
 ref = {k: eng.skin_mesh(v, n, cv, sw, jm)[0].clone() for k, (v, n) in meshes.items()}
 print('%-6s %-5s | %s | near_flag' % ('cell', 'rmax', ' | '.join('%-18s' % k for k in meshes)))
-for cell in ('0.03', '0.04', '0.06'):
-    for rmax in ('1', '2', '3', '4', '6'):
+quick = len(sys.argv) > 1 and sys.argv[1] == 'quick'          # only the default setting (A/B of two library builds through AVC_LIB_PATH)
+for cell in (('0.04',) if quick else ('0.03', '0.04', '0.06')):
+    for rmax in (('4',) if quick else ('1', '2', '3', '4', '6')):
         os.environ['AVC_KNN_CELL'] = cell; os.environ['AVC_KNN_RMAX'] = rmax
         row = []
         for k, (v, n) in meshes.items():
