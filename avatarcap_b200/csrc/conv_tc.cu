@@ -385,6 +385,47 @@ __global__ void __launch_bounds__(256) bicubic_up2_add_kernel(const float* __res
   }
 }
 
+// nn.Upsample(mode='bilinear', scale_factor=2, align_corners=False) of [relu](x) written as fp16 hi / lo planes -- the input stage of
+// UpConv2DBlock(up_mode='upsample') (network/unets.py:41-44, 47-49): src = (dst + 0.5) / 2 - 0.5 clamped at 0, second tap clamped to the
+// last row / column (ATen upsample_bilinear2d). x: (h, w) pixels, channels [c_off, c_off + C) of rows of length ld; planes: (2h * 2w, cpad).
+__global__ void __launch_bounds__(256) bilinear_up2_split_kernel(const float* __restrict__ x, int h, int w, int C, int ld, int c_off, int relu,
+                                                                 __half* __restrict__ hi, __half* __restrict__ lo, int cpad) {
+  const int H = 2 * h, W = 2 * w, C4 = C / 4;
+  const int64_t n = (int64_t)H * W * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4; const int64_t t = i / C4; const int ox = (int)(t % W), oy = (int)(t / W);
+    const float sy = fmaxf(((float)oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf(((float)ox + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx, y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* base = x + c_off + c;
+    float4 a = *reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x0) * ld), b = *reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x1) * ld);
+    float4 d = *reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x0) * ld), e = *reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x1) * ld);
+    if (relu) {
+      a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)); b = make_float4(fmaxf(b.x, 0.f), fmaxf(b.y, 0.f), fmaxf(b.z, 0.f), fmaxf(b.w, 0.f));
+      d = make_float4(fmaxf(d.x, 0.f), fmaxf(d.y, 0.f), fmaxf(d.z, 0.f), fmaxf(d.w, 0.f)); e = make_float4(fmaxf(e.x, 0.f), fmaxf(e.y, 0.f), fmaxf(e.z, 0.f), fmaxf(e.w, 0.f));
+    }
+    // ATen: hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11)
+    const float v[4] = {hy * (hx * a.x + lx * b.x) + ly * (hx * d.x + lx * e.x), hy * (hx * a.y + lx * b.y) + ly * (hx * d.y + lx * e.y),
+                        hy * (hx * a.z + lx * b.z) + ly * (hx * d.z + lx * e.z), hy * (hx * a.w + lx * b.w) + ly * (hx * d.w + lx * e.w)};
+    __half hh[4], ll[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { hh[j] = __float2half_rn(v[j]); ll[j] = __float2half_rn(v[j] - __half2float(hh[j])); }
+    const size_t o = ((size_t)oy * W + ox) * cpad + c;
+    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<const uint2*>(hh);
+    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<const uint2*>(ll);
+  }
+}
+
+// dst[:, c_off : c_off + C] = src (P, C): the skip half of torch.cat([conv, skip], 1) (unets.py:55-56) lands in its channel slice
+__global__ void __launch_bounds__(256) copy_slice_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t P, int C, int ld, int c_off) {
+  const int C4 = C / 4;
+  const int64_t n = P * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / C4; const int c = (int)(i % C4) * 4;
+    *reinterpret_cast<float4*>(dst + p * ld + c_off + c) = *reinterpret_cast<const float4*>(src + p * C + c);
+  }
+}
+
 // HGFilter.conv1: 7x7, stride 2, padding 3, 6 -> 64 channels, with bias (HGFilters.py:136, 180), fp32 on the CUDA cores (1.2 GMAC).
 // in: (6, Hin, Win) f32 (the reference's NCHW input), out: (Hin/2, Win/2, 64) f32. Block = 16x16 output pixels, thread = 1 pixel,
 // weights staged per 8-output-channel group.
@@ -459,7 +500,7 @@ int make_tmap(avc_ctx* ctx, CUtensorMap* m, const void* base, uint64_t d0, uint6
 
 // ------------------------------------------------------------------------------------------------ the op program
 // One op = 16 int32: [kind, a0..a14]. Buffers are numbered; f32 buffers and fp16 plane pairs live in one arena each.
-enum { ENC_OP_STEM = 1, ENC_OP_GN = 2, ENC_OP_CONV = 3, ENC_OP_ADD = 4, ENC_OP_POOL = 5, ENC_OP_UPADD = 6 };
+enum { ENC_OP_STEM = 1, ENC_OP_GN = 2, ENC_OP_CONV = 3, ENC_OP_ADD = 4, ENC_OP_POOL = 5, ENC_OP_UPADD = 6, ENC_OP_INPUT = 7, ENC_OP_UPSPLIT = 8, ENC_OP_COPY = 9 };
 
 struct EncConv { CUtensorMap a_hi, a_lo, b_hi, b_lo; ConvArgs args; size_t smem; int grid; };
 
@@ -533,10 +574,23 @@ extern "C" int avc_encoder_create(avc_ctx* ctx, const int32_t* program, int64_t 
   ENC_CUDA(cudaMalloc(&e->d_partial, (size_t)1024 * 32 * 2 * sizeof(double)));
   ENC_CUDA(cudaMalloc(&e->d_ticket, 64)); ENC_CUDA(cudaMemset(e->d_ticket, 0, 64));
   ENC_CUDA(cudaMalloc(&e->d_stats, 64 * sizeof(float)));
-  // tensor maps + launch geometry of every convolution
+  // tensor maps + launch geometry of every convolution; buffer / plane indices of every op
   for (int o = 0; o < nops; ++o) {
     const int32_t* op = ops + 16 * o;
     auto bad = [&](const char* what) { return fail(avc_fail(ctx, AVC_EFORMAT, "encoder program: op %d (%d): %s", o, op[0], what)); };
+    auto buf_ok = [&](int b) { return b >= 0 && b < nb; };
+    switch (op[0]) {
+      case ENC_OP_STEM: if (!buf_ok(op[3])) return bad("buffer index"); break;
+      case ENC_OP_GN: if (!buf_ok(op[1]) || op[9] >= np || (op[10] >= 0 && !buf_ok(op[10])) || (op[3] & 31) || op[3] > 256) return bad("buffer / plane index or channel count"); break;
+      case ENC_OP_ADD: if (!buf_ok(op[1]) || !buf_ok(op[2]) || op[3] > sizes[op[1]] || op[3] > sizes[op[2]]) return bad("buffer index / size"); break;
+      case ENC_OP_POOL: if (!buf_ok(op[1]) || !buf_ok(op[2])) return bad("buffer index"); break;
+      case ENC_OP_UPADD: if (!buf_ok(op[1]) || !buf_ok(op[2]) || !buf_ok(op[3])) return bad("buffer index"); break;
+      case ENC_OP_INPUT: if (!buf_ok(op[1]) || op[2] < 0 || op[3] < 0 || op[3] > sizes[op[1]]) return bad("buffer index / size"); break;
+      case ENC_OP_UPSPLIT: if (!buf_ok(op[1]) || op[8] < 0 || op[8] >= np || (op[4] & 3) || (int64_t)4 * op[2] * op[3] != pl[2 * op[8]]) return bad("buffer / plane"); break;
+      case ENC_OP_COPY: if (!buf_ok(op[1]) || !buf_ok(op[2]) || (op[4] & 3) || (int64_t)op[3] * op[5] > sizes[op[2]]) return bad("buffer index / size"); break;
+      case ENC_OP_CONV: break;
+      default: return bad("unknown op");
+    }
     if (op[0] != ENC_OP_CONV) continue;
     // [3, plane, w_off_bytes, out_buf, H, W, cin_pad, N, taps, c_off, ldc, accumulate, bias_off(-1), weight scale exponent s]
     const int plane = op[1], H = op[4], W = op[5], cin = op[6], N = op[7], taps = op[8];
@@ -623,6 +677,21 @@ static int enc_enqueue(avc_encoder* e, const float* in, float* outp, cudaStream_
       }
       case ENC_OP_UPADD: {      // [6, up1_buf, low_buf, dst_buf, h, w, C]  (low is h x w, up1 / dst are 2h x 2w)
         bicubic_up2_add_kernel<<<blocks_for((int64_t)4 * op[4] * op[5] * op[6] / 4), 256, 0, st>>>(e->f32_bufs[op[1]], e->f32_bufs[op[2]], e->f32_bufs[op[3]], op[4], op[5], op[6]);
+        ++nl; break;
+      }
+      case ENC_OP_INPUT: {      // [7, dst_buf, offset (floats) into the caller's input, n_floats]: programs with several input tensors
+        if (cudaMemcpyAsync(e->f32_bufs[op[1]], in + op[2], (size_t)op[3] * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+          return avc_check_cuda(ctx, cudaGetLastError(), "encoder input copy");
+        break;
+      }
+      case ENC_OP_UPSPLIT: {    // [8, src_buf, h, w, C, ld, c_off, relu, plane]: bilinear x2 (align_corners=False) of [relu](src) -> fp16 planes
+        const int plane = op[8];
+        bilinear_up2_split_kernel<<<blocks_for((int64_t)4 * op[2] * op[3] * op[4] / 4), 256, 0, st>>>(e->f32_bufs[op[1]], op[2], op[3], op[4], op[5], op[6], op[7],
+                                                                                                   e->plane_hi[plane], e->plane_lo[plane], e->plane_cpad[plane]);
+        ++nl; break;
+      }
+      case ENC_OP_COPY: {       // [9, src_buf, dst_buf, P, C, ld_dst, c_off_dst]
+        copy_slice_kernel<<<blocks_for((int64_t)op[3] * op[4] / 4), 256, 0, st>>>(e->f32_bufs[op[1]], e->f32_bufs[op[2]], (int64_t)op[3], op[4], op[5], op[6]);
         ++nl; break;
       }
       default: return avc_fail(ctx, AVC_EFORMAT, "encoder program: unknown op %d", op[0]);

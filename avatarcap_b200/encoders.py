@@ -202,7 +202,7 @@ class ImageFeatureEncoder:
 # buffers and packs the weights (fp16 hi / lo planes, (C_out, taps, C_in) K-major, power-of-two pre-scale); every arithmetic
 # operation runs in the CUDA library: tcgen05 implicit-GEMM convolutions fed by TMA tensor loads, GroupNorm, pooling, bicubic
 # up-sampling and the 7x7 stem as kernels of ours, all captured in one CUDA graph.
-OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD = 1, 2, 3, 4, 5, 6
+OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD, OP_INPUT, OP_UPSPLIT, OP_COPY = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 class _Program:
@@ -225,6 +225,11 @@ class _Program:
     def param(self, arr) -> int:
         off = sum(len(a) for a in self.params)
         self.params.append(np.asarray(arr, np.float32).reshape(-1)); return off
+
+    def conv_weight_bias(self, w: np.ndarray, bias):
+        """conv_weight + a bias vector (or None) -> (weight offset, scale exponent, C_in_pad, bias offset | -1)"""
+        off, s, cpad = self.conv_weight(w)
+        return off, s, cpad, (-1 if bias is None else self.param(bias))
 
     def conv_weight(self, w: np.ndarray):
         """(C_out, C_in, kh, kw) f32 -> byte offset of [hi plane | lo plane], each (C_out, taps, C_in_pad) fp16, and the scale exponent"""
@@ -330,6 +335,110 @@ def build_hgfilter_program(state_dict: Dict, prefix: str = '', in_hw=(512, 512))
     conv(pr.plane(P, 256), 'l0.weight', out, H, W, 32, 0, 32, bias='l0.bias')                  # use_sigmoid=False: no tanh
     build_hgfilter_program.last_marks = pr.marks
     return pr.pack((6, Hin, Win), out, (H, W, 32))
+
+
+def build_unet_tail_program(state_dict: Dict, prefix: str = '', out_hw=(256, 256)):
+    """The three `UpConv2DBlock(up_mode='upsample')` stages that end UnetNoCond7DS.forward (unets.py:217-219: upconvC5, upconvC6,
+    upconvC7 = relu -> bilinear x2 -> 3x3 convolution (+ eval BatchNorm, folded) [-> cat skip]) as a library program: 7.8 of the UNet's
+    10.5 GFLOP. Input = one flat f32 buffer [u4 (H/8, W/8, 384) | a2 (H/4, W/4, 64) | a1 (H/2, W/2, 32)], all (H, W, C) order; output
+    (H, W, 64). -> (program, weights, params, input float counts)."""
+    g = lambda k: np.asarray(state_dict[prefix + k].detach().cpu().numpy() if hasattr(state_dict[prefix + k], 'detach') else state_dict[prefix + k], np.float64)   # noqa: E731
+    H, W = out_hw
+    if H % 128 or W % 128:
+        raise ValueError('the UNet needs H, W multiples of 128')
+    pr = _Program()
+
+    def folded(name, bn):
+        w = g(name + '.up.1.weight'); b = g(name + '.up.1.bias')
+        if bn:
+            s = 1.0 / np.sqrt(g(name + '.bn.running_var') + BN_EPS)
+            w = w * s[:, None, None, None]; b = (b - g(name + '.bn.running_mean')) * s
+        return w.astype(np.float32), b.astype(np.float32)
+
+    h8, w8, h4, w4, h2, w2 = H // 8, W // 8, H // 4, W // 4, H // 2, W // 2
+    n_u4, n_a2, n_a1 = h8 * w8 * 384, h4 * w4 * 64, h2 * w2 * 32
+    u4 = pr.buf(n_u4); a2 = pr.buf(n_a2); a1 = pr.buf(n_a1)
+    pr.op(OP_INPUT, u4, 0, n_u4); pr.op(OP_INPUT, a2, n_u4, n_a2); pr.op(OP_INPUT, a1, n_u4 + n_a2, n_a1)
+    # upconvC5: relu(u4) -> up -> conv 384 -> 64 (+bn) ; cat a2
+    c5 = pr.buf(h4 * w4 * 128)
+    pr.op(OP_UPSPLIT, u4, h8, w8, 384, 384, 0, 1, pr.plane(h4 * w4, 384))
+    wt, b = folded('upconvC5', True); off, s_, cpad, boff = pr.conv_weight_bias(wt, b)
+    pr.op(OP_CONV, pr.plane(h4 * w4, 384), off, c5, h4, w4, cpad, 64, 9, 0, 128, 0, boff, s_)
+    pr.op(OP_COPY, a2, c5, h4 * w4, 64, 128, 64)
+    # upconvC6: relu(c5) -> up -> conv 128 -> 32 (+bn) ; cat a1
+    c6 = pr.buf(h2 * w2 * 64)
+    pr.op(OP_UPSPLIT, c5, h4, w4, 128, 128, 0, 1, pr.plane(h2 * w2, 128))
+    wt, b = folded('upconvC6', True); off, s_, cpad, boff = pr.conv_weight_bias(wt, b)
+    pr.op(OP_CONV, pr.plane(h2 * w2, 128), off, c6, h2, w2, cpad, 32, 9, 0, 64, 0, boff, s_)
+    pr.op(OP_COPY, a1, c6, h2 * w2, 32, 64, 32)
+    # upconvC7: relu(c6) -> up -> conv 64 -> 64 + bias (no bn)
+    out = pr.buf(H * W * 64)
+    pr.op(OP_UPSPLIT, c6, h2, w2, 64, 64, 0, 1, pr.plane(H * W, 64))
+    wt, b = folded('upconvC7', False); off, s_, cpad, boff = pr.conv_weight_bias(wt, b)
+    pr.op(OP_CONV, pr.plane(H * W, 64), off, out, H, W, cpad, 64, 9, 0, 64, 0, boff, s_)
+    return pr.pack((n_u4 + n_a2 + n_a1, 1, 1), out, (H, W, 64)) + ((n_u4, n_a2, n_a1),)
+
+
+class PoseFeatureEncoderTC(PoseFeatureEncoder):
+    """PoseFeatureEncoder whose three final up-sampling stages (upconvC5 / C6 / C7: 3x3 convolutions at 64^2, 128^2 and 256^2, three
+    quarters of the UNet's FLOPs) run on the library's tcgen05 convolution kernel; the stride-2 4x4 encoder and the transposed
+    convolutions of the shared decoder (small, latency bound) stay on the cuDNN CUDA-graph replay of the parent class."""
+
+    def __init__(self, state_dict: Dict, prefix: str = '', engine=None, in_hw=(256, 256), use_graph: bool = True):
+        import ctypes as C
+        from .engine import default_engine
+        self.engine = engine if engine is not None else default_engine()
+        super().__init__(state_dict, prefix=prefix, device=self.engine.device, use_graph=False, channels_last=True)
+        self.in_hw = tuple(in_hw)
+        self.use_graph = bool(use_graph)
+        prog, wbytes, params, self._in_counts = build_unet_tail_program(state_dict, prefix, in_hw)
+        h = C.c_void_p()
+        e = self.engine
+        e._check(e.lib.avc_encoder_create(e._h, prog.ctypes.data_as(C.c_void_p), len(prog), wbytes, len(wbytes), params.ctypes.data_as(C.c_void_p),
+                                          len(params), C.byref(h)))
+        self._h = h
+        self._tail_in = torch.empty(sum(self._in_counts), device=self.device, dtype=torch.float32)
+        self._out = torch.empty((in_hw[0], in_hw[1], 64), device=self.device, dtype=torch.float32)
+        self._head = _GraphedForward(self._forward_head, self.device, use_graph)
+
+    def _forward_head(self, x: torch.Tensor) -> torch.Tensor:
+        """conv1..7 + the shared decoder (unets.py:201-215) on cuDNN; writes [u4 | a2 | a1] in (H, W, C) order into the tail's input buffer"""
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.benchmark, deterministic=self.deterministic, allow_tf32=self.allow_tf32):
+            x = x.contiguous(memory_format=self.mf)
+            a = []
+            h = F.conv2d(x, self.down[0][0], None, stride=2, padding=1)
+            for w, b in self.down[1:]:
+                h = F.leaky_relu(h, 0.2)
+                a.append(h)
+                h = F.conv2d(h, w, b, stride=2, padding=1)
+            for (w, b), skip in zip((self.up[0], self.up[1], self.up[2], self.up[2]), (a[5], a[4], a[3], a[2])):
+                h = torch.cat([F.conv_transpose2d(F.relu(h), w, b, stride=2, padding=1), skip], 1)
+            n4, n2, n1 = self._in_counts
+            self._tail_in[:n4].view(h.shape[2], h.shape[3], h.shape[1]).copy_(h[0].permute(1, 2, 0))
+            self._tail_in[n4:n4 + n2].view(a[1].shape[2], a[1].shape[3], a[1].shape[1]).copy_(a[1][0].permute(1, 2, 0))
+            self._tail_in[n4 + n2:].view(a[0].shape[2], a[0].shape[3], a[0].shape[1]).copy_(a[0][0].permute(1, 2, 0))
+            return self._tail_in
+
+    def close(self) -> None:
+        if getattr(self, '_h', None) and getattr(self.engine, '_h', None):
+            self.engine.lib.avc_encoder_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, smpl_pos_map) -> torch.Tensor:
+        import ctypes as C
+        x = torch.as_tensor(smpl_pos_map)
+        if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != 6 or tuple(x.shape[2:]) != self.in_hw:
+            raise ValueError('smpl_pos_map must be (1,6,%d,%d), got %s' % (self.in_hw + (tuple(x.shape),)))
+        self._head(x)
+        e = self.engine
+        e._check(e.lib.avc_encoder_run(self._h, C.c_void_p(self._tail_in.data_ptr()), C.c_void_p(self._out.data_ptr()), int(self.use_graph), e._stream()))
+        return self._out.permute(2, 0, 1)[None]            # (1,64,H,W) view with channels_last strides; overwritten by the next call
 
 
 class ImageFeatureEncoderTC:

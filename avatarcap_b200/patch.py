@@ -248,8 +248,16 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
         def precompute_conv(self, batch):
             if not _inference(self) or not batch['smpl_pos_map'].is_cuda:
                 return o_pc(self, batch)
-            # clone: the graph owns its output buffer and the reference keeps pose_feat_map across calls (arch_avatar.py:111)
-            self.pose_feat_map = _encoder('unet', self.unet, enc_mod.PoseFeatureEncoder)(batch['smpl_pos_map']).clone(memory_format=torch.preserve_format)
+            # clone: the encoder owns its output buffer and the reference keeps pose_feat_map across calls (arch_avatar.py:111)
+            x = batch['smpl_pos_map']
+            e = _engine()
+            if e.has_tensor_core_path and x.shape[0] == 1 and x.shape[2] % 128 == 0 and x.shape[3] % 128 == 0:
+                # cuDNN head + the three final 3x3 stages (3/4 of the FLOPs) on the library's tcgen05 convolutions
+                hw = (int(x.shape[2]), int(x.shape[3]))
+                cls = lambda sd, device: enc_mod.PoseFeatureEncoderTC(sd, engine=e, in_hw=hw)      # noqa: E731
+                self.pose_feat_map = _encoder('unettc%dx%d' % hw, self.unet, cls)(x).clone(memory_format=torch.preserve_format)
+            else:
+                self.pose_feat_map = _encoder('unet', self.unet, enc_mod.PoseFeatureEncoder)(x).clone(memory_format=torch.preserve_format)
         arch_avatar.WarpingField.precompute_conv = precompute_conv
 
         o_gfm = keep(arch_recon.ReconNetwork, 'get_feat_maps')

@@ -60,6 +60,16 @@ def main():
     print('HGFilter: tcgen05 eager %.3f ms, tcgen05 graph %.3f ms, cuDNN f32 graph %.3f ms' % (timed(lambda: tc(y)), timed(lambda: tcg(y)), timed(lambda: refg(y))))
     o2 = tcg(y).clone(); o3 = tcg(y).clone()
     print('graph == eager: %s, replay deterministic: %s' % (bool(torch.equal(o2, out)), bool(torch.equal(o2, o3))))
+    # UNet: cuDNN head + tcgen05 tail
+    xs = torch.from_numpy(synth.smpl_pos_map()).cuda()
+    usd = synth.unet_state_dict()
+    utc = encoders.PoseFeatureEncoderTC(usd, engine=eng)
+    uref = encoders.PoseFeatureEncoder(usd, device='cuda', use_graph=True)
+    uo = utc(xs).clone(); ur = uref(xs).clone()
+    samp = uo[0].reshape(64, -1)[:, torch.from_numpy(g['pose_idx']).cuda()].cpu().numpy()
+    print('UNet tcgen05 tail: vs cuDNN f32 max-abs %.3e, vs the reference golden %.3e (range %.3g .. %.3g)' % (
+        float((uo - ur).abs().max()), float(np.abs(samp - g['pose_feat']).max()), float(ur.min()), float(ur.max())))
+    print('UNet: cuDNN head + tcgen05 tail %.3f ms, all-cuDNN f32 graph %.3f ms' % (timed(lambda: utc(xs)), timed(lambda: uref(xs))))
 
 
 if __name__ == '__main__':

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD = 1, 2, 3, 4, 5, 6
+OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD, OP_INPUT, OP_UPSPLIT, OP_COPY = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 def run_program(prog: np.ndarray, weights: bytes, params: np.ndarray, x_chw: np.ndarray) -> np.ndarray:
@@ -22,6 +22,7 @@ def run_program(prog: np.ndarray, weights: bytes, params: np.ndarray, x_chw: np.
     plane = [torch.zeros((int(p), int(c)), dtype=torch.float32) for p, c in planes]       # what hi + lo represent
     wbytes = np.frombuffer(weights, dtype=np.float16)
     x = torch.from_numpy(np.ascontiguousarray(x_chw))
+    flat_in = x.reshape(-1)
     for op in ops:
         k = int(op[0])
         if k == OP_STEM:
@@ -67,6 +68,18 @@ def run_program(prog: np.ndarray, weights: bytes, params: np.ndarray, x_chw: np.
             lo_t = bufs[low][:h * w * C].view(h, w, C).permute(2, 0, 1)[None]
             y = F.interpolate(lo_t, scale_factor=2, mode='bicubic', align_corners=True)[0].permute(1, 2, 0).reshape(-1)
             bufs[dst][:y.numel()] = bufs[up1][:y.numel()] + y
+        elif k == OP_INPUT:
+            bufs[op[1]][:op[3]] = flat_in[op[2]:op[2] + op[3]]
+        elif k == OP_UPSPLIT:
+            src, h, w, C, ld, c_off, relu, pl = (int(v) for v in op[1:9])
+            v = bufs[src][:h * w * ld].view(h, w, ld)[:, :, c_off:c_off + C].permute(2, 0, 1)[None]
+            if relu:
+                v = torch.relu(v)
+            y = F.interpolate(v, scale_factor=2, mode='bilinear', align_corners=False)[0].permute(1, 2, 0).reshape(4 * h * w, C)
+            plane[pl][:, :C] = y
+        elif k == OP_COPY:
+            src, dst, P, C, ld, c_off = (int(v) for v in op[1:7])
+            bufs[dst][:P * ld].view(P, ld)[:, c_off:c_off + C] = bufs[src][:P * C].view(P, C)
         else:
             raise ValueError('unknown op %d' % k)
     return bufs[out_buf][:out_h * out_w * out_c].view(out_h, out_w, out_c).numpy()

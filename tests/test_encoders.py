@@ -102,6 +102,61 @@ def test_hgfilter_program_interpreted_on_the_cpu_vs_golden():
     assert err < 5e-6
 
 
+def test_unet_tail_program_interpreted_on_the_cpu_vs_golden():
+    """upconvC5 / C6 / C7 of the UNet as a library program (encoders.build_unet_tail_program: bilinear x2 + tcgen05 3x3 convolutions with
+    the eval BatchNorm folded, skips copied into their channel slices), executed by the CPU interpreter on the functional head's tensors,
+    against the reference's own UnetNoCond7DS output."""
+    import torch.nn.functional as F
+    import encoder_program_interp as interp
+    g = load_golden('encoder_golden.npz')
+    sd = synth.unet_state_dict()
+    prog, wbytes, params, counts = encoders.build_unet_tail_program(sd)
+    assert counts == (32 * 32 * 384, 64 * 64 * 64, 128 * 128 * 32) and tuple(prog[8:11]) == (64, 256, 256)
+    pe = encoders.PoseFeatureEncoder(sd, device='cpu', use_graph=False)
+    x = torch.from_numpy(synth.smpl_pos_map())
+    with torch.no_grad():                                   # the head exactly as PoseFeatureEncoderTC._forward_head runs it
+        a = []
+        h = F.conv2d(x.contiguous(memory_format=pe.mf), pe.down[0][0], None, stride=2, padding=1)
+        for w, b in pe.down[1:]:
+            h = F.leaky_relu(h, 0.2); a.append(h); h = F.conv2d(h, w, b, stride=2, padding=1)
+        for (w, b), skip in zip((pe.up[0], pe.up[1], pe.up[2], pe.up[2]), (a[5], a[4], a[3], a[2])):
+            h = torch.cat([F.conv_transpose2d(F.relu(h), w, b, stride=2, padding=1), skip], 1)
+        flat = torch.cat([t[0].permute(1, 2, 0).reshape(-1) for t in (h, a[1], a[0])]).numpy()
+    out = interp.run_program(prog, wbytes, params, flat)      # (256, 256, 64)
+    err = _report('unet tail program on the CPU interpreter', out.reshape(-1, 64)[g['pose_idx']].T, g['pose_feat'])
+    assert err < 5e-6
+
+
+@pytest.mark.gpu
+def test_unet_tensor_core_tail_vs_golden():
+    """PoseFeatureEncoderTC: cuDNN head + the three final 3x3 convolution stages on the library's tcgen05 kernel, against the reference's
+    UnetNoCond7DS (golden) and the all-cuDNN restatement; deterministic; hands the (H,W,C) map to the field kernel unchanged."""
+    from avatarcap_b200.engine import Engine
+    g = load_golden('encoder_golden.npz')
+    eng = Engine()
+    if not eng.has_tensor_core_path:
+        pytest.skip('needs sm_100')
+    x = torch.from_numpy(synth.smpl_pos_map()).cuda()
+    tc = encoders.PoseFeatureEncoderTC(synth.unet_state_dict(), engine=eng)
+    out = tc(x).clone()
+    assert tuple(out.shape) == (1, 64, 256, 256) and out.is_contiguous(memory_format=torch.channels_last)
+    assert _report('unet tcgen05 tail', _sampled(out, g['pose_idx']), g['pose_feat']) < 1e-5
+    ref = encoders.PoseFeatureEncoder(synth.unet_state_dict(), device='cuda', use_graph=False, deterministic=True)(x)
+    print('vs the cuDNN f32 restatement: max-abs %.3g' % float((out - ref).abs().max()))
+    assert float((out - ref).abs().max()) < 1e-5
+    other = tc(x * 0.5 + 0.1).clone(); assert float((other - out).abs().max()) > 1e-3
+    assert torch.equal(tc(x), out)
+    eng.load_avatar(synth.avatar_state_dict())
+    frame = synth.make_frame(synth.SynthBody(), None)
+    pts = eng.make_grid(frame['cano_bounds'], (32, 32, 32))
+    eng.set_pose_feature_map(out)
+    a = eng.eval_occupancy(pts, frame['cano_smpl_center'])
+    eng.set_pose_feature_map(out.contiguous())
+    b = eng.eval_occupancy(pts, frame['cano_smpl_center'])
+    assert torch.equal(a['occ'], b['occ'])
+    tc.close(); eng.close()
+
+
 @pytest.mark.gpu
 def test_hgfilter_tensor_core_vs_golden():
     """HGFilter on kernels of the library (csrc/conv_tc.cu: tcgen05 implicit-GEMM convolutions fed by TMA tensor loads, fp16 hi/lo split
