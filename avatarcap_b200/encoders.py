@@ -384,11 +384,12 @@ class PoseFeatureEncoderTC(PoseFeatureEncoder):
     quarters of the UNet's FLOPs) run on the library's tcgen05 convolution kernel; the stride-2 4x4 encoder and the transposed
     convolutions of the shared decoder (small, latency bound) stay on the cuDNN CUDA-graph replay of the parent class."""
 
-    def __init__(self, state_dict: Dict, prefix: str = '', engine=None, in_hw=(256, 256), use_graph: bool = True):
+    def __init__(self, state_dict: Dict, prefix: str = '', engine=None, in_hw=(256, 256), use_graph: bool = True, deterministic: bool = False):
         import ctypes as C
         from .engine import default_engine
         self.engine = engine if engine is not None else default_engine()
-        super().__init__(state_dict, prefix=prefix, device=self.engine.device, use_graph=False, channels_last=True)
+        # `deterministic` concerns the cuDNN head only (its transposed convolutions may pick atomics-based algorithms); the tail always is
+        super().__init__(state_dict, prefix=prefix, device=self.engine.device, use_graph=False, channels_last=True, deterministic=deterministic)
         self.in_hw = tuple(in_hw)
         self.use_graph = bool(use_graph)
         prog, wbytes, params, self._in_counts = build_unet_tail_program(state_dict, prefix, in_hw)
