@@ -426,6 +426,107 @@ __global__ void __launch_bounds__(256) copy_slice_kernel(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 4x4 stride-2 (transposed) convolutions
+// The UNet's encoder (Conv2DBlock: 4x4, stride 2, padding 1, unets.py:8-29, 201-207) and shared decoder (UpConv2DBlock with
+// ConvTranspose2d 4x4, stride 2, padding 1, unets.py:32-58, 211-215) work on maps of 128^2 down to 2^2 pixels with up to 512 input channels:
+// 2.5 GFLOP of weight streaming over a handful of pixels. One split-K gather-GEMM on the CUDA cores, fp32 like the reference:
+//   out[m, n] = sum_k A[m, k] * Wk[cls][k, n],   k = tap * Ci + ci
+// stride-2 convolution: m = output pixel (qy, qx), 16 taps (ky, kx), input pixel (2 qy + ky - 1, 2 qx + kx - 1), one class;
+// transposed: four output-parity classes (ry, rx), m = (qy, qx) of the INPUT lattice, output pixel (2 qy + ry, 2 qx + rx), 4 taps (ty, tx)
+//   reading input pixel (qy + ry - ty, qx + rx - tx) with kernel element (ky, kx) = (1 - ry + 2 ty, 1 - rx + 2 tx) (packed by the host).
+// Block = 64 x 64 outputs over one K slice (grid.y = slices), thread = 4 x 4; partial sums go to a workspace that conv4_reduce_kernel
+// folds in slice order (deterministic), adding the bias (eval BatchNorm folded) and the LeakyReLU(0.2) the reference applies in place.
+struct Conv4Args {
+  const float* src; const float* w; float* part;
+  long long sp, sc;                  // source strides in floats: pixel, channel ((H,W,C) buffer: ld, 1; the caller's (C,H,W) input: 1, H*W)
+  int c_off, Hin, Win, Ci, Co, K, kc, wq, Mcls, Mtot, Wout, transposed, in_relu;
+};
+constexpr int C4_BM = 64, C4_BN = 64, C4_BK = 16;
+
+__global__ void __launch_bounds__(256) conv4_gemm_kernel(const Conv4Args a) {
+  __shared__ __align__(16) float As[C4_BK][C4_BM + 4];
+  __shared__ __align__(16) float Bs[C4_BK][C4_BN];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * C4_BN;
+  const int mtiles = (a.Mcls + C4_BM - 1) / C4_BM;
+  const int cls = blockIdx.z / mtiles, m0 = (blockIdx.z % mtiles) * C4_BM;
+  const int ry = cls >> 1, rx = cls & 1;
+  const int k_begin = blockIdx.y * a.kc, k_end = min(a.K, k_begin + a.kc);
+  // loader roles: A element (row (t >> 4) + 16 i, k = t & 15); B element (k = (t >> 6) + 4 i, column t & 63)
+  const int ak = t & 15, ar = t >> 4;
+  int qy[4], qx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ar + 16 * i;
+    qy[i] = m < a.Mcls ? m / a.wq : -(1 << 20);       // rows past the end gather nothing
+    qx[i] = m < a.Mcls ? m % a.wq : -(1 << 20);
+  }
+  const float* wbase = a.w + (size_t)cls * a.K * a.Co;
+  const int bn = t & 63, bk = t >> 6;
+  const int ty4 = (t >> 4) * 4, tx4 = (t & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = k_begin; k0 < k_end; k0 += C4_BK) {
+    {
+      const int k = k0 + ak;
+      const bool kin = k < k_end;
+      const int tap = kin ? k / a.Ci : 0, ci = k - tap * a.Ci;
+      int dy, dx;
+      if (a.transposed) { dy = ry - (tap >> 1); dx = rx - (tap & 1); }
+      else { dy = (tap >> 2) - 1; dx = (tap & 3) - 1; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int iy = a.transposed ? qy[i] + dy : 2 * qy[i] + dy, ix = a.transposed ? qx[i] + dx : 2 * qx[i] + dx;
+        float v = 0.f;
+        if (kin && iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win) v = __ldg(a.src + ((size_t)iy * a.Win + ix) * a.sp + a.c_off + (size_t)ci * a.sc);
+        As[ak][ar + 16 * i] = a.in_relu ? fmaxf(v, 0.f) : v;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = k0 + bk + 4 * i;
+        Bs[bk + 4 * i][bn] = (kk < k_end && n0 + bn < a.Co) ? __ldg(wbase + (size_t)kk * a.Co + n0 + bn) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < C4_BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx4]);
+      const float am[4] = {av.x, av.y, av.z, av.w}, bm[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bm[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (n0 + tx4 >= a.Co) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty4 + i;
+    if (m >= a.Mcls) continue;
+    const int my = m / a.wq, mx = m % a.wq;
+    const int opix = a.transposed ? (2 * my + ry) * a.Wout + 2 * mx + rx : m;
+    *reinterpret_cast<float4*>(a.part + ((size_t)blockIdx.y * a.Mtot + opix) * a.Co + n0 + tx4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+}
+
+// dst[m, c_off + n] = act(sum_s part[s][m][n] + bias[n]), slices added in order; act = LeakyReLU(0.2) when `leaky`
+__global__ void __launch_bounds__(256) conv4_reduce_kernel(const float4* __restrict__ part, int S, int64_t mn4, int Co, const float* __restrict__ bias, int leaky,
+                                                           float* __restrict__ dst, int ld, int c_off) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = part[i];
+    for (int s = 1; s < S; ++s) { const float4 p = part[(int64_t)s * mn4 + i]; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    const int64_t e = i * 4; const int n = (int)(e % Co); const int64_t m = e / Co;
+    if (bias) { v.x += bias[n]; v.y += bias[n + 1]; v.z += bias[n + 2]; v.w += bias[n + 3]; }
+    if (leaky) { v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y; v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w; }
+    *reinterpret_cast<float4*>(dst + m * ld + c_off + n) = v;
+  }
+}
+
 // HGFilter.conv1: 7x7, stride 2, padding 3, 6 -> 64 channels, with bias (HGFilters.py:136, 180), fp32 on the CUDA cores (1.2 GMAC).
 // in: (6, Hin, Win) f32 (the reference's NCHW input), out: (Hin/2, Win/2, 64) f32. Block = 16x16 output pixels, thread = 1 pixel,
 // weights staged per 8-output-channel group.
@@ -500,9 +601,11 @@ int make_tmap(avc_ctx* ctx, CUtensorMap* m, const void* base, uint64_t d0, uint6
 
 // ------------------------------------------------------------------------------------------------ the op program
 // One op = 16 int32: [kind, a0..a14]. Buffers are numbered; f32 buffers and fp16 plane pairs live in one arena each.
-enum { ENC_OP_STEM = 1, ENC_OP_GN = 2, ENC_OP_CONV = 3, ENC_OP_ADD = 4, ENC_OP_POOL = 5, ENC_OP_UPADD = 6, ENC_OP_INPUT = 7, ENC_OP_UPSPLIT = 8, ENC_OP_COPY = 9 };
+enum { ENC_OP_STEM = 1, ENC_OP_GN = 2, ENC_OP_CONV = 3, ENC_OP_ADD = 4, ENC_OP_POOL = 5, ENC_OP_UPADD = 6, ENC_OP_INPUT = 7, ENC_OP_UPSPLIT = 8, ENC_OP_COPY = 9,
+       ENC_OP_CONV4 = 10 };
 
 struct EncConv { CUtensorMap a_hi, a_lo, b_hi, b_lo; ConvArgs args; size_t smem; int grid; };
+struct EncConv4 { Conv4Args args; dim3 grid; int S; };
 
 struct avc_encoder {
   avc_ctx* ctx = nullptr;
@@ -513,6 +616,8 @@ struct avc_encoder {
   float* d_f32 = nullptr; __half* d_planes = nullptr; unsigned char* d_weights = nullptr; float* d_params = nullptr;
   double* d_partial = nullptr; unsigned int* d_ticket = nullptr; float* d_stats = nullptr;
   std::vector<EncConv> convs;               // one per ENC_OP_CONV, in op order
+  std::vector<EncConv4> conv4s;             // one per ENC_OP_CONV4, in op order
+  float* d_ws = nullptr;                    // split-K partial sums of the 4x4 convolutions
   int in_c = 0, in_h = 0, in_w = 0, out_buf = 0, out_c = 0, out_h = 0, out_w = 0;
   cudaGraphExec_t graph = nullptr; const float* graph_in = nullptr; float* graph_out = nullptr;
   int64_t launches_per_run = 0;
@@ -528,6 +633,7 @@ static void enc_free(avc_encoder* e) {
   if (e->d_partial) cudaFree(e->d_partial);
   if (e->d_ticket) cudaFree(e->d_ticket);
   if (e->d_stats) cudaFree(e->d_stats);
+  if (e->d_ws) cudaFree(e->d_ws);
   delete e;
 }
 
@@ -575,6 +681,7 @@ extern "C" int avc_encoder_create(avc_ctx* ctx, const int32_t* program, int64_t 
   ENC_CUDA(cudaMalloc(&e->d_ticket, 64)); ENC_CUDA(cudaMemset(e->d_ticket, 0, 64));
   ENC_CUDA(cudaMalloc(&e->d_stats, 64 * sizeof(float)));
   // tensor maps + launch geometry of every convolution; buffer / plane indices of every op
+  size_t ws_floats = 0;
   for (int o = 0; o < nops; ++o) {
     const int32_t* op = ops + 16 * o;
     auto bad = [&](const char* what) { return fail(avc_fail(ctx, AVC_EFORMAT, "encoder program: op %d (%d): %s", o, op[0], what)); };
@@ -589,6 +696,34 @@ extern "C" int avc_encoder_create(avc_ctx* ctx, const int32_t* program, int64_t 
       case ENC_OP_UPSPLIT: if (!buf_ok(op[1]) || op[8] < 0 || op[8] >= np || (op[4] & 3) || (int64_t)4 * op[2] * op[3] != pl[2 * op[8]]) return bad("buffer / plane"); break;
       case ENC_OP_COPY: if (!buf_ok(op[1]) || !buf_ok(op[2]) || (op[4] & 3) || (int64_t)op[3] * op[5] > sizes[op[2]]) return bad("buffer index / size"); break;
       case ENC_OP_CONV: break;
+      case ENC_OP_CONV4: {
+        // [10, src_buf (-1: the caller's (C,H,W) input), dst_buf, Hin, Win, Ci, ld_src, c_off_src, Co, ld_dst, c_off_dst, w_off (params), bias_off (-1),
+        //  flags: 1 = transposed (ConvTranspose2d 4x4 s2 p1: out 2Hin x 2Win; else Conv2d 4x4 s2 p1: out Hin/2 x Win/2), 2 = ReLU on the input, 4 = LeakyReLU(0.2) out]
+        const int src = op[1], Hin = op[3], Win = op[4], Ci = op[5], lds = op[6], cos = op[7], Co = op[8], ldd = op[9], cod = op[10], flags = op[13];
+        const bool tr = flags & 1;
+        if (src < -1 || src >= nb || !buf_ok(op[2]) || src == op[2]) return bad("buffer index");
+        if (Hin < 1 || Win < 1 || Ci < 1 || Co < 4 || (Co & 3) || (!tr && ((Hin | Win) & 1)) || (flags & ~7)) return bad("shape / flags");
+        const int Ho = tr ? 2 * Hin : Hin / 2, Wo = tr ? 2 * Win : Win / 2;
+        if (src >= 0 ? (cos < 0 || cos + Ci > lds || (int64_t)Hin * Win * lds > sizes[src]) : (Ci != e->in_c || Hin != e->in_h || Win != e->in_w)) return bad("input slice");
+        if ((ldd & 3) || (cod & 3) || cod < 0 || cod + Co > ldd || (int64_t)Ho * Wo * ldd > sizes[op[2]]) return bad("output slice");
+        const int64_t K = (int64_t)(tr ? 4 : 16) * Ci, nw = (tr ? 4 : 1) * K * Co;
+        if ((K & 15) || op[11] < 0 || op[11] + nw > n_params || (op[12] >= 0 && op[12] + Co > n_params)) return bad("weight / bias offset");
+        EncConv4 c;
+        Conv4Args& a = c.args;
+        a.src = src >= 0 ? e->f32_bufs[src] : nullptr; a.w = e->d_params + op[11]; a.part = nullptr;
+        a.sp = src >= 0 ? lds : 1; a.sc = src >= 0 ? 1 : (long long)Hin * Win; a.c_off = src >= 0 ? cos : 0;
+        a.Hin = Hin; a.Win = Win; a.Ci = Ci; a.Co = Co; a.K = (int)K; a.wq = tr ? Win : Wo; a.Mcls = tr ? Hin * Win : Ho * Wo; a.Mtot = Ho * Wo; a.Wout = Wo;
+        a.transposed = tr; a.in_relu = (flags >> 1) & 1;
+        const int tiles = ((Co + C4_BN - 1) / C4_BN) * ((a.Mcls + C4_BM - 1) / C4_BM) * (tr ? 4 : 1);
+        int S = (4 * ctx->sm_count + tiles - 1) / tiles;          // 4 resident blocks per SM (64 registers x 256 threads) if (S > (int)(K / 64)) S = (int)(K / 64); if (S < 1) S = 1;
+        a.kc = (int)(((K + S - 1) / S + C4_BK - 1) / C4_BK) * C4_BK;
+        S = (int)((K + a.kc - 1) / a.kc);
+        c.S = S; c.grid = dim3((Co + C4_BN - 1) / C4_BN, S, ((a.Mcls + C4_BM - 1) / C4_BM) * (tr ? 4 : 1));
+        const size_t need = (size_t)S * a.Mtot * Co;
+        if (need > ws_floats) ws_floats = need;
+        e->conv4s.push_back(c);
+        break;
+      }
       default: return bad("unknown op");
     }
     if (op[0] != ENC_OP_CONV) continue;
@@ -621,6 +756,10 @@ extern "C" int avc_encoder_create(avc_ctx* ctx, const int32_t* program, int64_t 
     c.grid = a.n_tiles < ctx->sm_count ? a.n_tiles : ctx->sm_count;
     e->convs.push_back(c);
   }
+  if (ws_floats) {
+    ENC_CUDA(cudaMalloc(&e->d_ws, ws_floats * sizeof(float)));
+    for (auto& c : e->conv4s) c.args.part = e->d_ws;
+  }
   cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
   if (ce != cudaSuccess) return fail(avc_check_cuda(ctx, ce, "cudaFuncSetAttribute(conv_tc_kernel)"));
 #undef ENC_CUDA
@@ -632,7 +771,7 @@ extern "C" int avc_encoder_create(avc_ctx* ctx, const int32_t* program, int64_t 
 static int enc_enqueue(avc_encoder* e, const float* in, float* outp, cudaStream_t st, int64_t* n_launch) {
   avc_ctx* ctx = e->ctx;
   const int nops = (int)(e->ops.size() / 16);
-  int conv_i = 0;
+  int conv_i = 0, conv4_i = 0;
   int64_t nl = 0;
   auto blocks_for = [&](int64_t n) { int64_t b = (n + 255) / 256; const int64_t cap = (int64_t)ctx->sm_count * 8; return (int)(b < cap ? (b > 0 ? b : 1) : cap); };
   for (int o = 0; o < nops; ++o) {
@@ -693,6 +832,16 @@ static int enc_enqueue(avc_encoder* e, const float* in, float* outp, cudaStream_
       case ENC_OP_COPY: {       // [9, src_buf, dst_buf, P, C, ld_dst, c_off_dst]
         copy_slice_kernel<<<blocks_for((int64_t)op[3] * op[4] / 4), 256, 0, st>>>(e->f32_bufs[op[1]], e->f32_bufs[op[2]], (int64_t)op[3], op[4], op[5], op[6]);
         ++nl; break;
+      }
+      case ENC_OP_CONV4: {      // see avc_encoder_create
+        EncConv4& c = e->conv4s[conv4_i++];
+        Conv4Args a = c.args;
+        if (op[1] < 0) a.src = in;
+        conv4_gemm_kernel<<<c.grid, 256, 0, st>>>(a);
+        const int64_t mn4 = (int64_t)a.Mtot * a.Co / 4;
+        conv4_reduce_kernel<<<blocks_for(mn4), 256, 0, st>>>(reinterpret_cast<const float4*>(a.part), c.S, mn4, a.Co, op[12] >= 0 ? e->d_params + op[12] : nullptr,
+                                                            (op[13] >> 2) & 1, e->f32_bufs[op[2]], op[9], op[10]);
+        nl += 2; break;
       }
       default: return avc_fail(ctx, AVC_EFORMAT, "encoder program: unknown op %d", op[0]);
     }

@@ -202,7 +202,7 @@ class ImageFeatureEncoder:
 # buffers and packs the weights (fp16 hi / lo planes, (C_out, taps, C_in) K-major, power-of-two pre-scale); every arithmetic
 # operation runs in the CUDA library: tcgen05 implicit-GEMM convolutions fed by TMA tensor loads, GroupNorm, pooling, bicubic
 # up-sampling and the 7x7 stem as kernels of ours, all captured in one CUDA graph.
-OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD, OP_INPUT, OP_UPSPLIT, OP_COPY = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD, OP_INPUT, OP_UPSPLIT, OP_COPY, OP_CONV4 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 
 class _Program:
@@ -337,17 +337,12 @@ def build_hgfilter_program(state_dict: Dict, prefix: str = '', in_hw=(512, 512))
     return pr.pack((6, Hin, Win), out, (H, W, 32))
 
 
-def build_unet_tail_program(state_dict: Dict, prefix: str = '', out_hw=(256, 256)):
-    """The three `UpConv2DBlock(up_mode='upsample')` stages that end UnetNoCond7DS.forward (unets.py:217-219: upconvC5, upconvC6,
-    upconvC7 = relu -> bilinear x2 -> 3x3 convolution (+ eval BatchNorm, folded) [-> cat skip]) as a library program: 7.8 of the UNet's
-    10.5 GFLOP. Input = one flat f32 buffer [u4 (H/8, W/8, 384) | a2 (H/4, W/4, 64) | a1 (H/2, W/2, 32)], all (H, W, C) order; output
-    (H, W, 64). -> (program, weights, params, input float counts)."""
-    g = lambda k: np.asarray(state_dict[prefix + k].detach().cpu().numpy() if hasattr(state_dict[prefix + k], 'detach') else state_dict[prefix + k], np.float64)   # noqa: E731
-    H, W = out_hw
-    if H % 128 or W % 128:
-        raise ValueError('the UNet needs H, W multiples of 128')
-    pr = _Program()
+def _unet_getter(state_dict, prefix):
+    return lambda k: np.asarray(state_dict[prefix + k].detach().cpu().numpy() if hasattr(state_dict[prefix + k], 'detach') else state_dict[prefix + k], np.float64)   # noqa: E731
 
+
+def _emit_unet_tail(pr: '_Program', g, u4: int, a2: int, a1: int, H: int, W: int) -> int:
+    """upconvC5 / C6 / C7 (unets.py:217-219) on buffers u4 (H/8, W/8, 384), a2 (H/4, W/4, 64), a1 (H/2, W/2, 32) -> the output buffer (H, W, 64)"""
     def folded(name, bn):
         w = g(name + '.up.1.weight'); b = g(name + '.up.1.bias')
         if bn:
@@ -356,9 +351,6 @@ def build_unet_tail_program(state_dict: Dict, prefix: str = '', out_hw=(256, 256
         return w.astype(np.float32), b.astype(np.float32)
 
     h8, w8, h4, w4, h2, w2 = H // 8, W // 8, H // 4, W // 4, H // 2, W // 2
-    n_u4, n_a2, n_a1 = h8 * w8 * 384, h4 * w4 * 64, h2 * w2 * 32
-    u4 = pr.buf(n_u4); a2 = pr.buf(n_a2); a1 = pr.buf(n_a1)
-    pr.op(OP_INPUT, u4, 0, n_u4); pr.op(OP_INPUT, a2, n_u4, n_a2); pr.op(OP_INPUT, a1, n_u4 + n_a2, n_a1)
     # upconvC5: relu(u4) -> up -> conv 384 -> 64 (+bn) ; cat a2
     c5 = pr.buf(h4 * w4 * 128)
     pr.op(OP_UPSPLIT, u4, h8, w8, 384, 384, 0, 1, pr.plane(h4 * w4, 384))
@@ -376,31 +368,129 @@ def build_unet_tail_program(state_dict: Dict, prefix: str = '', out_hw=(256, 256
     pr.op(OP_UPSPLIT, c6, h2, w2, 64, 64, 0, 1, pr.plane(H * W, 64))
     wt, b = folded('upconvC7', False); off, s_, cpad, boff = pr.conv_weight_bias(wt, b)
     pr.op(OP_CONV, pr.plane(H * W, 64), off, out, H, W, cpad, 64, 9, 0, 64, 0, boff, s_)
+    return out
+
+
+def build_unet_tail_program(state_dict: Dict, prefix: str = '', out_hw=(256, 256)):
+    """The three `UpConv2DBlock(up_mode='upsample')` stages that end UnetNoCond7DS.forward (unets.py:217-219: upconvC5, upconvC6,
+    upconvC7 = relu -> bilinear x2 -> 3x3 convolution (+ eval BatchNorm, folded) [-> cat skip]) as a library program: 7.8 of the UNet's
+    10.5 GFLOP. Input = one flat f32 buffer [u4 (H/8, W/8, 384) | a2 (H/4, W/4, 64) | a1 (H/2, W/2, 32)], all (H, W, C) order; output
+    (H, W, 64). -> (program, weights, params, input float counts)."""
+    g = _unet_getter(state_dict, prefix)
+    H, W = out_hw
+    if H % 128 or W % 128:
+        raise ValueError('the UNet needs H, W multiples of 128')
+    pr = _Program()
+    n_u4, n_a2, n_a1 = (H // 8) * (W // 8) * 384, (H // 4) * (W // 4) * 64, (H // 2) * (W // 2) * 32
+    u4 = pr.buf(n_u4); a2 = pr.buf(n_a2); a1 = pr.buf(n_a1)
+    pr.op(OP_INPUT, u4, 0, n_u4); pr.op(OP_INPUT, a2, n_u4, n_a2); pr.op(OP_INPUT, a1, n_u4 + n_a2, n_a1)
+    out = _emit_unet_tail(pr, g, u4, a2, a1, H, W)
     return pr.pack((n_u4 + n_a2 + n_a1, 1, 1), out, (H, W, 64)) + ((n_u4, n_a2, n_a1),)
 
 
-class PoseFeatureEncoderTC(PoseFeatureEncoder):
-    """PoseFeatureEncoder whose three final up-sampling stages (upconvC5 / C6 / C7: 3x3 convolutions at 64^2, 128^2 and 256^2, three
-    quarters of the UNet's FLOPs) run on the library's tcgen05 convolution kernel; the stride-2 4x4 encoder and the transposed
-    convolutions of the shared decoder (small, latency bound) stay on the cuDNN CUDA-graph replay of the parent class."""
+def pack_conv4_weight(w: np.ndarray, transposed: bool) -> np.ndarray:
+    """4x4 stride-2 kernels in the K-major order csrc/conv_tc.cu conv4_gemm_kernel streams: Conv2d weight (Co, Ci, 4, 4) ->
+    [(ky*4 + kx) * Ci + ci][co]; ConvTranspose2d weight (Ci, Co, 4, 4) -> four output-parity classes (ry, rx), each
+    [(ty*2 + tx) * Ci + ci][co] holding kernel element (ky, kx) = (1 - ry + 2 ty, 1 - rx + 2 tx)."""
+    w = np.asarray(w, np.float32)
+    if not transposed:
+        co, ci = w.shape[:2]
+        return np.ascontiguousarray(w.transpose(2, 3, 1, 0)).reshape(16 * ci, co)
+    ci, co = w.shape[:2]
+    out = np.empty((4, 4 * ci, co), np.float32)
+    for ry in range(2):
+        for rx in range(2):
+            for ty in range(2):
+                for tx in range(2):
+                    out[ry * 2 + rx, (ty * 2 + tx) * ci:(ty * 2 + tx + 1) * ci] = w[:, :, 1 - ry + 2 * ty, 1 - rx + 2 * tx]
+    return out
 
-    def __init__(self, state_dict: Dict, prefix: str = '', engine=None, in_hw=(256, 256), use_graph: bool = True, deterministic: bool = False):
+
+def build_unet_program(state_dict: Dict, prefix: str = '', in_hw=(256, 256)):
+    """All of UnetNoCond7DS.forward (unets.py:201-219) as ONE library program: conv1..7 (4x4 stride-2 convolutions, eval BatchNorm folded,
+    in-place LeakyReLU), upconv1, 2, 3, 3 (transposed 4x4 stride-2 convolutions on relu(cat)) as split-K fp32 gather-GEMMs (OP_CONV4),
+    then upconvC5 / C6 / C7 on the tcgen05 convolution. Every encoder output is written straight into the channel slice of the concatenated
+    buffer its skip connection feeds (the reference's torch.cat), and read from there by the next encoder level.
+    Input (6, H, W) as the reference feeds it, output (H, W, 64). -> (program, weights, params)."""
+    g = _unet_getter(state_dict, prefix)
+    H, W = in_hw
+    if H % 128 or W % 128:
+        raise ValueError('the UNet needs H, W multiples of 128')
+    pr = _Program()
+
+    def fold(wkey, bnkey, transposed=False):
+        w = g(wkey)
+        if bnkey is None:
+            return w.astype(np.float32), None
+        s = 1.0 / np.sqrt(g(bnkey + '.running_var') + BN_EPS)
+        w = w * (s[None, :, None, None] if transposed else s[:, None, None, None])
+        return w.astype(np.float32), (-g(bnkey + '.running_mean') * s).astype(np.float32)
+
+    def conv4(src, dst, hin, win, ci, ld_src, c_off_src, co, ld_dst, c_off_dst, wb, transposed=False, in_relu=False, leaky=False):
+        w, b = wb
+        assert w.shape[:2] == ((ci, co) if transposed else (co, ci)), (w.shape, ci, co)
+        pr.op(OP_CONV4, src, dst, hin, win, ci, ld_src, c_off_src, co, ld_dst, c_off_dst, pr.param(pack_conv4_weight(w, transposed)),
+              -1 if b is None else pr.param(b), (1 if transposed else 0) | (2 if in_relu else 0) | (4 if leaky else 0))
+
+    down = [fold('conv%d.conv.weight' % i, 'conv%d.bn' % i if 2 <= i <= 6 else None) for i in range(1, 8)]
+    up = [fold('upconv%d.up.weight' % i, 'upconv%d.bn' % i, transposed=True) for i in (1, 2, 3)]
+    hs = [H >> i for i in range(8)]; ws = [W >> i for i in range(8)]            # extent after i stride-2 levels
+    a1 = pr.buf(hs[1] * ws[1] * 32)                 # d1 (skip of upconvC6)
+    a2 = pr.buf(hs[2] * ws[2] * 64)                 # d2 (skip of upconvC5)
+    cat4 = pr.buf(hs[3] * ws[3] * 384)              # [upconv3(u3) 256 | d3 128] = u4
+    cat3 = pr.buf(hs[4] * ws[4] * 512)              # [upconv3(u2) 256 | d4 256]
+    cat2 = pr.buf(hs[5] * ws[5] * 512)              # [upconv2(u1) 256 | d5 256]
+    cat1 = pr.buf(hs[6] * ws[6] * 512)              # [upconv1(d7) 256 | d6 256]
+    d7 = pr.buf(hs[7] * ws[7] * 256)
+    conv4(-1, a1, H, W, 6, 0, 0, 32, 32, 0, down[0], leaky=True)
+    conv4(a1, a2, hs[1], ws[1], 32, 32, 0, 64, 64, 0, down[1], leaky=True)
+    conv4(a2, cat4, hs[2], ws[2], 64, 64, 0, 128, 384, 256, down[2], leaky=True)
+    conv4(cat4, cat3, hs[3], ws[3], 128, 384, 256, 256, 512, 256, down[3], leaky=True)
+    conv4(cat3, cat2, hs[4], ws[4], 256, 512, 256, 256, 512, 256, down[4], leaky=True)
+    conv4(cat2, cat1, hs[5], ws[5], 256, 512, 256, 256, 512, 256, down[5], leaky=True)
+    conv4(cat1, d7, hs[6], ws[6], 256, 512, 256, 256, 256, 0, down[6])
+    conv4(d7, cat1, hs[7], ws[7], 256, 256, 0, 256, 512, 0, up[0], transposed=True, in_relu=True)
+    conv4(cat1, cat2, hs[6], ws[6], 512, 512, 0, 256, 512, 0, up[1], transposed=True, in_relu=True)
+    conv4(cat2, cat3, hs[5], ws[5], 512, 512, 0, 256, 512, 0, up[2], transposed=True, in_relu=True)
+    conv4(cat3, cat4, hs[4], ws[4], 512, 512, 0, 256, 384, 0, up[2], transposed=True, in_relu=True)          # upconv3 AGAIN (unets.py:215)
+    out = _emit_unet_tail(pr, g, cat4, a2, a1, H, W)
+    return pr.pack((6, H, W), out, (H, W, 64))
+
+
+class PoseFeatureEncoderTC(PoseFeatureEncoder):
+    """PoseFeatureEncoder on kernels of this library: same call, same result layout.
+
+    head='library' (default): the whole UNet is ONE program (build_unet_program): the 4x4 stride-2 encoder and the transposed
+    convolutions of the shared decoder as split-K fp32 gather-GEMMs (weight streaming over 2^2 .. 128^2 pixels; cuDNN spends 1.35 ms there
+    on grids of 8-16 blocks), the three final 3x3 stages (three quarters of the FLOPs) on the tcgen05 convolution kernel; one CUDA graph.
+    head='cudnn': the stride-2 / transposed head on the cuDNN CUDA-graph replay of the parent class, only the tail in the library (A/B)."""
+
+    def __init__(self, state_dict: Dict, prefix: str = '', engine=None, in_hw=(256, 256), use_graph: bool = True, deterministic: bool = False,
+                 head: str = 'library'):
         import ctypes as C
         from .engine import default_engine
+        if head not in ('library', 'cudnn'):
+            raise ValueError("head must be 'library' or 'cudnn'")
         self.engine = engine if engine is not None else default_engine()
-        # `deterministic` concerns the cuDNN head only (its transposed convolutions may pick atomics-based algorithms); the tail always is
-        super().__init__(state_dict, prefix=prefix, device=self.engine.device, use_graph=False, channels_last=True, deterministic=deterministic)
+        self.head = head
         self.in_hw = tuple(in_hw)
         self.use_graph = bool(use_graph)
-        prog, wbytes, params, self._in_counts = build_unet_tail_program(state_dict, prefix, in_hw)
+        if head == 'cudnn':
+            # `deterministic` concerns the cuDNN head only (its transposed convolutions may pick atomics-based algorithms); the library is
+            super().__init__(state_dict, prefix=prefix, device=self.engine.device, use_graph=False, channels_last=True, deterministic=deterministic)
+            prog, wbytes, params, self._in_counts = build_unet_tail_program(state_dict, prefix, in_hw)
+            self._tail_in = torch.empty(sum(self._in_counts), device=self.device, dtype=torch.float32)
+            self._head = _GraphedForward(self._forward_head, self.device, use_graph)
+        else:
+            self.device = self.engine.device
+            prog, wbytes, params = build_unet_program(state_dict, prefix, in_hw)
+            self._in = torch.empty((6,) + self.in_hw, device=self.device, dtype=torch.float32)
         h = C.c_void_p()
         e = self.engine
         e._check(e.lib.avc_encoder_create(e._h, prog.ctypes.data_as(C.c_void_p), len(prog), wbytes, len(wbytes), params.ctypes.data_as(C.c_void_p),
                                           len(params), C.byref(h)))
         self._h = h
-        self._tail_in = torch.empty(sum(self._in_counts), device=self.device, dtype=torch.float32)
         self._out = torch.empty((in_hw[0], in_hw[1], 64), device=self.device, dtype=torch.float32)
-        self._head = _GraphedForward(self._forward_head, self.device, use_graph)
 
     def _forward_head(self, x: torch.Tensor) -> torch.Tensor:
         """conv1..7 + the shared decoder (unets.py:201-215) on cuDNN; writes [u4 | a2 | a1] in (H, W, C) order into the tail's input buffer"""
@@ -436,9 +526,14 @@ class PoseFeatureEncoderTC(PoseFeatureEncoder):
         x = torch.as_tensor(smpl_pos_map)
         if x.dim() != 4 or x.shape[0] != 1 or x.shape[1] != 6 or tuple(x.shape[2:]) != self.in_hw:
             raise ValueError('smpl_pos_map must be (1,6,%d,%d), got %s' % (self.in_hw + (tuple(x.shape),)))
-        self._head(x)
+        if self.head == 'cudnn':
+            self._head(x)
+            src = self._tail_in
+        else:
+            self._in.copy_(x[0].to(device=self.device, dtype=torch.float32))          # (6,H,W) as the reference feeds it; a stable pointer for the graph
+            src = self._in
         e = self.engine
-        e._check(e.lib.avc_encoder_run(self._h, C.c_void_p(self._tail_in.data_ptr()), C.c_void_p(self._out.data_ptr()), int(self.use_graph), e._stream()))
+        e._check(e.lib.avc_encoder_run(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(self._out.data_ptr()), int(self.use_graph), e._stream()))
         return self._out.permute(2, 0, 1)[None]            # (1,64,H,W) view with channels_last strides; overwritten by the next call
 
 

@@ -60,16 +60,19 @@ def main():
     print('HGFilter: tcgen05 eager %.3f ms, tcgen05 graph %.3f ms, cuDNN f32 graph %.3f ms' % (timed(lambda: tc(y)), timed(lambda: tcg(y)), timed(lambda: refg(y))))
     o2 = tcg(y).clone(); o3 = tcg(y).clone()
     print('graph == eager: %s, replay deterministic: %s' % (bool(torch.equal(o2, out)), bool(torch.equal(o2, o3))))
-    # UNet: cuDNN head + tcgen05 tail
+    # UNet: the whole network as a library program (head='library') and cuDNN head + library tail (head='cudnn')
     xs = torch.from_numpy(synth.smpl_pos_map()).cuda()
     usd = synth.unet_state_dict()
-    utc = encoders.PoseFeatureEncoderTC(usd, engine=eng)
     uref = encoders.PoseFeatureEncoder(usd, device='cuda', use_graph=True)
-    uo = utc(xs).clone(); ur = uref(xs).clone()
-    samp = uo[0].reshape(64, -1)[:, torch.from_numpy(g['pose_idx']).cuda()].cpu().numpy()
-    print('UNet tcgen05 tail: vs cuDNN f32 max-abs %.3e, vs the reference golden %.3e (range %.3g .. %.3g)' % (
-        float((uo - ur).abs().max()), float(np.abs(samp - g['pose_feat']).max()), float(ur.min()), float(ur.max())))
-    print('UNet: cuDNN head + tcgen05 tail %.3f ms, all-cuDNN f32 graph %.3f ms' % (timed(lambda: utc(xs)), timed(lambda: uref(xs))))
+    ur = uref(xs).clone()
+    for head in ('library', 'cudnn'):
+        utc = encoders.PoseFeatureEncoderTC(usd, engine=eng, head=head)
+        uo = utc(xs).clone()
+        samp = uo[0].reshape(64, -1)[:, torch.from_numpy(g['pose_idx']).cuda()].cpu().numpy()
+        print('UNet head=%s: vs cuDNN f32 max-abs %.3e, vs the reference golden %.3e (range %.3g .. %.3g); %.3f ms (all-cuDNN f32 graph %.3f ms)' % (
+            head, float((uo - ur).abs().max()), float(np.abs(samp - g['pose_feat']).max()), float(ur.min()), float(ur.max()),
+            timed(lambda: utc(xs)), timed(lambda: uref(xs))))
+        utc.close()
 
 
 if __name__ == '__main__':

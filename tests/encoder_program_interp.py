@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD, OP_INPUT, OP_UPSPLIT, OP_COPY = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OP_STEM, OP_GN, OP_CONV, OP_ADD, OP_POOL, OP_UPADD, OP_INPUT, OP_UPSPLIT, OP_COPY, OP_CONV4 = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 
 def run_program(prog: np.ndarray, weights: bytes, params: np.ndarray, x_chw: np.ndarray) -> np.ndarray:
@@ -80,6 +80,41 @@ def run_program(prog: np.ndarray, weights: bytes, params: np.ndarray, x_chw: np.
         elif k == OP_COPY:
             src, dst, P, C, ld, c_off = (int(v) for v in op[1:7])
             bufs[dst][:P * ld].view(P, ld)[:, c_off:c_off + C] = bufs[src][:P * C].view(P, C)
+        elif k == OP_CONV4:
+            # the gather-GEMM of csrc/conv_tc.cu conv4_gemm_kernel, index formulas transcribed (NOT F.conv2d): what is pinned here is the
+            # tap -> input pixel map, the output-parity classes of the transposed convolution and the K-major weight packing
+            src, dst, Hin, Win, Ci, lds, cos, Co, ldd, cod, w_off, b_off, flags = (int(v) for v in op[1:14])
+            tr = flags & 1
+            X = (bufs[src][:Hin * Win * lds].view(Hin, Win, lds)[:, :, cos:cos + Ci] if src >= 0 else x.permute(1, 2, 0)).contiguous()
+            if flags & 2:
+                X = torch.relu(X)
+            Ho, Wo = (2 * Hin, 2 * Win) if tr else (Hin // 2, Win // 2)
+            ntaps, ncls = (4, 4) if tr else (16, 1)
+            K = ntaps * Ci
+            Wk = torch.from_numpy(params[w_off:w_off + ncls * K * Co].reshape(ncls, K, Co).copy())
+            hq, wq = (Hin, Win) if tr else (Ho, Wo)
+            qy = torch.arange(hq)[:, None].expand(hq, wq); qx = torch.arange(wq)[None, :].expand(hq, wq)
+            Y = torch.zeros(Ho, Wo, Co)
+            for cls in range(ncls):
+                ry, rx = cls >> 1, cls & 1
+                A = torch.zeros(hq, wq, ntaps, Ci)
+                for tap in range(ntaps):
+                    if tr:
+                        iy = qy + (ry - (tap >> 1)); ix = qx + (rx - (tap & 1))
+                    else:
+                        iy = 2 * qy + ((tap >> 2) - 1); ix = 2 * qx + ((tap & 3) - 1)
+                    ok = (iy >= 0) & (iy < Hin) & (ix >= 0) & (ix < Win)
+                    A[:, :, tap] = X[iy.clamp(0, Hin - 1), ix.clamp(0, Win - 1)] * ok[:, :, None]
+                y = (A.reshape(hq * wq, K) @ Wk[cls]).view(hq, wq, Co)
+                if tr:
+                    Y[ry::2, rx::2] = y
+                else:
+                    Y = y
+            if b_off >= 0:
+                Y = Y + torch.from_numpy(params[b_off:b_off + Co].copy())
+            if flags & 4:
+                Y = F.leaky_relu(Y, 0.2)
+            bufs[dst][:Ho * Wo * ldd].view(Ho * Wo, ldd)[:, cod:cod + Co] = Y.reshape(Ho * Wo, Co)
         else:
             raise ValueError('unknown op %d' % k)
     return bufs[out_buf][:out_h * out_w * out_c].view(out_h, out_w, out_c).numpy()

@@ -127,9 +127,46 @@ def test_unet_tail_program_interpreted_on_the_cpu_vs_golden():
     assert err < 5e-6
 
 
+def test_unet_whole_program_interpreted_on_the_cpu_vs_golden():
+    """The whole UNet as one library program (encoders.build_unet_program): the 4x4 stride-2 and transposed convolutions as the gather-GEMM
+    of conv4_gemm_kernel -- the interpreter transcribes its index formulas, it does not call F.conv2d for them -- with every skip written
+    into the channel slice of its concatenated buffer, then the tcgen05 tail; against the reference's own UnetNoCond7DS output."""
+    import encoder_program_interp as interp
+    g = load_golden('encoder_golden.npz')
+    prog, wbytes, params = encoders.build_unet_program(synth.unet_state_dict())
+    assert tuple(prog[4:7]) == (6, 256, 256) and tuple(prog[8:11]) == (64, 256, 256)
+    assert sum(1 for o in prog[16 + prog[1] + 2 * prog[2]:].reshape(-1, 16) if o[0] == encoders.OP_CONV4) == 11
+    out = interp.run_program(prog, wbytes, params, synth.smpl_pos_map()[0])
+    assert _report('unet program on the CPU interpreter', out.reshape(-1, 64)[g['pose_idx']].T, g['pose_feat']) < 5e-6
+
+
+def test_conv4_weight_packing_matches_torch():
+    """pack_conv4_weight + the interpreter's gather-GEMM == F.conv2d / F.conv_transpose2d (4x4, stride 2, padding 1) on odd shapes: non-square
+    maps, a 1-pixel-high input of the transposed convolution, channel slices of wider buffers, ReLU in / LeakyReLU out."""
+    import torch.nn.functional as F
+    import encoder_program_interp as interp
+    rs = np.random.RandomState(5)
+    for tr, hin, win, ci, co in ((False, 6, 10, 8, 12), (True, 1, 3, 4, 8), (True, 5, 2, 12, 4), (False, 2, 2, 20, 4)):
+        pr = encoders._Program()
+        w = rs.randn(*((ci, co, 4, 4) if tr else (co, ci, 4, 4))).astype(np.float32); b = rs.randn(co).astype(np.float32)
+        ho, wo = (2 * hin, 2 * win) if tr else (hin // 2, win // 2)
+        src = pr.buf(hin * win * (ci + 8)); dst = pr.buf(ho * wo * (co + 4)); pr.plane(1, 64)
+        x = rs.randn(hin, win, ci + 8).astype(np.float32)
+        pr.op(encoders.OP_INPUT, src, 0, x.size)
+        pr.op(encoders.OP_CONV4, src, dst, hin, win, ci, ci + 8, 4, co, co + 4, 4, pr.param(encoders.pack_conv4_weight(w, tr)), pr.param(b), (1 if tr else 0) | 2 | 4)
+        prog, wb, params = pr.pack((x.size, 1, 1), dst, (ho, wo, co + 4))
+        got = interp.run_program(prog, wb, params, x.reshape(-1, 1, 1))[:, :, 4:]
+        xin = torch.relu(torch.from_numpy(x[:, :, 4:4 + ci])).permute(2, 0, 1)[None]
+        ref = (F.conv_transpose2d if tr else F.conv2d)(xin, torch.from_numpy(w), torch.from_numpy(b), stride=2, padding=1)
+        ref = F.leaky_relu(ref, 0.2)[0].permute(1, 2, 0).numpy()
+        assert np.abs(got - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), (tr, hin, win, ci, co)
+
+
 @pytest.mark.gpu
-def test_unet_tensor_core_tail_vs_golden():
-    """PoseFeatureEncoderTC: cuDNN head + the three final 3x3 convolution stages on the library's tcgen05 kernel, against the reference's
+@pytest.mark.parametrize('head', ['library', 'cudnn'])
+def test_unet_tensor_core_tail_vs_golden(head):
+    """PoseFeatureEncoderTC -- head='library': the whole UNet on kernels of this library (split-K fp32 gather-GEMMs for the 4x4 stride-2 /
+    transposed convolutions, tcgen05 for the 3x3 stages); head='cudnn': cuDNN head + library tail -- against the reference's
     UnetNoCond7DS (golden) and the all-cuDNN restatement; deterministic; hands the (H,W,C) map to the field kernel unchanged."""
     from avatarcap_b200.engine import Engine
     g = load_golden('encoder_golden.npz')
@@ -137,7 +174,7 @@ def test_unet_tensor_core_tail_vs_golden():
     if not eng.has_tensor_core_path:
         pytest.skip('needs sm_100')
     x = torch.from_numpy(synth.smpl_pos_map()).cuda()
-    tc = encoders.PoseFeatureEncoderTC(synth.unet_state_dict(), engine=eng, deterministic=True)
+    tc = encoders.PoseFeatureEncoderTC(synth.unet_state_dict(), engine=eng, deterministic=True, head=head)
     out = tc(x).clone()
     assert tuple(out.shape) == (1, 64, 256, 256) and out.is_contiguous(memory_format=torch.channels_last)
     assert _report('unet tcgen05 tail', _sampled(out, g['pose_idx']), g['pose_feat']) < 1e-5
@@ -146,7 +183,7 @@ def test_unet_tensor_core_tail_vs_golden():
     assert float((out - ref).abs().max()) < 1e-5
     other = tc(x * 0.5 + 0.1).clone(); assert float((other - out).abs().max()) > 1e-3
     again = tc(x); print('replay difference', float((again - out).abs().max())); assert torch.equal(again, out)
-    eager = encoders.PoseFeatureEncoderTC(synth.unet_state_dict(), engine=eng, use_graph=False, deterministic=True)
+    eager = encoders.PoseFeatureEncoderTC(synth.unet_state_dict(), engine=eng, use_graph=False, deterministic=True, head=head)
     assert torch.equal(eager(x), out); eager.close()                    # graph replay == eager launches
     eng.load_avatar(synth.avatar_state_dict())
     frame = synth.make_frame(synth.SynthBody(), None)
