@@ -514,12 +514,22 @@ __global__ void __launch_bounds__(256) conv4_gemm_kernel(const Conv4Args a) {
   }
 }
 
-// dst[m, c_off + n] = act(sum_s part[s][m][n] + bias[n]), slices added in order; act = LeakyReLU(0.2) when `leaky`
+// dst[m, c_off + n] = act(sum_s part[s][m][n] + bias[n]); act = LeakyReLU(0.2) when `leaky`. A group of L lanes (a power of two <= 32) owns
+// one float4 of the output: lane j adds slices j, j + L, ... in order, the group folds by xor shuffles -- a fixed order, so deterministic.
 __global__ void __launch_bounds__(256) conv4_reduce_kernel(const float4* __restrict__ part, int S, int64_t mn4, int Co, const float* __restrict__ bias, int leaky,
-                                                           float* __restrict__ dst, int ld, int c_off) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < mn4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = part[i];
-    for (int s = 1; s < S; ++s) { const float4 p = part[(int64_t)s * mn4 + i]; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+                                                           float* __restrict__ dst, int ld, int c_off, int L) {
+  const int lane = threadIdx.x & (L - 1), gpb = 256 / L;
+  for (int64_t base = (int64_t)blockIdx.x * gpb; base < mn4; base += (int64_t)gridDim.x * gpb) {      // uniform per block: every lane reaches the shuffles
+    const int64_t i = base + threadIdx.x / L;
+    const bool ok = i < mn4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok)
+      for (int s = lane; s < S; s += L) { const float4 p = part[(int64_t)s * mn4 + i]; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    for (int o = L >> 1; o > 0; o >>= 1) {
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    }
+    if (!ok || lane) continue;
     const int64_t e = i * 4; const int n = (int)(e % Co); const int64_t m = e / Co;
     if (bias) { v.x += bias[n]; v.y += bias[n + 1]; v.z += bias[n + 2]; v.w += bias[n + 3]; }
     if (leaky) { v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y; v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w; }
@@ -715,7 +725,10 @@ extern "C" int avc_encoder_create(avc_ctx* ctx, const int32_t* program, int64_t 
         a.Hin = Hin; a.Win = Win; a.Ci = Ci; a.Co = Co; a.K = (int)K; a.wq = tr ? Win : Wo; a.Mcls = tr ? Hin * Win : Ho * Wo; a.Mtot = Ho * Wo; a.Wout = Wo;
         a.transposed = tr; a.in_relu = (flags >> 1) & 1;
         const int tiles = ((Co + C4_BN - 1) / C4_BN) * ((a.Mcls + C4_BM - 1) / C4_BM) * (tr ? 4 : 1);
-        int S = (4 * ctx->sm_count + tiles - 1) / tiles;          // 4 resident blocks per SM (64 registers x 256 threads) if (S > (int)(K / 64)) S = (int)(K / 64); if (S < 1) S = 1;
+        // K slices: one wave of 4 resident blocks per SM (64 registers x 256 threads), at least 64 k per slice
+        int S = (4 * ctx->sm_count) / tiles;
+        if (S > (int)(K / 64)) S = (int)(K / 64);
+        if (S < 1) S = 1;
         a.kc = (int)(((K + S - 1) / S + C4_BK - 1) / C4_BK) * C4_BK;
         S = (int)((K + a.kc - 1) / a.kc);
         c.S = S; c.grid = dim3((Co + C4_BN - 1) / C4_BN, S, ((a.Mcls + C4_BM - 1) / C4_BM) * (tr ? 4 : 1));
@@ -839,8 +852,9 @@ static int enc_enqueue(avc_encoder* e, const float* in, float* outp, cudaStream_
         if (op[1] < 0) a.src = in;
         conv4_gemm_kernel<<<c.grid, 256, 0, st>>>(a);
         const int64_t mn4 = (int64_t)a.Mtot * a.Co / 4;
-        conv4_reduce_kernel<<<blocks_for(mn4), 256, 0, st>>>(reinterpret_cast<const float4*>(a.part), c.S, mn4, a.Co, op[12] >= 0 ? e->d_params + op[12] : nullptr,
-                                                            (op[13] >> 2) & 1, e->f32_bufs[op[2]], op[9], op[10]);
+        int L = 1; while (L < c.S && L < 32) L <<= 1;
+        conv4_reduce_kernel<<<blocks_for(mn4 * L), 256, 0, st>>>(reinterpret_cast<const float4*>(a.part), c.S, mn4, a.Co, op[12] >= 0 ? e->d_params + op[12] : nullptr,
+                                                                (op[13] >> 2) & 1, e->f32_bufs[op[2]], op[9], op[10], L);
         nl += 2; break;
       }
       default: return avc_fail(ctx, AVC_EFORMAT, "encoder program: unknown op %d", op[0]);
