@@ -108,9 +108,11 @@ int avc_set_feature_map_hwc(avc_ctx* ctx, int which, const float* hwc /*[dev]*/,
  * up-sampling) plus a weight blob (fp16 hi / lo planes, (C_out, taps, C_in) each) and a parameter blob (f32). The library owns copies.
  * avc_encoder_run: in [dev] (C,H,W) f32 as the reference feeds it, out [dev] (H/2, W/2, 32) f32 = the (H,W,C) order
  * avc_set_feature_map_hwc takes; use_graph != 0 replays the program from a CUDA graph captured on first use.
- * The same interpreter runs the last three stages of GeoTexAvatar's UNet (network/unets.py:191-193, 217-219 upconvC5/C6/C7 = bilinear x2 + 3x3
- * convolution with the eval BatchNorm folded + ReLU; build_unet_tail_program): for such a program `in` is a flat f32 vector of (H,W,C)
- * tensors (the stride-2 head's outputs) which INPUT ops slice into buffers, UPSPLIT up-samples + splits, COPY places the skips.       */
+ * The same interpreter runs GeoTexAvatar's UNet (WarpingField.precompute_conv, arch_avatar.py:109-111 = UnetNoCond7DS.forward,
+ * network/unets.py:201-219; build_unet_program): conv1..7 and upconv1, 2, 3, 3 (4x4 stride-2 / transposed convolutions, eval BatchNorm
+ * folded, in-place LeakyReLU) as split-K fp32 gather-GEMMs (CONV4) that write each skip into its slice of the concatenated buffer, then
+ * upconvC5/C6/C7 (bilinear x2 + fp16 split = UPSPLIT, tcgen05 3x3 CONV, skip COPY): in [dev] (6,H,W) f32, out [dev] (H,W,64) f32.
+ * A program may instead take a flat f32 vector of (H,W,C) tensors that INPUT ops slice into buffers (build_unet_tail_program).       */
 typedef struct avc_encoder avc_encoder;
 int  avc_encoder_create(avc_ctx* ctx, const int32_t* program /*[host]*/, int64_t n_words, const void* weights_f16 /*[host]*/, size_t weight_bytes,
                         const float* params_f32 /*[host]*/, int64_t n_params, avc_encoder** out);
