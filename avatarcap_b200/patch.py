@@ -252,7 +252,7 @@ def install(engine: Optional[Engine] = None, impl: Optional[str] = None, modules
             x = batch['smpl_pos_map']
             e = _engine()
             if e.has_tensor_core_path and x.shape[0] == 1 and x.shape[2] % 128 == 0 and x.shape[3] % 128 == 0:
-                # cuDNN head + the three final 3x3 stages (3/4 of the FLOPs) on the library's tcgen05 convolutions
+                # the UNet as one program of library kernels (split-K fp32 gather-GEMMs + tcgen05 3x3 convolutions), encoders.build_unet_program
                 hw = (int(x.shape[2]), int(x.shape[3]))
                 cls = lambda sd, device: enc_mod.PoseFeatureEncoderTC(sd, engine=e, in_hw=hw)      # noqa: E731
                 self.pose_feat_map = _encoder('unettc%dx%d' % hw, self.unet, cls)(x).clone(memory_format=torch.preserve_format)

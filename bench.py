@@ -510,7 +510,7 @@ def run_ours(args):
             ietc = encoders.ImageFeatureEncoderTC(synth.hgfilter_state_dict(), engine=eng)
             enc_ms['encoder_hgfilter_tc_ms'], _ = timed(lambda: ietc(nin))
             ietc.close()
-            petc = encoders.PoseFeatureEncoderTC(synth.unet_state_dict(), engine=eng)         # UNet: cuDNN head + tcgen05 tail
+            petc = encoders.PoseFeatureEncoderTC(synth.unet_state_dict(), engine=eng)         # UNet as one library program (gather-GEMMs + tcgen05 tail)
             enc_ms['encoder_unet_tc_ms'], _ = timed(lambda: petc(xin))
             petc.close()
         except Exception as ex:
