@@ -140,6 +140,19 @@ def test_unet_whole_program_interpreted_on_the_cpu_vs_golden():
     assert _report('unet program on the CPU interpreter', out.reshape(-1, 64)[g['pose_idx']].T, g['pose_feat']) < 5e-6
 
 
+def test_unet_program_on_a_non_square_input():
+    """The same program builder at 128 x 256 (conv7 ends on a 1 x 2 map, the first transposed convolution starts from it): interpreter vs the
+    functional restatement, which test_encoders pins against the reference at 256 x 256."""
+    import encoder_program_interp as interp
+    sd = synth.unet_state_dict()
+    x = np.random.RandomState(3).randn(1, 6, 128, 256).astype(np.float32)
+    prog, wbytes, params = encoders.build_unet_program(sd, in_hw=(128, 256))
+    out = interp.run_program(prog, wbytes, params, x[0])
+    ref = encoders.PoseFeatureEncoder(sd, device='cpu', use_graph=False)(torch.from_numpy(x))[0].permute(1, 2, 0).numpy()
+    assert out.shape == ref.shape == (128, 256, 64)
+    assert _report('unet program at 128 x 256', out, ref) < 2e-6 * float(np.abs(ref).max())          # f32 rounding, relative to the +-10 range
+
+
 def test_conv4_weight_packing_matches_torch():
     """pack_conv4_weight + the interpreter's gather-GEMM == F.conv2d / F.conv_transpose2d (4x4, stride 2, padding 1) on odd shapes: non-square
     maps, a 1-pixel-high input of the transposed convolution, channel slices of wider buffers, ReLU in / LeakyReLU out."""
